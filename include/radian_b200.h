@@ -1,0 +1,141 @@
+/*
+ * radian_b200 -- C ABI of the B200-native RADIAN decode hot path.
+ *
+ * The reference (comprna/radian) has no FFI layer: its hot path is two in-process Python
+ * functions.  These entry points are what a binding for that path calls instead:
+ *
+ *   radian_decode_batch_*    replaces  decode.beam_search            radian/decode.py:100-212
+ *                            (call sites radian/basecall.py:102-109 global, :113-120 chunk)
+ *   radian_assemble_batch_*  replaces  matrix_assembly.assemble_matrices
+ *                                                                    radian/matrix_assembly.py:6-53
+ *                            (call site radian/basecall.py:100)
+ *   radian_table_*           replaces  the dict built from the RNA model JSON
+ *                                                                    radian/basecall.py:47-57
+ *                            and the entropy memo `entr_cache`       radian/decode.py:86-90
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative RADIAN_E_* code otherwise;
+ *     radian_last_error() gives a thread-local message for the last failure.
+ *   - symbols: A,C,G,T = 0..3, CTC blank = column 4 of every posterior row (decode.py:124).
+ *   - sequences are returned in decode order (3'->5'); the caller reverses them, exactly as
+ *     basecall.py:129 does.
+ *   - "_dev" functions take device pointers and enqueue work on `stream` without
+ *     synchronising; "_host" functions take host pointers, copy in, run, copy out and
+ *     synchronise before returning.
+ *   - the library never falls back to a CPU implementation: without a CUDA device every
+ *     compute entry point fails with RADIAN_E_CUDA.
+ */
+#ifndef RADIAN_B200_H
+#define RADIAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RADIAN_OK 0
+#define RADIAN_E_ARG (-1)      /* bad argument (ValueError in the Python layer) */
+#define RADIAN_E_CUDA (-2)     /* CUDA runtime failure or no device */
+#define RADIAN_E_CONTEXT (-3)  /* len_context does not match the table (KeyError, decode.py:83) */
+#define RADIAN_E_READ (-4)     /* at least one read failed; see out_status */
+#define RADIAN_E_GAP (-5)      /* a chunk starts past the rows assembled so far (IndexError,
+                                  matrix_assembly.py:27) */
+
+/* per-read status written to out_status */
+#define RADIAN_READ_OK 0
+#define RADIAN_READ_SEQ_OVERFLOW 1   /* decoded sequence longer than the caller's slot */
+#define RADIAN_READ_TRIE_OVERFLOW 2  /* back-pointer arena too small even after compaction */
+
+#define RADIAN_MAX_BEAM_WIDTH 32
+#define RADIAN_MAX_CONTEXT 13
+
+typedef struct radian_table radian_table_t;
+typedef void *radian_stream_t; /* cudaStream_t */
+
+const char *radian_last_error(void);
+const char *radian_version(void);
+int radian_device_count(void);
+
+/*
+ * Dense RNA k-mer table.  probs: host array of 4^L rows x 4 float64 linear probabilities,
+ * row index = big-endian base-4 value of the L context symbols, oldest symbol most
+ * significant (the key order of basecall.py:54-57).  The row entropies of decode.py:86-90
+ * are computed once here, on the host, in float64 with libm's log in the reference's
+ * operation order, and uploaded with the rows; the table stays resident in HBM.
+ */
+int radian_table_create(const double *probs, int L, int device, radian_table_t **out);
+int radian_table_destroy(radian_table_t *t);
+int radian_table_context_len(const radian_table_t *t);
+/* copies the 4^L float64 row entropies back to the host (tests) */
+int radian_table_entropies(const radian_table_t *t, double *out_host);
+
+/*
+ * CTC prefix beam search with optional gated RNA-model fusion over a batch of reads.
+ *
+ *  post          concatenated posterior rows, 5 per frame, float32 (post_is_f64 == 0) or
+ *                float64; read r owns rows [frame_offsets[r], frame_offsets[r+1]).
+ *  order         optional permutation of 0..n_reads-1: the order in which reads are handed to
+ *                the device work queue (longest first balances the tail); NULL = 0,1,2,...
+ *  beam_width    1..RADIAN_MAX_BEAM_WIDTH (decode.py:145).
+ *  table         NULL = RNA model off (lm falsy, decode.py:157,180).  When given, len_context
+ *                must equal radian_table_context_len(table).
+ *  s_threshold, r_threshold   decode.py:93, both comparisons strict.
+ *  out_seq       symbols of the best labeling of read r at out_seq[seq_offsets[r] ...];
+ *                slot size seq_offsets[r+1]-seq_offsets[r] (T_r is always enough).
+ *  out_len       decoded length per read.
+ *  out_score     2 per read: natural-log pr_total of the best and of the second-best final
+ *                beam (-inf when it has probability 0, NaN when there is no second beam).
+ *  out_status    RADIAN_READ_* per read.
+ *  out_counters  optional, 2 per read: number of lm[context] reads the reference would have
+ *                done (decode.py:83) and number of combine_dists calls (decode.py:94).
+ */
+size_t radian_decode_workspace_bytes(int device, int beam_width, int64_t max_frames);
+
+int radian_decode_batch_dev(const void *post, int post_is_f64, const int64_t *frame_offsets,
+                            int n_reads, const int32_t *order, int64_t max_frames, int beam_width,
+                            const radian_table_t *table, int len_context, double s_threshold,
+                            double r_threshold, uint8_t *out_seq, const int64_t *seq_offsets,
+                            int64_t *out_len, double *out_score, int32_t *out_status,
+                            uint64_t *out_counters, void *workspace, size_t workspace_bytes,
+                            radian_stream_t stream);
+
+int radian_decode_batch_host(const void *post, int post_is_f64, const int64_t *frame_offsets,
+                             int n_reads, int beam_width, const radian_table_t *table,
+                             int len_context, double s_threshold, double r_threshold,
+                             uint8_t *out_seq, const int64_t *seq_offsets, int64_t *out_len,
+                             double *out_score, int32_t *out_status, uint64_t *out_counters,
+                             int device);
+
+/*
+ * Merge of overlapping chunk posteriors for a batch of reads (matrix_assembly.py:6-53,
+ * including its first-chunk-wins behaviour: np.add's result is discarded at :52).
+ *
+ *  chunks             all chunk rows of all reads back to back, 5 float32 per row.
+ *  chunk_row_offsets  n_chunks+1 row offsets into `chunks`.
+ *  read_chunk_ranges  n_reads+1 chunk indices: read r owns chunks
+ *                     [read_chunk_ranges[r], read_chunk_ranges[r+1]), the k-th of them starts at
+ *                     global row k*step of the read (create_vstack, :12-34).
+ *  out_row_offsets    n_reads+1 row offsets into `out` (row counts from radian_assemble_plan).
+ *  out_is_f64         per batch: 1 writes float64 rows (rows covered by more than one chunk are
+ *                     L1-normalised in float64, others are exact casts), 0 writes float32
+ *                     (only valid when no row of the batch is covered twice).
+ */
+int radian_assemble_plan(const int64_t *chunk_row_offsets, const int64_t *read_chunk_ranges,
+                         int n_reads, int step, int64_t *out_rows_per_read, int *out_any_overlap,
+                         int32_t *out_max_chunk_rows);
+
+int radian_assemble_batch_dev(const float *chunks, const int64_t *chunk_row_offsets,
+                              const int64_t *read_chunk_ranges, const int64_t *out_row_offsets,
+                              int n_reads, int step, int32_t max_chunk_rows, void *out,
+                              int out_is_f64, radian_stream_t stream);
+
+int radian_assemble_batch_host(const float *chunks, const int64_t *chunk_row_offsets,
+                               const int64_t *read_chunk_ranges, const int64_t *out_row_offsets,
+                               int n_reads, int step, void *out, int out_is_f64, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADIAN_B200_H */

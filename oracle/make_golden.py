@@ -1,0 +1,250 @@
+"""TEST INFRASTRUCTURE -- generate tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden [--long]
+
+Every fixture stores the exact inputs handed to the reference's own
+``decode.beam_search`` / ``matrix_assembly.assemble_matrices`` and what they returned
+(plus the final candidates' pr_total values captured by wrapping
+``BeamList.sort_labelings``, see ref_loader.beam_search_with_scores).  Large RNA tables
+are stored as (L, seed) of radian_b200.synth.make_table, which is bit-reproducible.
+Environment of the recorded run: CPython 3.12, numpy 2.3.5, scikit-learn 1.9.0
+(the reference pins numpy~=1.19.5 / scikit-learn~=1.1.2, requirements.txt:5,9).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+from multiprocessing import Pool
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+from radian_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SYM = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+
+def seq_to_u8(s):
+    return np.array([SYM[c] for c in s], dtype=np.uint8)
+
+
+def random_posteriors(rng, T, peaky, zero_frac, dtype):
+    """Small random softmax matrices with optional exact zeros (not renormalised)."""
+    logits = rng.normal(0, 1, size=(T, 5))
+    logits[:, 4] += rng.choice([0.0, 2.0, 6.0])
+    if peaky:
+        k = rng.integers(0, 4, size=T)
+        m = rng.random(T) < 0.3
+        logits[np.arange(T)[m], k[m]] += rng.choice([4.0, 8.0, 12.0])
+    p = np.exp(logits - logits.max(1, keepdims=True))
+    p = (p / p.sum(1, keepdims=True)).astype(np.float32)
+    if zero_frac:
+        z = rng.random((T, 5)) < zero_frac
+        p[z] = 0.0
+    return p.astype(dtype)
+
+
+_TABLES = {}
+
+
+def run_case(args):
+    mat, bw, L, tseed, s_thr, r_thr = args
+    dec, _, _ = ref_loader.load()
+    lm = None
+    if L:
+        if (L, tseed) not in _TABLES:
+            _TABLES.clear()
+            _TABLES[(L, tseed)] = synth.make_table(L, tseed)
+        lm = ref_loader.DenseLM(_TABLES[(L, tseed)])
+    t0 = time.time()
+    seq, scores, ncomb = ref_loader.beam_search_with_scores(dec, mat, bw, lm, s_thr, r_thr, L, topk=8)
+    nl = lm.n_lookup if lm is not None else 0
+    return seq, scores, nl, ncomb, time.time() - t0
+
+
+def pack_cases(cases, results):
+    """Flatten variable-length cases into arrays for one npz."""
+    out = {}
+    mats32 = [c[0] for c in cases if c[0].dtype == np.float32]
+    mats64 = [c[0] for c in cases if c[0].dtype == np.float64]
+    out["post32"] = np.concatenate(mats32) if mats32 else np.zeros((0, 5), np.float32)
+    out["post64"] = np.concatenate(mats64) if mats64 else np.zeros((0, 5), np.float64)
+    meta = []
+    o32 = o64 = 0
+    seqs = []
+    scores = np.full((len(cases), 8), np.nan)
+    for i, (c, r) in enumerate(zip(cases, results)):
+        mat, bw, L, tseed, s_thr, r_thr = c
+        T = mat.shape[0]
+        is64 = int(mat.dtype == np.float64)
+        off = o64 if is64 else o32
+        if is64:
+            o64 += T
+        else:
+            o32 += T
+        seq, sc, nl, ncomb, _ = r
+        seqs.append(seq_to_u8(seq))
+        scores[i, :len(sc)] = sc
+        meta.append([is64, off, T, bw, L, tseed, len(seq), nl, ncomb])
+    out["meta"] = np.array(meta, dtype=np.int64)
+    out["thr"] = np.array([[c[4] if c[4] is not None else np.nan,
+                            c[5] if c[5] is not None else np.nan] for c in cases])
+    out["seq"] = np.concatenate(seqs) if seqs else np.zeros(0, np.uint8)
+    out["scores"] = scores
+    return out
+
+
+def gen_decode_random(n_cases, seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for i in range(n_cases):
+        T = int(rng.integers(1, 400))
+        bw = int(rng.choice([1, 2, 3, 6, 16, 32, 64]))
+        lm_on = rng.random() < 0.7
+        L = int(rng.integers(1, 7)) if lm_on else 0
+        dtype = np.float64 if rng.random() < 0.6 else np.float32
+        peaky = rng.random() < 0.7
+        zf = float(rng.choice([0.0, 0.0, 0.01, 0.2]))
+        mat = random_posteriors(rng, T, peaky, zf, dtype)
+        if lm_on:
+            s_thr = float(rng.choice([0.0, 0.5, 0.5, 1.0, np.log(4.0), 0.3]))
+            r_thr = float(rng.choice([0.0, 0.5, 0.5, 1.0, np.log(4.0), 0.9]))
+        else:
+            s_thr = r_thr = None
+        cases.append((mat, bw, L, int(rng.integers(0, 1 << 30)) if lm_on else 0, s_thr, r_thr))
+    return cases
+
+
+def gen_decode_kat():
+    """Known-answer micro-cases from SURVEY.md section 4."""
+    cases = []
+    blank = np.zeros((7, 5), np.float32)
+    blank[:, 4] = 1.0
+    cases.append((blank, 6, 0, 0, None, None))                       # all blank -> ''
+    two = np.zeros((6, 5), np.float32)
+    two[:, 1] = 0.5
+    two[:, 4] = 0.5
+    cases.append((two, 4, 0, 0, None, None))                         # exact zeros, -inf beams kept
+    cases.append((np.full((3, 5), 0.2, np.float32), 3, 0, 0, None, None))   # stable tie-break -> 'A'
+    cases.append((np.full((9, 5), 0.2, np.float64), 6, 2, 7, 0.5, 0.5))     # ties with the LM on
+    cases.append((np.full((5, 5), 0.2, np.float32), 16, 0, 0, None, None))
+    z = np.zeros((4, 5), np.float32)                                  # all-zero rows
+    cases.append((z, 3, 0, 0, None, None))
+    one = np.zeros((1, 5), np.float32)
+    one[0] = [0.7, 0.1, 0.1, 0.05, 0.05]
+    cases.append((one, 1, 0, 0, None, None))                          # T=1, bw=1
+    rep = np.zeros((8, 5), np.float64)                                # repeats need a blank between
+    rep[:, 0] = [0.9, 0.05, 0.9, 0.9, 0.05, 0.9, 0.05, 0.05]
+    rep[:, 4] = 1 - rep[:, 0]
+    cases.append((rep, 6, 1, 3, 0.0, 2.0))
+    return cases
+
+
+def gen_decode_real_shape(quick):
+    """Reads drawn from the bench generator (synth.make_reads), default flags of the reference."""
+    import torch  # noqa: F401
+
+    cases = []
+    nb = np.array([60, 35, 90, 120] if quick else [60, 35, 90, 120, 150, 100])
+    post, off = synth.make_reads(nb, seed=11)
+    post = post.numpy()
+    off = off.numpy()
+    for i in range(len(nb)):
+        m32 = post[off[i]:off[i + 1]]
+        # config 2: pure CTC, bw=6, float32 (chunk-mode call, basecall.py:113-120)
+        cases.append((m32.copy(), 6, 0, 0, None, None))
+        # config 3: LM global decode, bw=16, L in {6, 11}, thresholds 0.5/0.5, float64 matrix
+        m64 = m32.astype(np.float64)
+        m64 = m64 / np.abs(m64).sum(1, keepdims=True)
+        cases.append((m64, 16, 6 if i % 2 else 11, 5, 0.5, 0.5))
+    # config 1 shape: bw=6 (default), L=11, float64
+    cases.append((post[off[0]:off[1]].astype(np.float64), 6, 11, 5, 0.5, 0.5))
+    return cases
+
+
+def gen_assembly(n_cases, seed):
+    _, ma, _ = ref_loader.load()
+    rng = np.random.default_rng(seed)
+    recs = []
+    chunks_all, lens_all, outs32, outs64 = [], [], [], []
+    for i in range(n_cases):
+        W = int(rng.integers(1, 80))
+        S = int(rng.integers(1, W + 1))
+        if i % 4 == 0:      # the reference's own windowing (preprocess.py:4-22 + basecall.py:96)
+            T = int(rng.integers(1, 6 * W))
+            full = random_posteriors(rng, T, True, 0.02, np.float32)
+            if i % 8 == 0:
+                full[rng.integers(0, T)] = 0.0    # an all-zero row: norm 0 -> left unchanged
+            mats = synth.split_windows(full, W, S)
+        else:               # ragged chunk lengths (anything the reference accepts)
+            n = int(rng.integers(1, 7))
+            mats = []
+            end = 0
+            for k in range(n):
+                lo = max(0, k * S - end)  # must at least reach the current end (no gaps)
+                ln = int(rng.integers(lo, lo + W + 1)) if k * S <= end else 0
+                if k * S > end:
+                    ln = 0
+                mats.append(random_posteriors(rng, ln, True, 0.05, np.float32) if ln else
+                            np.zeros((0, 5), np.float32))
+                if ln:
+                    end = max(end, k * S + ln)
+            if not any(len(m) for m in mats):
+                mats[0] = random_posteriors(rng, 3, True, 0.0, np.float32)
+        ref = ma.assemble_matrices([m for m in mats], S)
+        ref = np.asarray(ref)
+        if ref.ndim == 1:
+            ref = ref.reshape(0, 5)
+        lens = [len(m) for m in mats]
+        recs.append([S, len(mats), sum(lens), ref.shape[0], int(ref.dtype == np.float64)])
+        lens_all.extend(lens)
+        chunks_all.extend([m for m in mats if len(m)])
+        (outs64 if ref.dtype == np.float64 else outs32).append(ref)
+    return {
+        "meta": np.array(recs, dtype=np.int64),
+        "chunk_lens": np.array(lens_all, dtype=np.int32),
+        "chunks": np.concatenate(chunks_all),
+        "out32": np.concatenate(outs32).astype(np.float32) if outs32 else np.zeros((0, 5), np.float32),
+        "out64": np.concatenate(outs64) if outs64 else np.zeros((0, 5), np.float64),
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--long", action="store_true", help="also the slow full-length reads")
+    ap.add_argument("--procs", type=int, default=os.cpu_count())
+    a = ap.parse_args()
+    os.makedirs(GOLDEN, exist_ok=True)
+
+    np.savez_compressed(os.path.join(GOLDEN, "assembly.npz"), **gen_assembly(120, 2024))
+    print("assembly.npz written")
+
+    sets = {
+        "decode_kat": gen_decode_kat(),
+        "decode_random": gen_decode_random(240, 77),
+        "decode_synth": gen_decode_real_shape(quick=not a.long),
+    }
+    if a.long:
+        post, off = synth.make_reads(np.array([1500]), seed=12)
+        m32 = post.numpy()
+        m64 = m32.astype(np.float64)
+        m64 = m64 / np.abs(m64).sum(1, keepdims=True)
+        sets["decode_long"] = [(m32, 6, 0, 0, None, None), (m64, 16, 11, 5, 0.5, 0.5)]
+    with Pool(a.procs) as pool:
+        for name, cases in sets.items():
+            t0 = time.time()
+            res = pool.map(run_case, cases, chunksize=1)
+            np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), **pack_cases(cases, res))
+            print(f"{name}.npz: {len(cases)} cases, {time.time() - t0:.1f}s wall, "
+                  f"ref cpu {sum(r[4] for r in res):.1f}s")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,50 @@
+"""Pins oracle/radian_oracle.c against outputs of the unmodified reference (tests/golden)."""
+import numpy as np
+import pytest
+
+import golden_io
+from oracle import oracle
+
+FILES = ["decode_kat.npz", "decode_random.npz", "decode_synth.npz", "decode_long.npz"]
+CASES = [c for f in FILES for c in golden_io.decode_cases(f)]
+
+
+def check_scores(got, want, rel=1e-12):
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        if np.isinf(w):
+            assert g == w
+        else:
+            assert abs(g - w) <= rel * max(1.0, abs(w)), (g, w)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_decode_matches_reference(case):
+    tab = golden_io.table(case.L, case.tseed) if case.L else None
+    seq, scores, nfin, (nl, nc) = oracle.beam_search(case.mat, case.bw, tab, case.L, case.s_thr,
+                                                     case.r_thr, topk=8)
+    assert seq.tolist() == case.seq.tolist()
+    check_scores(scores, case.scores)
+    assert nl == case.n_lookup
+    assert nc == case.n_combine
+
+
+def test_assembly_matches_reference():
+    cases = golden_io.assembly_cases()
+    assert len(cases) >= 100
+    n64 = 0
+    for S, mats, ref in cases:
+        got = oracle.assemble(mats, S)
+        assert got.dtype == ref.dtype
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref)
+        n64 += ref.dtype == np.float64
+    assert n64 > 10
+
+
+def test_kat_answers():
+    """SURVEY.md section 4 known answers, as literal strings."""
+    kat = golden_io.decode_cases("decode_kat.npz")
+    assert kat[0].seq.tolist() == []              # all blank -> ''
+    assert kat[1].seq.tolist() == [1, 1]          # 'CC'
+    assert kat[2].seq.tolist() == [0]             # uniform, bw=3, T=3 -> 'A'
