@@ -91,15 +91,22 @@ int radian_table_entropies(const radian_table_t *t, double *out_host);
  *  out_counters  optional, 2 per read: number of lm[context] reads the reference would have
  *                done (decode.py:83) and number of combine_dists calls (decode.py:94).
  */
-size_t radian_decode_workspace_bytes(int device, int beam_width, int64_t max_frames);
+/*
+ *  arena_nodes   capacity of the per-read back-pointer arena; 0 picks a default from max_frames
+ *                (exact worst case for small problems, else beam lanes x max_frames/8).  A read
+ *                that needs more gets RADIAN_READ_TRIE_OVERFLOW; lanes x (T+1) always suffices.
+ *                The _host entry point retries such reads by itself.
+ */
+size_t radian_decode_workspace_bytes(int device, int beam_width, int64_t max_frames,
+                                     int64_t arena_nodes);
 
 int radian_decode_batch_dev(const void *post, int post_is_f64, const int64_t *frame_offsets,
                             int n_reads, const int32_t *order, int64_t max_frames, int beam_width,
                             const radian_table_t *table, int len_context, double s_threshold,
                             double r_threshold, uint8_t *out_seq, const int64_t *seq_offsets,
                             int64_t *out_len, double *out_score, int32_t *out_status,
-                            uint64_t *out_counters, void *workspace, size_t workspace_bytes,
-                            radian_stream_t stream);
+                            uint64_t *out_counters, int64_t arena_nodes, void *workspace,
+                            size_t workspace_bytes, radian_stream_t stream);
 
 int radian_decode_batch_host(const void *post, int post_is_f64, const int64_t *frame_offsets,
                              int n_reads, int beam_width, const radian_table_t *table,
@@ -128,8 +135,9 @@ int radian_assemble_plan(const int64_t *chunk_row_offsets, const int64_t *read_c
 
 int radian_assemble_batch_dev(const float *chunks, const int64_t *chunk_row_offsets,
                               const int64_t *read_chunk_ranges, const int64_t *out_row_offsets,
-                              int n_reads, int step, int32_t max_chunk_rows, void *out,
-                              int out_is_f64, radian_stream_t stream);
+                              int n_reads, int step, int32_t max_chunk_rows,
+                              int64_t total_out_rows, void *out, int out_is_f64,
+                              radian_stream_t stream);
 
 int radian_assemble_batch_host(const float *chunks, const int64_t *chunk_row_offsets,
                                const int64_t *read_chunk_ranges, const int64_t *out_row_offsets,

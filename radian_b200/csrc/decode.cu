@@ -1,0 +1,614 @@
+// CTC prefix beam search with gated RNA-model fusion, sm_100a.
+//
+// What it computes is radian/decode.py:100-212 of the reference (beam_search), per read:
+//   frame loop 141-204, COPY 150-175, EXTEND 177-201, apply_rna_model 79-96,
+//   combine_dists 52-64, frame entropy 135-138 (+67-76), final pick 207-210.
+// How it computes it is new:
+//   * one group of G lanes (8/16/32) owns a read; lane == beam, all per-beam state in registers;
+//     a warp carries 32/G reads; a persistent grid pulls reads from an atomic queue.
+//   * scores are kept in the LINEAR domain as float64, rescaled every frame by an exact power
+//     of two (exponent accumulated in an integer).  logaddexp becomes '+', '+ log p' becomes
+//     '* p', and combine_dists is already linear, so the frame loop has no transcendental at
+//     all; ordering by pr_total is unchanged because log is monotone.  One log per read at
+//     the end gives the reference's log score.
+//   * the T x 5 posterior rows are streamed through shared memory in tiles of G frames: each
+//     lane loads one frame (prefetched one tile ahead), does the per-frame work that does not
+//     depend on the beams (float64 conversion, base-sum, p/S, entropy gate) once, and the G
+//     lanes then consume the records by broadcast reads.
+//   * a labeling is identified by a 64-bit rolling hash + length (the reference's dict key is
+//     the tuple itself); the only collision the algorithm can produce is copy(X) with
+//     extend(parent(X), last(X)), found through a parent-lane pointer kept per beam.
+//   * stable top-k: rank = #candidates with (score desc, dict insertion position asc) before
+//     it, counted exactly on the float64 bit patterns; candidates that cannot reach the
+//     beam (below the worst copy) are pruned first.
+//   * labelings live in a per-group back-pointer arena (parent<<2|symbol).  The live beams of a
+//     read are combinations of its few most ambiguous positions, so their common ancestor stays
+//     near the start of the read: nothing can be flushed early.  The arena is generational
+//     instead: new nodes go to a small nursery; when it fills, the nodes still reachable from a
+//     live beam are slid down onto the old generation (never revisited) and the rest is dropped.
+//     Every lineage promotes each of its symbols once, so the old generation is bounded by
+//     beam_width x decoded length.  The best labeling is read back by one walk at the end.
+#include <math.h>
+
+#include "internal.h"
+
+namespace radian {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint16_t kPosInvalid = 0xffff;
+constexpr int kNursery = 4096;  // arena nodes between two collections
+
+template <int G, bool LM>
+struct __align__(16) GroupSmem {
+    static constexpr int REC = LM ? 12 : 6;  // doubles per frame: P0..P4, gate, q0..q3, S, pad
+    double rec[G * REC];
+    double ex[G * 4];                 // extension scores of every lane, for the copy/extend merge
+    unsigned long long key[5 * G];    // candidate list: [0,G) copies by lane, [G,..) extensions
+    uint32_t kill[G];                 // byte c of word l: extension (l,c) merged into a copy
+    uint16_t pos[5 * G];              // dict insertion position of the candidate
+    uint8_t src[5 * G];               // lane*4+c of an extension candidate
+    uint8_t rnk[5 * G];               // rank of the candidate
+    uint8_t newlist[G];               // candidate indices of the new beams, in list order
+    uint8_t lanerank[G];              // previous rank of every lane
+};
+
+__device__ __forceinline__ unsigned long long hash_step(unsigned long long h, int c)
+{
+    h = (h ^ (unsigned long long)(c + 1)) * 0x9E3779B97F4A7C15ull;
+    return h ^ (h >> 29);
+}
+
+template <typename PT>
+__device__ __forceinline__ void load_row(const PT *post, long long frame, PT (&v)[5])
+{
+    const PT *r = post + frame * 5;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v[i] = __ldg(r + i);
+}
+
+// Per-frame work shared by all beams of a read, done by the lane that loaded the frame.
+// Reference: decode.py:135-138 (s_entropies), 67-76 (normalise, entropy), 54-55 (base sum and
+// p/S of combine_dists).  float32 input follows the numpy>=2 promotion the pinned oracle uses.
+template <bool LM>
+__device__ __forceinline__ void make_record(const double (&v)[5], double s_thr, double *rec)
+{
+#pragma unroll
+    for (int i = 0; i < 5; ++i) rec[i] = v[i];
+    if (LM) {
+        double S = __dadd_rn(__dadd_rn(__dadd_rn(v[0], v[1]), v[2]), v[3]);
+        double H = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double q = (S == 0.0) ? v[i] : v[i] / S;
+            rec[6 + i] = q;
+            if (q > 0.0) H = __dadd_rn(H, __dmul_rn(q, log(q)));
+        }
+        rec[10] = S;
+        rec[5] = (-H > s_thr) ? 1.0 : 0.0;
+    }
+}
+
+template <bool LM>
+__device__ __forceinline__ void make_record(const float (&v)[5], double s_thr, double *rec)
+{
+#pragma unroll
+    for (int i = 0; i < 5; ++i) rec[i] = (double)v[i];
+    if (LM) {
+        float S = __fadd_rn(__fadd_rn(__fadd_rn(v[0], v[1]), v[2]), v[3]);
+        float H = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float q = (S == 0.0f) ? v[i] : __fdiv_rn(v[i], S);
+            rec[6 + i] = (double)q;
+            if (q > 0.0f) H = __fadd_rn(H, __fmul_rn(q, __double2float_rn(log((double)q))));
+        }
+        rec[10] = (double)S;
+        rec[5] = (-H > (float)s_thr) ? 1.0 : 0.0;
+    }
+}
+
+template <int G, bool LM, typename PT, bool COUNT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+decode_kernel(const DecodeArgs a)
+{
+    constexpr int GPW = 32 / G;  // groups (reads) per warp
+    constexpr int REC = GroupSmem<G, LM>::REC;
+    __shared__ GroupSmem<G, LM> smem[kWarpsPerBlock * GPW];
+
+    const int lane = threadIdx.x & 31;
+    const int li = lane % G;
+    const int gw = lane / G;
+    const unsigned gshift = gw * G;
+    const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << gshift);
+    const unsigned below = gmask & ((1u << lane) - 1u);
+    const int gib = (threadIdx.x >> 5) * GPW + gw;  // group in block
+    GroupSmem<G, LM> &sm = smem[gib];
+    const int slot = blockIdx.x * (kWarpsPerBlock * GPW) + gib;
+
+    const int bw = a.beam_width;
+    const int L = a.L;
+    const uint32_t ctx_mask = LM ? (uint32_t)((1ull << (2 * L)) - 1ull) : 0u;
+    const PT *post_all = (const PT *)a.post;
+    const int cap = a.arena_cap;
+    uint32_t *const arena = a.arena + (size_t)slot * (size_t)(cap + kNursery);
+    uint32_t *const fwd = arena + cap;
+
+    // ---- per-beam (lane) state
+    double ptot = 0.0, pnb = 0.0, pb = 0.0;
+    unsigned long long h = 0, hp = 0;
+    uint32_t ctx = 0;
+    int len = 0, node = 0, rank = 0, plane = -1, last = 0;
+    bool alive = false;
+    double rext0 = 0, rext1 = 0, rext2 = 0, rext3 = 0, rcopy = 0;
+    bool gext = false, gcopy = false;
+    // ---- per-read (group-uniform) state
+    int read = -1, top = 0, old_top = 0, na = 0, status = 0;
+    long long T = 0, t = 0, foff = 0, kacc = 0, seq_off = 0, seq_cap = 0;
+    unsigned long long n_lookup = 0, n_combine = 0;
+    PT pf[5];
+    bool active = true;
+
+    while (__any_sync(kFull, active)) {
+        if (!active) continue;
+
+        // ------------------------------------------------------------ fetch a read
+        if (read < 0) {
+            int idx = 0;
+            if (li == 0) idx = atomicAdd(a.queue, 1);
+            idx = __shfl_sync(gmask, idx, gshift);
+            if (idx >= a.n_reads) {
+                active = false;
+                continue;
+            }
+            read = a.order ? a.order[idx] : idx;
+            foff = a.frame_offsets[read];
+            T = a.frame_offsets[read + 1] - foff;
+            seq_off = a.seq_offsets[read];
+            seq_cap = a.seq_offsets[read + 1] - seq_off;
+            t = 0;
+            // initial beam: the empty labeling, pr_blank = pr_total = log 1 (decode.py:128-132)
+            alive = (li == 0);
+            ptot = alive ? 1.0 : 0.0;
+            pb = ptot;
+            pnb = 0.0;
+            h = 0x243F6A8885A308D3ull;
+            hp = 0;
+            ctx = 0;
+            len = 0;
+            node = 0;
+            rank = 0;
+            plane = -1;
+            last = 0;
+            gext = gcopy = false;
+            top = 1;  // node 0 = the empty labeling
+            old_top = 1;
+            na = 1;
+            status = 0;
+            kacc = 0;
+            n_lookup = n_combine = 0;
+            if (li < T) load_row(post_all + foff * 5, li, pf);
+        }
+
+        if (t < T) {
+            // -------------------------------------------------------- tile refill
+            if ((t % G) == 0) {
+                __syncwarp(gmask);
+                if (t + li < T) make_record<LM>(pf, a.s_thr, &sm.rec[li * REC]);
+                if (t + G + li < T) load_row(post_all + foff * 5, t + G + li, pf);
+                __syncwarp(gmask);
+            }
+
+            // -------------------------------------------------------- nursery collection
+            if (top + G > old_top + kNursery || top + G > cap) {
+                // 1. mark nursery nodes reachable from a live beam (stop at the old generation or
+                //    at a node somebody marked in an earlier step)
+                int cur = node;
+                bool walking = alive && cur >= old_top;
+                while (__any_sync(gmask, walking)) {
+                    if (walking) {
+                        const uint32_t w = arena[cur];
+                        if (w >> 31) {
+                            walking = false;
+                        } else {
+                            arena[cur] = w | 0x80000000u;
+                            cur = (int)(w >> 2);
+                            walking = cur >= old_top;
+                        }
+                    }
+                    __syncwarp(gmask);
+                }
+                // 2. slide marked nodes down in index order (parents always precede children);
+                //    fwd[] keeps the new index of every moved node for its children and the beams
+                int cnt = old_top;
+                for (int base = old_top; base < top; base += G) {
+                    const int i = base + li;
+                    const uint32_t w = (i < top) ? arena[i] : 0u;
+                    const bool mk = (w >> 31) != 0;
+                    const unsigned bal = __ballot_sync(gmask, mk);
+                    const int ni = cnt + __popc(bal & below);
+                    const int par = (int)((w & 0x7fffffffu) >> 2);
+                    int npar = par;
+                    if (mk && par >= old_top) {
+                        if (par >= base) {
+                            const unsigned pm = gmask & ((1u << (gshift + (par - base))) - 1u);
+                            npar = cnt + __popc(bal & pm);
+                        } else {
+                            npar = (int)fwd[par - old_top];
+                        }
+                    }
+                    __syncwarp(gmask);
+                    if (mk) {
+                        arena[ni] = ((uint32_t)npar << 2) | (w & 3u);
+                        fwd[i - old_top] = (uint32_t)ni;
+                    }
+                    cnt += __popc(bal);
+                    __syncwarp(gmask);
+                }
+                if (alive && node >= old_top) node = (int)fwd[node - old_top];
+                __syncwarp(gmask);
+                old_top = cnt;
+                top = cnt;
+                if (top + G > cap) status = RADIAN_READ_TRIE_OVERFLOW;
+            }
+
+            if (status == RADIAN_READ_TRIE_OVERFLOW) {
+                t = T;  // give up on this read; reported through out_status
+            } else {
+                // ---------------------------------------------------- one frame
+                const double *rec = &sm.rec[(int)(t % G) * REC];
+                const double P4 = rec[4];
+                const double2 P01 = *reinterpret_cast<const double2 *>(rec);
+                const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
+                bool fgate = false;
+                double2 q01 = make_double2(0, 0), q23 = make_double2(0, 0);
+                double S = 0.0;
+                if (LM) {
+                    fgate = rec[5] != 0.0;
+                    if (fgate) {
+                        q01 = *reinterpret_cast<const double2 *>(rec + 6);
+                        q23 = *reinterpret_cast<const double2 *>(rec + 8);
+                        S = rec[10];
+                    }
+                }
+                const bool has_last = alive && len > 0;
+                const bool lm_copy = LM && alive && len >= L + 1;  // decode.py:157
+                const bool lm_ext = LM && alive && len >= L;       // decode.py:180
+                if (COUNT && LM) {
+                    n_lookup += __popc(__ballot_sync(gmask, lm_copy)) + __popc(__ballot_sync(gmask, lm_ext));
+                    n_combine += __popc(__ballot_sync(gmask, lm_copy && gcopy && fgate)) +
+                                 __popc(__ballot_sync(gmask, lm_ext && gext && fgate));
+                }
+
+                // COPY (decode.py:150-175)
+                double dl_ = has_last ? rec[last] : 0.0;
+                if (LM && lm_copy && gcopy && fgate) {
+                    double ql = rec[6 + last];
+                    dl_ = __dmul_rn(__dmul_rn(__dadd_rn(rcopy, ql), 0.5), S);  // decode.py:58-61
+                }
+                double npnb = has_last ? __dmul_rn(pnb, dl_) : 0.0;
+                double npb = __dmul_rn(ptot, P4);
+                double nptot = __dadd_rn(npb, npnb);
+
+                // EXTEND (decode.py:177-201)
+                double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
+                if (LM && lm_ext && gext && fgate) {
+                    d0 = __dmul_rn(__dmul_rn(__dadd_rn(rext0, q01.x), 0.5), S);
+                    d1 = __dmul_rn(__dmul_rn(__dadd_rn(rext1, q01.y), 0.5), S);
+                    d2 = __dmul_rn(__dmul_rn(__dadd_rn(rext2, q23.x), 0.5), S);
+                    d3 = __dmul_rn(__dmul_rn(__dadd_rn(rext3, q23.y), 0.5), S);
+                }
+                double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+                if (alive) {
+                    e0 = __dmul_rn((has_last && last == 0) ? pb : ptot, d0);  // decode.py:192-195
+                    e1 = __dmul_rn((has_last && last == 1) ? pb : ptot, d1);
+                    e2 = __dmul_rn((has_last && last == 2) ? pb : ptot, d2);
+                    e3 = __dmul_rn((has_last && last == 3) ? pb : ptot, d3);
+                }
+
+                // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference
+                *reinterpret_cast<double2 *>(&sm.ex[li * 4]) = make_double2(e0, e1);
+                *reinterpret_cast<double2 *>(&sm.ex[li * 4 + 2]) = make_double2(e2, e3);
+                sm.kill[li] = 0u;
+                sm.lanerank[li] = (uint8_t)rank;
+                __syncwarp(gmask);
+                int pos_copy = 5 * rank;
+                if (alive && plane >= 0) {
+                    double v = sm.ex[plane * 4 + last];
+                    npnb = __dadd_rn(npnb, v);
+                    nptot = __dadd_rn(nptot, v);
+                    reinterpret_cast<uint8_t *>(sm.kill)[plane * 4 + last] = 1;
+                    int pp = 5 * (int)sm.lanerank[plane] + 1 + last;
+                    pos_copy = pp < pos_copy ? pp : pos_copy;
+                }
+                __syncwarp(gmask);
+                const uint32_t killw = sm.kill[li];
+
+                // SELECT the best beam_width candidates (decode.py:145, 35-39)
+                const unsigned long long kcopy = (unsigned long long)__double_as_longlong(nptot);
+                const bool prune = (na >= bw);
+                unsigned long long tau = alive ? kcopy : ~0ull;
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) {
+                    unsigned long long x = __shfl_xor_sync(gmask, tau, o);
+                    tau = x < tau ? x : tau;
+                }
+                int n_ext = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double ec = c == 0 ? e0 : c == 1 ? e1 : c == 2 ? e2 : e3;
+                    const unsigned long long kc = (unsigned long long)__double_as_longlong(ec);
+                    const bool comp = alive && !((killw >> (8 * c)) & 1u) && (!prune || kc >= tau);
+                    const unsigned bal = __ballot_sync(gmask, comp);
+                    if (comp) {
+                        int idx = G + n_ext + __popc(bal & below);
+                        sm.key[idx] = kc;
+                        sm.pos[idx] = (uint16_t)(5 * rank + 1 + c);
+                        sm.src[idx] = (uint8_t)(li * 4 + c);
+                    }
+                    n_ext += __popc(bal);
+                }
+                sm.key[li] = kcopy;
+                sm.pos[li] = alive ? (uint16_t)pos_copy : kPosInvalid;
+                __syncwarp(gmask);
+                const int m = G + n_ext;
+                for (int idx = li; idx < m; idx += G) {
+                    const uint16_t p = sm.pos[idx];
+                    if (p != kPosInvalid) {
+                        const unsigned long long k = sm.key[idx];
+                        int cnt = 0;
+                        for (int j = 0; j < m; ++j) {
+                            const uint16_t pj = sm.pos[j];
+                            const unsigned long long kj = sm.key[j];
+                            cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
+                        }
+                        sm.rnk[idx] = (uint8_t)(cnt > 255 ? 255 : cnt);
+                    }
+                }
+                __syncwarp(gmask);
+
+                const int new_rank = alive ? (int)sm.rnk[li] : 255;
+                const bool survive = alive && new_rank < bw;
+                const unsigned evmask = __ballot_sync(gmask, alive && !survive);
+                const unsigned survmask = __ballot_sync(gmask, survive);
+                const unsigned freemask = gmask & ~survmask;
+                int n_new = 0;
+                for (int base = G; base < m; base += G) {
+                    const int idx = base + li;
+                    const bool isnew = idx < m && sm.rnk[idx] < bw;
+                    const unsigned bal = __ballot_sync(gmask, isnew);
+                    if (isnew) sm.newlist[n_new + __popc(bal & below)] = (uint8_t)idx;
+                    n_new += __popc(bal);
+                }
+
+                if (n_new > 0) {
+                    __syncwarp(gmask);
+                    const int ford = __popc(freemask & below);
+                    const bool take = !survive && ford < n_new;
+                    const int item = take ? (int)sm.newlist[ford] : 0;
+                    const int s = take ? (int)sm.src[item] : li * 4;
+                    const int ls = (s >> 2) + (int)gshift;
+                    const int c = s & 3;
+                    // parent state, read before anybody overwrites it
+                    const uint32_t p_ctx = __shfl_sync(gmask, ctx, ls);
+                    const int p_len = __shfl_sync(gmask, len, ls);
+                    const int p_node = __shfl_sync(gmask, node, ls);
+                    const unsigned long long p_h = __shfl_sync(gmask, h, ls);
+                    double p_r = 0.0;
+                    bool p_g = false;
+                    if (LM) {
+                        const double r0 = __shfl_sync(gmask, rext0, ls);
+                        const double r1 = __shfl_sync(gmask, rext1, ls);
+                        const double r2 = __shfl_sync(gmask, rext2, ls);
+                        const double r3 = __shfl_sync(gmask, rext3, ls);
+                        p_r = c == 0 ? r0 : c == 1 ? r1 : c == 2 ? r2 : r3;
+                        p_g = __shfl_sync(gmask, (int)gext, ls) != 0;
+                    }
+                    if (survive) {
+                        ptot = nptot;
+                        pnb = npnb;
+                        pb = npb;
+                        rank = new_rank;
+                        if (plane >= 0 && ((evmask >> (gshift + plane)) & 1u)) plane = -1;
+                    } else if (take) {
+                        const double sc = __longlong_as_double((long long)sm.key[item]);
+                        ptot = sc;
+                        pnb = sc;
+                        pb = 0.0;
+                        rank = (int)sm.rnk[item];
+                        node = top + ford;
+                        len = p_len + 1;
+                        ctx = (p_ctx << 2) | (uint32_t)c;
+                        last = c;
+                        hp = p_h;
+                        h = hash_step(p_h, c);
+                        plane = ((survmask >> ls) & 1u) ? (ls - (int)gshift) : -1;
+                        alive = true;
+                        arena[node] = ((uint32_t)p_node << 2) | (uint32_t)c;
+                        if (LM) {
+                            gcopy = p_g;
+                            rcopy = p_r;
+                            gext = false;
+                            if (len >= L) {
+                                const uint32_t ci = ctx & ctx_mask;
+                                const uint32_t gwd = __ldg(a.gate + (ci >> 5));
+                                const double2 *row = reinterpret_cast<const double2 *>(a.table + (size_t)ci * 4);
+                                const double2 ra = __ldg(row), rb = __ldg(row + 1);
+                                gext = (gwd >> (ci & 31u)) & 1u;
+                                rext0 = ra.x;
+                                rext1 = ra.y;
+                                rext2 = rb.x;
+                                rext3 = rb.y;
+                            }
+                        }
+                    } else {
+                        alive = false;
+                    }
+                    top += n_new;
+                    // a surviving beam whose parent labeling was just (re)created points at it
+                    // again: compare parent hash + length with every new beam
+                    const unsigned newmask = __ballot_sync(gmask, take);
+                    unsigned nm = newmask;
+                    while (nm) {
+                        const int zl = __ffs(nm) - 1;
+                        nm &= nm - 1;
+                        const unsigned long long zh = __shfl_sync(gmask, h, zl);
+                        const int zlen = __shfl_sync(gmask, len, zl);
+                        if (survive && plane < 0 && len == zlen + 1 && hp == zh && len > 0) plane = zl - (int)gshift;
+                    }
+                    na = __popc(survmask) + n_new;
+                } else {
+                    if (survive) {
+                        ptot = nptot;
+                        pnb = npnb;
+                        pb = npb;
+                        rank = new_rank;
+                        if (plane >= 0 && ((evmask >> (gshift + plane)) & 1u)) plane = -1;
+                    } else {
+                        alive = false;
+                    }
+                    na = __popc(survmask);
+                }
+
+                // RESCALE by the exponent of the best beam (exact)
+                {
+                    const unsigned bb = __ballot_sync(gmask, alive && rank == 0);
+                    const int bl = __ffs(bb) - 1;
+                    const int hi = __shfl_sync(gmask, __double2hiint(ptot), bl);
+                    const int ex = (hi >> 20) & 0x7ff;
+                    if (ex != 0 && ex != 0x7ff) {
+                        const int E = ex - 1023;
+                        const double sc = __hiloint2double((1023 - E) << 20, 0);
+                        ptot *= sc;
+                        pnb *= sc;
+                        pb *= sc;
+                        kacc += E;
+                    }
+                }
+                ++t;
+            }
+        }
+
+        // ------------------------------------------------------------ end of read
+        if (t >= T) {
+            const unsigned b0 = __ballot_sync(gmask, alive && rank == 0);
+            const unsigned b1 = __ballot_sync(gmask, alive && rank == 1);
+            const int l0 = __ffs(b0) - 1;
+            if (status == 0 && lane == l0) {
+                const long long n = len;
+                if (n > seq_cap) status = RADIAN_READ_SEQ_OVERFLOW;
+                int c = node;
+                for (long long i = n - 1; i >= 0; --i) {
+                    const uint32_t w = arena[c] & 0x7fffffffu;
+                    if (i < seq_cap) a.out_seq[seq_off + i] = (uint8_t)(w & 3u);
+                    c = (int)(w >> 2);
+                }
+                a.out_len[read] = n;
+                a.out_score[2 * read] = (ptot > 0.0) ? log(ptot) + (double)kacc * 0.693147180559945309417 : -INFINITY;
+                if (!b1) a.out_score[2 * read + 1] = NAN;
+                a.out_status[read] = status;
+                if (a.out_counters) {
+                    a.out_counters[2 * read] = n_lookup;
+                    a.out_counters[2 * read + 1] = n_combine;
+                }
+            }
+            if (status == 0 && b1 && lane == __ffs(b1) - 1)
+                a.out_score[2 * read + 1] = (ptot > 0.0) ? log(ptot) + (double)kacc * 0.693147180559945309417 : -INFINITY;
+            if (status != 0 && li == 0) {
+                a.out_len[read] = 0;
+                a.out_score[2 * read] = NAN;
+                a.out_score[2 * read + 1] = NAN;
+                a.out_status[read] = status;
+            }
+            read = -1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ host side
+
+static int group_size(int beam_width) { return beam_width <= 8 ? 8 : beam_width <= 16 ? 16 : 32; }
+
+template <int G, bool LM, typename PT>
+static const void *kernel_ptr(bool count)
+{
+    return count ? (const void *)decode_kernel<G, LM, PT, true> : (const void *)decode_kernel<G, LM, PT, false>;
+}
+
+static const void *pick_kernel(int G, bool lm, bool f64, bool count)
+{
+#define RADIAN_PICK(GG)                                                                        \
+    if (G == GG) {                                                                             \
+        if (lm) return f64 ? kernel_ptr<GG, true, double>(count) : kernel_ptr<GG, true, float>(count); \
+        return f64 ? kernel_ptr<GG, false, double>(count) : kernel_ptr<GG, false, float>(count);       \
+    }
+    RADIAN_PICK(8)
+    RADIAN_PICK(16)
+    RADIAN_PICK(32)
+#undef RADIAN_PICK
+    return nullptr;
+}
+
+int decode_nursery() { return kNursery; }
+
+int64_t decode_arena_cap(int beam_width, int64_t max_frames, int64_t arena_nodes)
+{
+    // Old generation <= beam_width x decoded length (see the header comment); decoded length <= T.
+    // Small problems get the exact worst case; large ones assume >= 8 frames per base and report
+    // RADIAN_READ_TRIE_OVERFLOW otherwise (the caller retries those reads with arena_nodes set).
+    const int64_t G = group_size(beam_width);
+    const int64_t exact = G * (max_frames + 1) + kNursery + 64;
+    if (arena_nodes > 0) return arena_nodes < exact ? arena_nodes + kNursery : exact;
+    if (exact <= (1 << 16)) return exact;
+    int64_t cap = G * (max_frames / 8 + 64) + kNursery;
+    return cap < (1 << 16) ? (1 << 16) : cap;
+}
+
+int decode_pick(int device, int beam_width, bool lm, bool f64, DecodeLaunch *out)
+{
+    DeviceInfo di;
+    int rc = device_info(device, &di);
+    if (rc) return rc;
+    const int G = group_size(beam_width);
+    const void *k = pick_kernel(G, lm, f64, true);
+    int blocks = 0;
+    RADIAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k, kWarpsPerBlock * 32, 0));
+    if (blocks < 1) blocks = 1;
+    out->grid = di.sm_count * blocks;
+    out->block = kWarpsPerBlock * 32;
+    out->groups_per_block = kWarpsPerBlock * (32 / G);
+    return 0;
+}
+
+int decode_max_slots(int device, int beam_width)
+{
+    int best = 0;
+    for (int lm = 0; lm < 2; ++lm)
+        for (int f64 = 0; f64 < 2; ++f64) {
+            DecodeLaunch dl;
+            if (decode_pick(device, beam_width, lm, f64, &dl)) return -1;
+            int s = dl.grid * dl.groups_per_block;
+            best = s > best ? s : best;
+        }
+    return best;
+}
+
+int decode_launch(const DecodeArgs &a, bool f64, int device, cudaStream_t stream)
+{
+    const bool lm = a.table != nullptr;
+    DecodeLaunch dl;
+    int rc = decode_pick(device, a.beam_width, lm, f64, &dl);
+    if (rc) return rc;
+    const int G = group_size(a.beam_width);
+    const void *k = pick_kernel(G, lm, f64, a.out_counters != nullptr);
+    // no more groups than reads: extra CTAs would only touch the queue
+    int64_t need = ((int64_t)a.n_reads + dl.groups_per_block - 1) / dl.groups_per_block;
+    int grid = (int)(need < dl.grid ? need : dl.grid);
+    if (grid < 1) grid = 1;
+    DecodeArgs args = a;
+    void *params[] = {(void *)&args};
+    RADIAN_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(dl.block), params, 0, stream));
+    return 0;
+}
+
+}  // namespace radian

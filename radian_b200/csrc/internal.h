@@ -1,0 +1,76 @@
+// Internal declarations shared by the translation units of libradian_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "radian_b200.h"
+
+namespace radian {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define RADIAN_CUDA(call)                                          \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return ::radian::cuda_fail(e__, #call); \
+    } while (0)
+
+struct DeviceInfo {
+    int sm_count;
+    int max_smem_optin;
+};
+int device_info(int device, DeviceInfo *out);
+
+}  // namespace radian
+
+struct radian_table {
+    int L;
+    int device;
+    size_t rows;
+    double *d_rows;      // rows x 4 float64 linear probabilities
+    double *d_entropy;   // rows float64, reference entropy() of each row (host libm)
+    uint32_t *d_gate;    // rows/32 words: bit = entropy < gate_threshold
+    double gate_threshold;
+    int gate_valid;
+};
+
+namespace radian {
+
+// (re)build table->d_gate for r_threshold on `stream` if it is not current
+int table_prepare_gate(radian_table *t, double r_threshold, cudaStream_t stream);
+
+struct DecodeArgs {
+    const void *post;
+    const int64_t *frame_offsets;
+    const int32_t *order;
+    int n_reads;
+    int beam_width;
+    const double *table;     // nullptr = LM off
+    const uint32_t *gate;
+    int L;
+    double s_thr;
+    uint8_t *out_seq;
+    const int64_t *seq_offsets;
+    int64_t *out_len;
+    double *out_score;
+    int32_t *out_status;
+    unsigned long long *out_counters;
+    uint32_t *arena;         // slots x (arena_cap + nursery) words: nodes, then forwarding scratch
+    int arena_cap;
+    int *queue;              // work-queue head, zeroed before launch
+};
+
+struct DecodeLaunch {
+    int grid;
+    int block;
+    int groups_per_block;
+};
+
+int decode_pick(int device, int beam_width, bool lm, bool f64, DecodeLaunch *out);
+int decode_launch(const DecodeArgs &a, bool f64, int device, cudaStream_t stream);
+int decode_max_slots(int device, int beam_width);
+int64_t decode_arena_cap(int beam_width, int64_t max_frames, int64_t arena_nodes);
+int decode_nursery();
+
+}  // namespace radian

@@ -1,0 +1,260 @@
+"""Drop-in for the reference's ``radian/decode.py`` beam search, running on the GPU.
+
+``beam_search`` keeps the reference's positional signature (decode.py:100-109) and return
+value (the best labeling as a string in decode order, decode.py:207-212).  Because one read
+per call cannot feed a B200, the batched entry points ``beam_search_batch`` (host arrays)
+and ``decode_batch_device`` (resident torch CUDA tensors, asynchronous) are added; they
+call the same kernel.  All arithmetic happens in libradian_b200.so; nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+import weakref
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native
+from ._native import lib
+
+N_BASES = 4  # decode.py:14
+
+
+class RnaTable:
+    """The RNA k-mer model resident in HBM: dense ``(4**L, 4)`` float64 rows indexed by the
+    2-bit packed context (oldest symbol most significant, basecall.py:54-57), plus the row
+    entropies the reference memoises in ``entr_cache`` (decode.py:86-90)."""
+
+    def __init__(self, dense: np.ndarray, device: int = 0):
+        dense = np.ascontiguousarray(dense, dtype=np.float64)
+        if dense.ndim != 2 or dense.shape[1] != 4:
+            raise ValueError("table must have shape (4**L, 4)")
+        L = 0
+        while 4 ** L < dense.shape[0]:
+            L += 1
+        if 4 ** L != dense.shape[0] or L < 1:
+            raise ValueError(f"table has {dense.shape[0]} rows, not a power of 4")
+        h = ctypes.c_void_p()
+        _native.check(lib.radian_table_create(_native.np_ptr(dense), L, int(device), ctypes.byref(h)))
+        self._h = h
+        self.L = L
+        self.device = int(device)
+
+    @classmethod
+    def from_dict(cls, lm: dict, len_context: int, device: int = 0) -> "RnaTable":
+        """Dense copy of the dict built at basecall.py:50-57 ({tuple of ints: [pA,pC,pG,pT]}).
+        A context missing from the dict is a KeyError in the reference when the search first
+        visits it (decode.py:83); here it is raised up front."""
+        L = int(len_context)
+        n = 4 ** L
+        dense = np.empty((n, 4), dtype=np.float64)
+        seen = np.zeros(n, dtype=bool)
+        for ctx, dist in lm.items():
+            if len(ctx) != L:
+                continue
+            idx = 0
+            for c in ctx:
+                idx = idx * 4 + int(c)
+            dense[idx] = dist
+            seen[idx] = True
+        if not seen.all():
+            missing = int(np.flatnonzero(~seen)[0])
+            ctx = tuple((missing >> (2 * (L - 1 - i))) & 3 for i in range(L))
+            raise KeyError(ctx)
+        return cls(dense, device)
+
+    @classmethod
+    def from_json(cls, path: str, device: int = 0) -> "RnaTable":
+        """Load the reference's RNA model JSON ({"ACGT...": [pA,pC,pG,pT]}, basecall.py:50-57)."""
+        import json
+
+        with open(path, "r") as f:
+            raw = json.load(f)
+        code = {"A": 0, "C": 1, "G": 2, "T": 3}
+        L = len(next(iter(raw)))
+        lm = {tuple(code[b] for b in k): v for k, v in raw.items()}
+        return cls.from_dict(lm, L, device)
+
+    def entropies(self) -> np.ndarray:
+        out = np.empty(4 ** self.L, dtype=np.float64)
+        _native.check(lib.radian_table_entropies(self._h, _native.np_ptr(out)))
+        return out
+
+    def __bool__(self):
+        return True
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib.radian_table_destroy(h)
+            except Exception:
+                pass
+
+
+_table_cache: "dict[tuple, RnaTable]" = {}
+_table_lock = threading.Lock()
+
+
+def _resolve_table(lm, len_context, device):
+    """lm truthiness follows decode.py:157,180: None / {} switch the model off."""
+    if isinstance(lm, RnaTable):
+        return lm
+    if not lm:
+        return None
+    if isinstance(lm, str):
+        # basecall.py:48-49 leaves --rna-model None as the *string* "None"; the reference then
+        # dies with this TypeError at decode.py:83 as soon as a beam is long enough.
+        raise TypeError("string indices must be integers, not 'tuple'")
+    key = (id(lm), int(len_context), int(device))
+    with _table_lock:
+        t = _table_cache.get(key)
+        if t is None:
+            t = RnaTable.from_dict(lm, len_context, device)
+            _table_cache[key] = t
+            try:
+                weakref.finalize(lm, _table_cache.pop, key, None)
+            except TypeError:
+                pass  # plain dicts cannot be weak-referenced: the entry lives as long as the process
+        return t
+
+
+def _current_device() -> int:
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
+
+
+def beam_search_batch(mats, beam_width, lm=None, s_threshold=None, r_threshold=None, len_context=None,
+                      bases="ACGT", device=None, return_details=False):
+    """Decode a list of (T_i, 5) posterior matrices (all float32 or all float64) in one launch.
+    Returns the list of decoded strings, or (strings, scores[n,2], counters[n,2]) with
+    ``return_details``."""
+    if len(bases) != N_BASES:
+        raise ValueError("this build decodes 4 bases + blank (chars == 5, decode.py:124-125)")
+    if int(beam_width) < 1 or int(beam_width) > _native.MAX_BEAM_WIDTH:
+        raise ValueError(f"beam_width must be in 1..{_native.MAX_BEAM_WIDTH}")
+    device = _current_device() if device is None else int(device)
+    table = _resolve_table(lm, len_context, device)
+    n = len(mats)
+    if n == 0:
+        return ([], np.zeros((0, 2)), np.zeros((0, 2), np.uint64)) if return_details else []
+    dt = np.float64 if any(np.asarray(m).dtype == np.float64 for m in mats) else np.float32
+    arrs = []
+    for m in mats:
+        m = np.asarray(m)
+        if m.ndim != 2 or m.shape[1] != N_BASES + 1:
+            if m.size == 0:
+                m = m.reshape(0, N_BASES + 1)
+            else:
+                raise ValueError(f"posterior matrix must be (T, 5), got {m.shape}")
+        arrs.append(np.ascontiguousarray(m, dtype=dt))
+    fo = np.zeros(n + 1, dtype=np.int64)
+    fo[1:] = np.cumsum([a.shape[0] for a in arrs])
+    post = np.concatenate(arrs) if fo[-1] else np.zeros((0, 5), dt)
+    so = np.zeros(n + 1, dtype=np.int64)
+    so[1:] = np.cumsum(np.maximum(fo[1:] - fo[:-1], 1))
+    seq = np.zeros(int(so[-1]), dtype=np.uint8)
+    ln = np.zeros(n, dtype=np.int64)
+    score = np.zeros((n, 2), dtype=np.float64)
+    status = np.zeros(n, dtype=np.int32)
+    cnt = np.zeros((n, 2), dtype=np.uint64) if return_details else None
+    rc = lib.radian_decode_batch_host(
+        _native.np_ptr(post), int(dt == np.float64), _native.np_ptr(fo), n, int(beam_width),
+        table._h if table else None, int(len_context) if table else 0,
+        float(s_threshold) if table else 0.0, float(r_threshold) if table else 0.0,
+        _native.np_ptr(seq), _native.np_ptr(so), _native.np_ptr(ln), _native.np_ptr(score),
+        _native.np_ptr(status), _native.np_ptr(cnt), device)
+    _native.check(rc)
+    lut = np.frombuffer(bases.encode("ascii"), dtype=np.uint8)
+    out = [lut[seq[so[i]:so[i] + ln[i]]].tobytes().decode("ascii") for i in range(n)]
+    return (out, score, cnt) if return_details else out
+
+
+def beam_search(mat, bases, beam_width, lm, s_threshold, r_threshold, len_context, entr_cache):
+    """Beam search decoder -- same signature and result as the reference (decode.py:100-212).
+
+    ``entr_cache`` is accepted for compatibility and ignored: it is a pure memo of row
+    entropies in the reference (decode.py:86-90); here they are computed once per table.
+    """
+    del entr_cache
+    return beam_search_batch([mat], beam_width, lm, s_threshold, r_threshold, len_context, bases=bases)[0]
+
+
+# --------------------------------------------------------------------------- resident path
+@dataclass
+class DeviceDecodeResult:
+    seq: "object"          # uint8 CUDA tensor, symbols 0..3
+    seq_offsets: "object"  # int64 CUDA tensor (n+1)
+    lengths: "object"      # int64 CUDA tensor (n)
+    scores: "object"       # float64 CUDA tensor (n, 2)
+    status: "object"       # int32 CUDA tensor (n)
+    counters: "object"     # uint64-as-int64 CUDA tensor (n, 2) or None
+
+    def strings(self, bases="ACGT"):
+        seq = self.seq.cpu().numpy()
+        so = self.seq_offsets.cpu().numpy()
+        ln = self.lengths.cpu().numpy()
+        lut = np.frombuffer(bases.encode("ascii"), dtype=np.uint8)
+        return [lut[seq[so[i]:so[i] + ln[i]]].tobytes().decode("ascii") for i in range(len(ln))]
+
+
+_workspaces: dict = {}
+
+
+def _workspace(device: int, nbytes: int):
+    import torch
+
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{device}")
+        _workspaces[device] = ws
+    return ws
+
+
+def decode_batch_device(post, frame_offsets, beam_width, table=None, s_threshold=0.0, r_threshold=0.0,
+                        *, max_frames, order=None, seq_offsets=None, counters=False, out=None, arena_nodes=0):
+    """Asynchronous decode of reads already resident in HBM (torch CUDA tensors), on the
+    current torch stream.  ``post``: (sum T, 5) float32/float64; ``frame_offsets``: int64
+    (n+1); ``order``: optional int32 processing order (longest first).  ``seq_offsets`` gives
+    every read its output slot (default: T_r bytes, always enough).  Reads whose status is
+    RADIAN_READ_TRIE_OVERFLOW (2) must be re-run with ``arena_nodes = 32 * (T + 1)``."""
+    import torch
+
+    dev = post.device.index
+    n = frame_offsets.numel() - 1
+    if seq_offsets is None:
+        seq_offsets = torch.zeros(n + 1, dtype=torch.int64, device=post.device)
+        seq_offsets[1:] = torch.cumsum(torch.clamp(frame_offsets[1:] - frame_offsets[:-1], min=1), 0)
+        total = int(post.shape[0]) + n
+    else:
+        total = int(seq_offsets[-1].item())
+    if out is None:
+        out = DeviceDecodeResult(
+            seq=torch.empty(total, dtype=torch.uint8, device=post.device),
+            seq_offsets=seq_offsets,
+            lengths=torch.empty(n, dtype=torch.int64, device=post.device),
+            scores=torch.empty((n, 2), dtype=torch.float64, device=post.device),
+            status=torch.empty(n, dtype=torch.int32, device=post.device),
+            counters=torch.zeros((n, 2), dtype=torch.int64, device=post.device) if counters else None)
+    nbytes = lib.radian_decode_workspace_bytes(dev, int(beam_width), int(max_frames), int(arena_nodes))
+    if nbytes == 0:
+        raise _native.RadianError(f"no CUDA device / bad beam width: {_native.last_error()}")
+    ws = _workspace(dev, nbytes)
+    stream = torch.cuda.current_stream(post.device).cuda_stream
+    rc = lib.radian_decode_batch_dev(
+        post.data_ptr(), int(post.dtype == torch.float64), frame_offsets.data_ptr(), n,
+        order.data_ptr() if order is not None else None, int(max_frames), int(beam_width),
+        table._h if table is not None else None, table.L if table is not None else 0,
+        float(s_threshold), float(r_threshold), out.seq.data_ptr(), out.seq_offsets.data_ptr(),
+        out.lengths.data_ptr(), out.scores.data_ptr(), out.status.data_ptr(),
+        out.counters.data_ptr() if out.counters is not None else None, int(arena_nodes),
+        ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream))
+    _native.check(rc)
+    return out

