@@ -104,7 +104,9 @@ def test_table_entropies_match_reference_formula():
     dense[5] = [0.5, 0.5, 0.0, 0.0]
     dense[6] = [1.0, 0.0, 0.0, 0.0]
     got = decode.RnaTable(dense).entropies()
-    want = np.array([-sum([p * math.log(p) for p in row if p > 0]) for row in dense.tolist()])
+    # iterate numpy scalars exactly like decode.py:75-76 (CPython >= 3.12 sums exact Python
+    # floats with compensation, np.float64 scalars go through the plain left-to-right path)
+    want = np.array([-sum([p * math.log(p) for p in row[row > 0]]) for row in dense])
     assert np.array_equal(got, want)
 
 
