@@ -42,9 +42,11 @@ constexpr int kNursery = 4096;  // arena nodes between two collections
 template <int G, bool LM>
 struct __align__(16) GroupSmem {
     static constexpr int REC = LM ? 12 : 6;  // doubles per frame: P0..P4, gate, q0..q3, S, pad
+    static constexpr int NK = (2 * G > 32) ? 2 * G : 32;  // candidate slots of the fast ranking path
     double rec[G * REC];
     double ex[G * 4];                 // extension scores of every lane, for the copy/extend merge
     unsigned long long key[5 * G];    // candidate list: [0,G) copies by lane, [G,..) extensions
+    uint32_t k32[NK];                 // high words of the candidate scores (0 = empty slot)
     uint32_t kill[G];                 // byte c of word l: extension (l,c) merged into a copy
     uint16_t pos[5 * G];              // dict insertion position of the candidate
     uint8_t src[5 * G];               // lane*4+c of an extension candidate
@@ -70,22 +72,35 @@ __device__ __forceinline__ void load_row(const PT *post, long long frame, PT (&v
 // Per-frame work shared by all beams of a read, done by the lane that loaded the frame.
 // Reference: decode.py:135-138 (s_entropies), 67-76 (normalise, entropy), 54-55 (base sum and
 // p/S of combine_dists).  float32 input follows the numpy>=2 promotion the pinned oracle uses.
+// The entropy only feeds the comparison H > s_threshold (decode.py:93): a float32 estimate with
+// the hardware log decides it unless it lands within 1e-4 of the threshold, in which case the
+// reference's exact operation order is evaluated.
 template <bool LM>
 __device__ __forceinline__ void make_record(const double (&v)[5], double s_thr, double *rec)
 {
 #pragma unroll
     for (int i = 0; i < 5; ++i) rec[i] = v[i];
     if (LM) {
-        double S = __dadd_rn(__dadd_rn(__dadd_rn(v[0], v[1]), v[2]), v[3]);
-        double H = 0.0;
+        const double S = __dadd_rn(__dadd_rn(__dadd_rn(v[0], v[1]), v[2]), v[3]);
+        double q[4];
+        float Ha = 0.0f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            double q = (S == 0.0) ? v[i] : v[i] / S;
-            rec[6 + i] = q;
-            if (q > 0.0) H = __dadd_rn(H, __dmul_rn(q, log(q)));
+            q[i] = (S == 0.0) ? v[i] : v[i] / S;
+            rec[6 + i] = q[i];
+            const float qf = (float)q[i];
+            if (qf > 0.0f) Ha -= qf * __logf(qf);
         }
         rec[10] = S;
-        rec[5] = (-H > s_thr) ? 1.0 : 0.0;
+        bool gate = Ha > (float)s_thr;
+        if (!(fabsf(Ha - (float)s_thr) > 1e-4f)) {
+            double H = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (q[i] > 0.0) H = __dadd_rn(H, __dmul_rn(q[i], log(q[i])));
+            gate = -H > s_thr;
+        }
+        rec[5] = gate ? 1.0 : 0.0;
     }
 }
 
@@ -95,16 +110,25 @@ __device__ __forceinline__ void make_record(const float (&v)[5], double s_thr, d
 #pragma unroll
     for (int i = 0; i < 5; ++i) rec[i] = (double)v[i];
     if (LM) {
-        float S = __fadd_rn(__fadd_rn(__fadd_rn(v[0], v[1]), v[2]), v[3]);
-        float H = 0.0f;
+        const float S = __fadd_rn(__fadd_rn(__fadd_rn(v[0], v[1]), v[2]), v[3]);
+        float q[4];
+        float Ha = 0.0f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float q = (S == 0.0f) ? v[i] : __fdiv_rn(v[i], S);
-            rec[6 + i] = (double)q;
-            if (q > 0.0f) H = __fadd_rn(H, __fmul_rn(q, __double2float_rn(log((double)q))));
+            q[i] = (S == 0.0f) ? v[i] : __fdiv_rn(v[i], S);
+            rec[6 + i] = (double)q[i];
+            if (q[i] > 0.0f) Ha -= q[i] * __logf(q[i]);
         }
         rec[10] = (double)S;
-        rec[5] = (-H > (float)s_thr) ? 1.0 : 0.0;
+        bool gate = Ha > (float)s_thr;
+        if (!(fabsf(Ha - (float)s_thr) > 1e-4f)) {
+            float H = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (q[i] > 0.0f) H = __fadd_rn(H, __fmul_rn(q[i], __double2float_rn(log((double)q[i]))));
+            gate = -H > (float)s_thr;
+        }
+        rec[5] = gate ? 1.0 : 0.0;
     }
 }
 
@@ -114,6 +138,8 @@ decode_kernel(const DecodeArgs a)
 {
     constexpr int GPW = 32 / G;  // groups (reads) per warp
     constexpr int REC = GroupSmem<G, LM>::REC;
+    constexpr int NK = GroupSmem<G, LM>::NK;
+    constexpr int EPL = (NK - G) / G;  // extension slots ranked by each lane on the fast path
     __shared__ GroupSmem<G, LM> smem[kWarpsPerBlock * GPW];
 
     const int lane = threadIdx.x & 31;
@@ -149,48 +175,62 @@ decode_kernel(const DecodeArgs a)
     PT pf[5];
     bool active = true;
 
-    while (__any_sync(kFull, active)) {
-        if (!active) continue;
-
+    while (true) {
         // ------------------------------------------------------------ fetch a read
-        if (read < 0) {
+        if (active && read < 0) {
             int idx = 0;
             if (li == 0) idx = atomicAdd(a.queue, 1);
             idx = __shfl_sync(gmask, idx, gshift);
             if (idx >= a.n_reads) {
                 active = false;
-                continue;
+            } else {
+                read = a.order ? a.order[idx] : idx;
+                foff = a.frame_offsets[read];
+                T = a.frame_offsets[read + 1] - foff;
+                seq_off = a.seq_offsets[read];
+                seq_cap = a.seq_offsets[read + 1] - seq_off;
+                t = 0;
+                // initial beam: the empty labeling, pr_blank = pr_total = log 1 (decode.py:128-132)
+                alive = (li == 0);
+                ptot = alive ? 1.0 : 0.0;
+                pb = ptot;
+                pnb = 0.0;
+                h = 0x243F6A8885A308D3ull;
+                hp = 0;
+                ctx = 0;
+                len = 0;
+                node = 0;
+                rank = 0;
+                plane = -1;
+                last = 0;
+                gext = gcopy = false;
+                top = 1;  // node 0 = the empty labeling
+                old_top = 1;
+                na = 1;
+                status = 0;
+                kacc = 0;
+                n_lookup = n_combine = 0;
+                if (li < T) load_row(post_all + foff * 5, li, pf);
             }
-            read = a.order ? a.order[idx] : idx;
-            foff = a.frame_offsets[read];
-            T = a.frame_offsets[read + 1] - foff;
-            seq_off = a.seq_offsets[read];
-            seq_cap = a.seq_offsets[read + 1] - seq_off;
-            t = 0;
-            // initial beam: the empty labeling, pr_blank = pr_total = log 1 (decode.py:128-132)
-            alive = (li == 0);
-            ptot = alive ? 1.0 : 0.0;
-            pb = ptot;
-            pnb = 0.0;
-            h = 0x243F6A8885A308D3ull;
-            hp = 0;
-            ctx = 0;
-            len = 0;
-            node = 0;
-            rank = 0;
-            plane = -1;
-            last = 0;
-            gext = gcopy = false;
-            top = 1;  // node 0 = the empty labeling
-            old_top = 1;
-            na = 1;
-            status = 0;
-            kacc = 0;
-            n_lookup = n_combine = 0;
-            if (li < T) load_row(post_all + foff * 5, li, pf);
+        }
+        if (!__any_sync(kFull, active)) break;
+
+        // frames every active group of this warp can run before one of them finishes its read
+        int rem = 0x7fffffff;
+        if (active) rem = (T - t) > 0x7ffffffell ? 0x7ffffffe : (int)(T - t);
+        int nrun = rem;
+#pragma unroll
+        for (int g = 0; g < GPW; ++g) {
+            const int x = __shfl_sync(kFull, rem, g * G);
+            nrun = x < nrun ? x : nrun;
         }
 
-        if (t < T) {
+        for (int it = 0; it < nrun; ++it) {
+            if (!active) continue;
+            if (status != 0) {
+                ++t;  // arena overflow: the read is reported as failed, its frames are skipped
+                continue;
+            }
             // -------------------------------------------------------- tile refill
             if ((t % G) == 0) {
                 __syncwarp(gmask);
@@ -249,109 +289,158 @@ decode_kernel(const DecodeArgs a)
                 __syncwarp(gmask);
                 old_top = cnt;
                 top = cnt;
-                if (top + G > cap) status = RADIAN_READ_TRIE_OVERFLOW;
+                if (top + G > cap) {
+                    status = RADIAN_READ_TRIE_OVERFLOW;
+                    ++t;
+                    continue;
+                }
             }
 
-            if (status == RADIAN_READ_TRIE_OVERFLOW) {
-                t = T;  // give up on this read; reported through out_status
-            } else {
-                // ---------------------------------------------------- one frame
-                const double *rec = &sm.rec[(int)(t % G) * REC];
-                const double P4 = rec[4];
-                const double2 P01 = *reinterpret_cast<const double2 *>(rec);
-                const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
-                bool fgate = false;
-                double2 q01 = make_double2(0, 0), q23 = make_double2(0, 0);
-                double S = 0.0;
-                if (LM) {
-                    fgate = rec[5] != 0.0;
-                    if (fgate) {
-                        q01 = *reinterpret_cast<const double2 *>(rec + 6);
-                        q23 = *reinterpret_cast<const double2 *>(rec + 8);
-                        S = rec[10];
-                    }
+            // -------------------------------------------------------- one frame
+            const double *rec = &sm.rec[(int)(t % G) * REC];
+            const double P4 = rec[4];
+            const double2 P01 = *reinterpret_cast<const double2 *>(rec);
+            const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
+            bool fgate = false;
+            double2 q01 = make_double2(0, 0), q23 = make_double2(0, 0);
+            double S = 0.0;
+            if (LM) {
+                fgate = rec[5] != 0.0;
+                if (fgate) {
+                    q01 = *reinterpret_cast<const double2 *>(rec + 6);
+                    q23 = *reinterpret_cast<const double2 *>(rec + 8);
+                    S = rec[10];
                 }
-                const bool has_last = alive && len > 0;
-                const bool lm_copy = LM && alive && len >= L + 1;  // decode.py:157
-                const bool lm_ext = LM && alive && len >= L;       // decode.py:180
-                if (COUNT && LM) {
-                    n_lookup += __popc(__ballot_sync(gmask, lm_copy)) + __popc(__ballot_sync(gmask, lm_ext));
-                    n_combine += __popc(__ballot_sync(gmask, lm_copy && gcopy && fgate)) +
-                                 __popc(__ballot_sync(gmask, lm_ext && gext && fgate));
-                }
+            }
+            const bool has_last = alive && len > 0;
+            const bool lm_copy = LM && alive && len >= L + 1;  // decode.py:157
+            const bool lm_ext = LM && alive && len >= L;       // decode.py:180
+            if (COUNT && LM) {
+                n_lookup += __popc(__ballot_sync(gmask, lm_copy)) + __popc(__ballot_sync(gmask, lm_ext));
+                n_combine += __popc(__ballot_sync(gmask, lm_copy && gcopy && fgate)) +
+                             __popc(__ballot_sync(gmask, lm_ext && gext && fgate));
+            }
 
-                // COPY (decode.py:150-175)
-                double dl_ = has_last ? rec[last] : 0.0;
-                if (LM && lm_copy && gcopy && fgate) {
-                    double ql = rec[6 + last];
-                    dl_ = __dmul_rn(__dmul_rn(__dadd_rn(rcopy, ql), 0.5), S);  // decode.py:58-61
-                }
-                double npnb = has_last ? __dmul_rn(pnb, dl_) : 0.0;
-                double npb = __dmul_rn(ptot, P4);
-                double nptot = __dadd_rn(npb, npnb);
+            // COPY (decode.py:150-175)
+            double dl_ = has_last ? rec[last] : 0.0;
+            if (LM && lm_copy && gcopy && fgate) {
+                const double ql = rec[6 + last];
+                dl_ = __dmul_rn(__dmul_rn(__dadd_rn(rcopy, ql), 0.5), S);  // decode.py:58-61
+            }
+            double npnb = has_last ? __dmul_rn(pnb, dl_) : 0.0;
+            const double npb = __dmul_rn(ptot, P4);
+            double nptot = __dadd_rn(npb, npnb);
 
-                // EXTEND (decode.py:177-201)
-                double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
-                if (LM && lm_ext && gext && fgate) {
-                    d0 = __dmul_rn(__dmul_rn(__dadd_rn(rext0, q01.x), 0.5), S);
-                    d1 = __dmul_rn(__dmul_rn(__dadd_rn(rext1, q01.y), 0.5), S);
-                    d2 = __dmul_rn(__dmul_rn(__dadd_rn(rext2, q23.x), 0.5), S);
-                    d3 = __dmul_rn(__dmul_rn(__dadd_rn(rext3, q23.y), 0.5), S);
-                }
-                double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-                if (alive) {
-                    e0 = __dmul_rn((has_last && last == 0) ? pb : ptot, d0);  // decode.py:192-195
-                    e1 = __dmul_rn((has_last && last == 1) ? pb : ptot, d1);
-                    e2 = __dmul_rn((has_last && last == 2) ? pb : ptot, d2);
-                    e3 = __dmul_rn((has_last && last == 3) ? pb : ptot, d3);
-                }
+            // EXTEND (decode.py:177-201)
+            double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
+            if (LM && lm_ext && gext && fgate) {
+                d0 = __dmul_rn(__dmul_rn(__dadd_rn(rext0, q01.x), 0.5), S);
+                d1 = __dmul_rn(__dmul_rn(__dadd_rn(rext1, q01.y), 0.5), S);
+                d2 = __dmul_rn(__dmul_rn(__dadd_rn(rext2, q23.x), 0.5), S);
+                d3 = __dmul_rn(__dmul_rn(__dadd_rn(rext3, q23.y), 0.5), S);
+            }
+            double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+            if (alive) {
+                e0 = __dmul_rn((has_last && last == 0) ? pb : ptot, d0);  // decode.py:192-195
+                e1 = __dmul_rn((has_last && last == 1) ? pb : ptot, d1);
+                e2 = __dmul_rn((has_last && last == 2) ? pb : ptot, d2);
+                e3 = __dmul_rn((has_last && last == 3) ? pb : ptot, d3);
+            }
 
-                // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference
-                *reinterpret_cast<double2 *>(&sm.ex[li * 4]) = make_double2(e0, e1);
-                *reinterpret_cast<double2 *>(&sm.ex[li * 4 + 2]) = make_double2(e2, e3);
-                sm.kill[li] = 0u;
-                sm.lanerank[li] = (uint8_t)rank;
-                __syncwarp(gmask);
-                int pos_copy = 5 * rank;
-                if (alive && plane >= 0) {
-                    double v = sm.ex[plane * 4 + last];
-                    npnb = __dadd_rn(npnb, v);
-                    nptot = __dadd_rn(nptot, v);
-                    reinterpret_cast<uint8_t *>(sm.kill)[plane * 4 + last] = 1;
-                    int pp = 5 * (int)sm.lanerank[plane] + 1 + last;
-                    pos_copy = pp < pos_copy ? pp : pos_copy;
-                }
-                __syncwarp(gmask);
-                const uint32_t killw = sm.kill[li];
-
-                // SELECT the best beam_width candidates (decode.py:145, 35-39)
-                const unsigned long long kcopy = (unsigned long long)__double_as_longlong(nptot);
-                const bool prune = (na >= bw);
-                unsigned long long tau = alive ? kcopy : ~0ull;
+            // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference
+            *reinterpret_cast<double2 *>(&sm.ex[li * 4]) = make_double2(e0, e1);
+            *reinterpret_cast<double2 *>(&sm.ex[li * 4 + 2]) = make_double2(e2, e3);
+            sm.kill[li] = 0u;
+            sm.lanerank[li] = (uint8_t)rank;
 #pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) {
-                    unsigned long long x = __shfl_xor_sync(gmask, tau, o);
-                    tau = x < tau ? x : tau;
-                }
-                int n_ext = 0;
+            for (int e = 0; e < EPL; ++e) sm.k32[G + e * G + li] = 0u;
+            __syncwarp(gmask);
+            int pos_copy = 5 * rank;
+            if (alive && plane >= 0) {
+                const double v = sm.ex[plane * 4 + last];
+                npnb = __dadd_rn(npnb, v);
+                nptot = __dadd_rn(nptot, v);
+                reinterpret_cast<uint8_t *>(sm.kill)[plane * 4 + last] = 1;
+                const int pp = 5 * (int)sm.lanerank[plane] + 1 + last;
+                pos_copy = pp < pos_copy ? pp : pos_copy;
+            }
+            __syncwarp(gmask);
+            const uint32_t killw = sm.kill[li];
+
+            // SELECT the best beam_width candidates (decode.py:145, 35-39).  Candidates below the
+            // worst copy cannot enter the beam when the beam is full; the rest is ranked.
+            const unsigned long long kcopy = (unsigned long long)__double_as_longlong(nptot);
+            const uint32_t kc32 = alive ? (uint32_t)(kcopy >> 32) : 0u;
+            const bool prune = (na >= bw);
+            uint32_t tau = alive ? kc32 : 0xffffffffu;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const double ec = c == 0 ? e0 : c == 1 ? e1 : c == 2 ? e2 : e3;
-                    const unsigned long long kc = (unsigned long long)__double_as_longlong(ec);
-                    const bool comp = alive && !((killw >> (8 * c)) & 1u) && (!prune || kc >= tau);
-                    const unsigned bal = __ballot_sync(gmask, comp);
-                    if (comp) {
-                        int idx = G + n_ext + __popc(bal & below);
-                        sm.key[idx] = kc;
-                        sm.pos[idx] = (uint16_t)(5 * rank + 1 + c);
-                        sm.src[idx] = (uint8_t)(li * 4 + c);
-                    }
-                    n_ext += __popc(bal);
+            for (int o = G / 2; o > 0; o >>= 1) {
+                const uint32_t x = __shfl_xor_sync(gmask, tau, o);
+                tau = x < tau ? x : tau;
+            }
+            int n_ext = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double ec = c == 0 ? e0 : c == 1 ? e1 : c == 2 ? e2 : e3;
+                const unsigned long long kc = (unsigned long long)__double_as_longlong(ec);
+                const uint32_t kh = (uint32_t)(kc >> 32);
+                const bool comp = alive && !((killw >> (8 * c)) & 1u) && (!prune || kh >= tau);
+                const unsigned bal = __ballot_sync(gmask, comp);
+                if (comp) {
+                    const int idx = G + n_ext + __popc(bal & below);
+                    sm.key[idx] = kc;
+                    sm.pos[idx] = (uint16_t)(5 * rank + 1 + c);
+                    sm.src[idx] = (uint8_t)(li * 4 + c);
+                    if (idx < NK) sm.k32[idx] = kh;
                 }
+                n_ext += __popc(bal);
+            }
+            sm.k32[li] = kc32;
+            __syncwarp(gmask);
+            const int m = G + n_ext;
+            int new_rank = 255;
+            bool fast = (m <= NK);
+            if (fast) {
+                // rank = number of candidates with a strictly larger high word.  Exact whenever
+                // the high words of the ranked candidates are all distinct, which the rank sum
+                // proves (any tie makes the sum fall short of mv(mv-1)/2).
+                uint32_t ke[EPL];
+                int ce[EPL];
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) {
+                    ke[e] = sm.k32[G + e * G + li];
+                    ce[e] = 0;
+                }
+                int cc = 0;
+                const uint4 *kv = reinterpret_cast<const uint4 *>(sm.k32);
+#pragma unroll
+                for (int j = 0; j < NK / 4; ++j) {
+                    const uint4 k4 = kv[j];
+                    cc += (k4.x > kc32) + (k4.y > kc32) + (k4.z > kc32) + (k4.w > kc32);
+#pragma unroll
+                    for (int e = 0; e < EPL; ++e)
+                        ce[e] += (k4.x > ke[e]) + (k4.y > ke[e]) + (k4.z > ke[e]) + (k4.w > ke[e]);
+                }
+                int ssum = alive ? cc : 0;
+#pragma unroll
+                for (int e = 0; e < EPL; ++e)
+                    if (e * G + li < n_ext) ssum += ce[e];
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(gmask, ssum, o);
+                const int mv = na + n_ext;
+                fast = (ssum == mv * (mv - 1) / 2);
+                if (fast) {
+                    new_rank = alive ? cc : 255;
+#pragma unroll
+                    for (int e = 0; e < EPL; ++e)
+                        if (e * G + li < n_ext) sm.rnk[G + e * G + li] = (uint8_t)ce[e];
+                }
+            }
+            if (!fast) {
+                // exact path: (score desc, dict insertion position asc) on the full float64 bits
                 sm.key[li] = kcopy;
                 sm.pos[li] = alive ? (uint16_t)pos_copy : kPosInvalid;
                 __syncwarp(gmask);
-                const int m = G + n_ext;
                 for (int idx = li; idx < m; idx += G) {
                     const uint16_t p = sm.pos[idx];
                     if (p != kPosInvalid) {
@@ -366,131 +455,131 @@ decode_kernel(const DecodeArgs a)
                     }
                 }
                 __syncwarp(gmask);
-
-                const int new_rank = alive ? (int)sm.rnk[li] : 255;
-                const bool survive = alive && new_rank < bw;
-                const unsigned evmask = __ballot_sync(gmask, alive && !survive);
-                const unsigned survmask = __ballot_sync(gmask, survive);
-                const unsigned freemask = gmask & ~survmask;
-                int n_new = 0;
-                for (int base = G; base < m; base += G) {
-                    const int idx = base + li;
-                    const bool isnew = idx < m && sm.rnk[idx] < bw;
-                    const unsigned bal = __ballot_sync(gmask, isnew);
-                    if (isnew) sm.newlist[n_new + __popc(bal & below)] = (uint8_t)idx;
-                    n_new += __popc(bal);
-                }
-
-                if (n_new > 0) {
-                    __syncwarp(gmask);
-                    const int ford = __popc(freemask & below);
-                    const bool take = !survive && ford < n_new;
-                    const int item = take ? (int)sm.newlist[ford] : 0;
-                    const int s = take ? (int)sm.src[item] : li * 4;
-                    const int ls = (s >> 2) + (int)gshift;
-                    const int c = s & 3;
-                    // parent state, read before anybody overwrites it
-                    const uint32_t p_ctx = __shfl_sync(gmask, ctx, ls);
-                    const int p_len = __shfl_sync(gmask, len, ls);
-                    const int p_node = __shfl_sync(gmask, node, ls);
-                    const unsigned long long p_h = __shfl_sync(gmask, h, ls);
-                    double p_r = 0.0;
-                    bool p_g = false;
-                    if (LM) {
-                        const double r0 = __shfl_sync(gmask, rext0, ls);
-                        const double r1 = __shfl_sync(gmask, rext1, ls);
-                        const double r2 = __shfl_sync(gmask, rext2, ls);
-                        const double r3 = __shfl_sync(gmask, rext3, ls);
-                        p_r = c == 0 ? r0 : c == 1 ? r1 : c == 2 ? r2 : r3;
-                        p_g = __shfl_sync(gmask, (int)gext, ls) != 0;
-                    }
-                    if (survive) {
-                        ptot = nptot;
-                        pnb = npnb;
-                        pb = npb;
-                        rank = new_rank;
-                        if (plane >= 0 && ((evmask >> (gshift + plane)) & 1u)) plane = -1;
-                    } else if (take) {
-                        const double sc = __longlong_as_double((long long)sm.key[item]);
-                        ptot = sc;
-                        pnb = sc;
-                        pb = 0.0;
-                        rank = (int)sm.rnk[item];
-                        node = top + ford;
-                        len = p_len + 1;
-                        ctx = (p_ctx << 2) | (uint32_t)c;
-                        last = c;
-                        hp = p_h;
-                        h = hash_step(p_h, c);
-                        plane = ((survmask >> ls) & 1u) ? (ls - (int)gshift) : -1;
-                        alive = true;
-                        arena[node] = ((uint32_t)p_node << 2) | (uint32_t)c;
-                        if (LM) {
-                            gcopy = p_g;
-                            rcopy = p_r;
-                            gext = false;
-                            if (len >= L) {
-                                const uint32_t ci = ctx & ctx_mask;
-                                const uint32_t gwd = __ldg(a.gate + (ci >> 5));
-                                const double2 *row = reinterpret_cast<const double2 *>(a.table + (size_t)ci * 4);
-                                const double2 ra = __ldg(row), rb = __ldg(row + 1);
-                                gext = (gwd >> (ci & 31u)) & 1u;
-                                rext0 = ra.x;
-                                rext1 = ra.y;
-                                rext2 = rb.x;
-                                rext3 = rb.y;
-                            }
-                        }
-                    } else {
-                        alive = false;
-                    }
-                    top += n_new;
-                    // a surviving beam whose parent labeling was just (re)created points at it
-                    // again: compare parent hash + length with every new beam
-                    const unsigned newmask = __ballot_sync(gmask, take);
-                    unsigned nm = newmask;
-                    while (nm) {
-                        const int zl = __ffs(nm) - 1;
-                        nm &= nm - 1;
-                        const unsigned long long zh = __shfl_sync(gmask, h, zl);
-                        const int zlen = __shfl_sync(gmask, len, zl);
-                        if (survive && plane < 0 && len == zlen + 1 && hp == zh && len > 0) plane = zl - (int)gshift;
-                    }
-                    na = __popc(survmask) + n_new;
-                } else {
-                    if (survive) {
-                        ptot = nptot;
-                        pnb = npnb;
-                        pb = npb;
-                        rank = new_rank;
-                        if (plane >= 0 && ((evmask >> (gshift + plane)) & 1u)) plane = -1;
-                    } else {
-                        alive = false;
-                    }
-                    na = __popc(survmask);
-                }
-
-                // RESCALE by the exponent of the best beam (exact)
-                {
-                    const unsigned bb = __ballot_sync(gmask, alive && rank == 0);
-                    const int bl = __ffs(bb) - 1;
-                    const int hi = __shfl_sync(gmask, __double2hiint(ptot), bl);
-                    const int ex = (hi >> 20) & 0x7ff;
-                    if (ex != 0 && ex != 0x7ff) {
-                        const int E = ex - 1023;
-                        const double sc = __hiloint2double((1023 - E) << 20, 0);
-                        ptot *= sc;
-                        pnb *= sc;
-                        pb *= sc;
-                        kacc += E;
-                    }
-                }
-                ++t;
+                new_rank = alive ? (int)sm.rnk[li] : 255;
+            } else {
+                __syncwarp(gmask);
             }
+
+            const bool survive = alive && new_rank < bw;
+            const unsigned evmask = __ballot_sync(gmask, alive && !survive);
+            const unsigned survmask = __ballot_sync(gmask, survive);
+            const unsigned freemask = gmask & ~survmask;
+            int n_new = 0;
+            for (int base = G; base < m; base += G) {
+                const int idx = base + li;
+                const bool isnew = idx < m && sm.rnk[idx] < bw;
+                const unsigned bal = __ballot_sync(gmask, isnew);
+                if (isnew) sm.newlist[n_new + __popc(bal & below)] = (uint8_t)idx;
+                n_new += __popc(bal);
+            }
+
+            if (n_new > 0) {
+                __syncwarp(gmask);
+                const int ford = __popc(freemask & below);
+                const bool take = !survive && ford < n_new;
+                const int item = take ? (int)sm.newlist[ford] : 0;
+                const int s = take ? (int)sm.src[item] : li * 4;
+                const int ls = (s >> 2) + (int)gshift;
+                const int c = s & 3;
+                // parent state, read before anybody overwrites it
+                const uint32_t p_ctx = __shfl_sync(gmask, ctx, ls);
+                const int p_len = __shfl_sync(gmask, len, ls);
+                const int p_node = __shfl_sync(gmask, node, ls);
+                const unsigned long long p_h = __shfl_sync(gmask, h, ls);
+                double p_r = 0.0;
+                bool p_g = false;
+                if (LM) {
+                    const double r0 = __shfl_sync(gmask, rext0, ls);
+                    const double r1 = __shfl_sync(gmask, rext1, ls);
+                    const double r2 = __shfl_sync(gmask, rext2, ls);
+                    const double r3 = __shfl_sync(gmask, rext3, ls);
+                    p_r = c == 0 ? r0 : c == 1 ? r1 : c == 2 ? r2 : r3;
+                    p_g = __shfl_sync(gmask, (int)gext, ls) != 0;
+                }
+                if (survive) {
+                    ptot = nptot;
+                    pnb = npnb;
+                    pb = npb;
+                    rank = new_rank;
+                    if (plane >= 0 && ((evmask >> (gshift + plane)) & 1u)) plane = -1;
+                } else if (take) {
+                    const double sc = __longlong_as_double((long long)sm.key[item]);
+                    ptot = sc;
+                    pnb = sc;
+                    pb = 0.0;
+                    rank = (int)sm.rnk[item];
+                    node = top + ford;
+                    len = p_len + 1;
+                    ctx = (p_ctx << 2) | (uint32_t)c;
+                    last = c;
+                    hp = p_h;
+                    h = hash_step(p_h, c);
+                    plane = ((survmask >> ls) & 1u) ? (ls - (int)gshift) : -1;
+                    alive = true;
+                    arena[node] = ((uint32_t)p_node << 2) | (uint32_t)c;
+                    if (LM) {
+                        gcopy = p_g;
+                        rcopy = p_r;
+                        gext = false;
+                        if (len >= L) {
+                            const uint32_t ci = ctx & ctx_mask;
+                            const uint32_t gwd = __ldg(a.gate + (ci >> 5));
+                            const double2 *row = reinterpret_cast<const double2 *>(a.table + (size_t)ci * 4);
+                            const double2 ra = __ldg(row), rb = __ldg(row + 1);
+                            gext = (gwd >> (ci & 31u)) & 1u;
+                            rext0 = ra.x;
+                            rext1 = ra.y;
+                            rext2 = rb.x;
+                            rext3 = rb.y;
+                        }
+                    }
+                } else {
+                    alive = false;
+                }
+                top += n_new;
+                // a surviving beam whose parent labeling was just (re)created points at it
+                // again: compare parent hash + length with every new beam
+                unsigned nm = __ballot_sync(gmask, take);
+                while (nm) {
+                    const int zl = __ffs(nm) - 1;
+                    nm &= nm - 1;
+                    const unsigned long long zh = __shfl_sync(gmask, h, zl);
+                    const int zlen = __shfl_sync(gmask, len, zl);
+                    if (survive && plane < 0 && len == zlen + 1 && hp == zh && len > 0) plane = zl - (int)gshift;
+                }
+                na = __popc(survmask) + n_new;
+            } else {
+                if (survive) {
+                    ptot = nptot;
+                    pnb = npnb;
+                    pb = npb;
+                    rank = new_rank;
+                    if (plane >= 0 && ((evmask >> (gshift + plane)) & 1u)) plane = -1;
+                } else {
+                    alive = false;
+                }
+                na = __popc(survmask);
+            }
+
+            // RESCALE by the exponent of the best beam (exact)
+            {
+                const unsigned bb = __ballot_sync(gmask, alive && rank == 0);
+                const int bl = __ffs(bb) - 1;
+                const int hi = __shfl_sync(gmask, __double2hiint(ptot), bl);
+                const int ex = (hi >> 20) & 0x7ff;
+                if (ex != 0 && ex != 0x7ff) {
+                    const double sc = __hiloint2double((2046 - ex) << 20, 0);
+                    ptot *= sc;
+                    pnb *= sc;
+                    pb *= sc;
+                    kacc += ex - 1023;
+                }
+            }
+            ++t;
         }
 
         // ------------------------------------------------------------ end of read
-        if (t >= T) {
+        if (active && t >= T) {
             const unsigned b0 = __ballot_sync(gmask, alive && rank == 0);
             const unsigned b1 = __ballot_sync(gmask, alive && rank == 1);
             const int l0 = __ffs(b0) - 1;
@@ -514,7 +603,7 @@ decode_kernel(const DecodeArgs a)
             }
             if (status == 0 && b1 && lane == __ffs(b1) - 1)
                 a.out_score[2 * read + 1] = (ptot > 0.0) ? log(ptot) + (double)kacc * 0.693147180559945309417 : -INFINITY;
-            if (status != 0 && li == 0) {
+            if (status == RADIAN_READ_TRIE_OVERFLOW && li == 0) {
                 a.out_len[read] = 0;
                 a.out_score[2 * read] = NAN;
                 a.out_score[2 * read + 1] = NAN;
@@ -564,13 +653,13 @@ int64_t decode_arena_cap(int beam_width, int64_t max_frames, int64_t arena_nodes
     return cap < (1 << 16) ? (1 << 16) : cap;
 }
 
-int decode_pick(int device, int beam_width, bool lm, bool f64, DecodeLaunch *out)
+int decode_pick(int device, int beam_width, bool lm, bool f64, bool count, DecodeLaunch *out)
 {
     DeviceInfo di;
     int rc = device_info(device, &di);
     if (rc) return rc;
     const int G = group_size(beam_width);
-    const void *k = pick_kernel(G, lm, f64, true);
+    const void *k = pick_kernel(G, lm, f64, count);
     int blocks = 0;
     RADIAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k, kWarpsPerBlock * 32, 0));
     if (blocks < 1) blocks = 1;
@@ -583,13 +672,12 @@ int decode_pick(int device, int beam_width, bool lm, bool f64, DecodeLaunch *out
 int decode_max_slots(int device, int beam_width)
 {
     int best = 0;
-    for (int lm = 0; lm < 2; ++lm)
-        for (int f64 = 0; f64 < 2; ++f64) {
-            DecodeLaunch dl;
-            if (decode_pick(device, beam_width, lm, f64, &dl)) return -1;
-            int s = dl.grid * dl.groups_per_block;
-            best = s > best ? s : best;
-        }
+    for (int v = 0; v < 8; ++v) {
+        DecodeLaunch dl;
+        if (decode_pick(device, beam_width, v & 1, v & 2, v & 4, &dl)) return -1;
+        int s = dl.grid * dl.groups_per_block;
+        best = s > best ? s : best;
+    }
     return best;
 }
 
@@ -597,7 +685,7 @@ int decode_launch(const DecodeArgs &a, bool f64, int device, cudaStream_t stream
 {
     const bool lm = a.table != nullptr;
     DecodeLaunch dl;
-    int rc = decode_pick(device, a.beam_width, lm, f64, &dl);
+    int rc = decode_pick(device, a.beam_width, lm, f64, a.out_counters != nullptr, &dl);
     if (rc) return rc;
     const int G = group_size(a.beam_width);
     const void *k = pick_kernel(G, lm, f64, a.out_counters != nullptr);
