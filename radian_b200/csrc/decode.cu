@@ -168,8 +168,11 @@ decode_kernel(const DecodeArgs a)
     bool alive = false;
     double rext0 = 0, rext1 = 0, rext2 = 0, rext3 = 0, rcopy = 0;
     bool gext = false, gcopy = false;
+    int succ = -1;          // lane (in group) of the beam ranked right after this one
+    uint32_t killw = 0;     // bit c: extension by c is merged into a live child's copy
     // ---- per-read (group-uniform) state
-    int read = -1, top = 0, old_top = 0, na = 0, status = 0;
+    int read = -1, top = 0, old_top = 0, na = 0, status = 0, first_lane = 0, last_lane = 0;
+    bool any_plane = false;
     long long T = 0, t = 0, foff = 0, kacc = 0, seq_off = 0, seq_cap = 0;
     unsigned long long n_lookup = 0, n_combine = 0;
     PT pf[5];
@@ -204,6 +207,10 @@ decode_kernel(const DecodeArgs a)
                 plane = -1;
                 last = 0;
                 gext = gcopy = false;
+                succ = -1;
+                killw = 0;
+                any_plane = false;
+                first_lane = last_lane = (int)gshift;
                 top = 1;  // node 0 = the empty labeling
                 old_top = 1;
                 na = 1;
@@ -347,225 +354,291 @@ decode_kernel(const DecodeArgs a)
                 e3 = __dmul_rn((has_last && last == 3) ? pb : ptot, d3);
             }
 
-            // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference
-            *reinterpret_cast<double2 *>(&sm.ex[li * 4]) = make_double2(e0, e1);
-            *reinterpret_cast<double2 *>(&sm.ex[li * 4 + 2]) = make_double2(e2, e3);
-            sm.kill[li] = 0u;
-            sm.lanerank[li] = (uint8_t)rank;
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) sm.k32[G + e * G + li] = 0u;
-            __syncwarp(gmask);
-            int pos_copy = 5 * rank;
-            if (alive && plane >= 0) {
-                const double v = sm.ex[plane * 4 + last];
-                npnb = __dadd_rn(npnb, v);
-                nptot = __dadd_rn(nptot, v);
-                reinterpret_cast<uint8_t *>(sm.kill)[plane * 4 + last] = 1;
-                const int pp = 5 * (int)sm.lanerank[plane] + 1 + last;
-                pos_copy = pp < pos_copy ? pp : pos_copy;
+            // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference.
+            // Which pairs merge only changes when the beam set changes, so the pairing (plane,
+            // killw) is state; per frame only the parent's extension score has to be fetched.
+            if (any_plane) {
+                *reinterpret_cast<double2 *>(&sm.ex[li * 4]) = make_double2(e0, e1);
+                *reinterpret_cast<double2 *>(&sm.ex[li * 4 + 2]) = make_double2(e2, e3);
+                __syncwarp(gmask);
+                if (alive && plane >= 0) {
+                    const double v = sm.ex[plane * 4 + last];
+                    npnb = __dadd_rn(npnb, v);
+                    nptot = __dadd_rn(nptot, v);
+                }
             }
-            __syncwarp(gmask);
-            const uint32_t killw = sm.kill[li];
 
-            // SELECT the best beam_width candidates (decode.py:145, 35-39).  Candidates below the
-            // worst copy cannot enter the beam when the beam is full; the rest is ranked.
+            // SELECT the best beam_width candidates (decode.py:145, 35-39).
+            // Most frames change nothing but the scores: the rank order is kept as state (succ =
+            // lane of the next-ranked beam) and re-validated with one compare per beam; an
+            // extension matters only if it is not below the worst copy of a full beam.
             const unsigned long long kcopy = (unsigned long long)__double_as_longlong(nptot);
             const uint32_t kc32 = alive ? (uint32_t)(kcopy >> 32) : 0u;
+            const uint32_t ksucc = __shfl_sync(gmask, kc32, succ >= 0 ? succ + (int)gshift : lane);
+            const bool order_ok = __all_sync(gmask, !alive || succ < 0 || kc32 > ksucc);
             const bool prune = (na >= bw);
-            uint32_t tau = alive ? kc32 : 0xffffffffu;
+            uint32_t tau;
+            if (order_ok) {
+                tau = __shfl_sync(gmask, kc32, last_lane);
+            } else {
+                tau = alive ? kc32 : 0xffffffffu;
 #pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) {
-                const uint32_t x = __shfl_xor_sync(gmask, tau, o);
-                tau = x < tau ? x : tau;
-            }
-            int n_ext = 0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double ec = c == 0 ? e0 : c == 1 ? e1 : c == 2 ? e2 : e3;
-                const unsigned long long kc = (unsigned long long)__double_as_longlong(ec);
-                const uint32_t kh = (uint32_t)(kc >> 32);
-                const bool comp = alive && !((killw >> (8 * c)) & 1u) && (!prune || kh >= tau);
-                const unsigned bal = __ballot_sync(gmask, comp);
-                if (comp) {
-                    const int idx = G + n_ext + __popc(bal & below);
-                    sm.key[idx] = kc;
-                    sm.pos[idx] = (uint16_t)(5 * rank + 1 + c);
-                    sm.src[idx] = (uint8_t)(li * 4 + c);
-                    if (idx < NK) sm.k32[idx] = kh;
+                for (int o = G / 2; o > 0; o >>= 1) {
+                    const uint32_t x = __shfl_xor_sync(gmask, tau, o);
+                    tau = x < tau ? x : tau;
                 }
-                n_ext += __popc(bal);
             }
-            sm.k32[li] = kc32;
-            __syncwarp(gmask);
-            const int m = G + n_ext;
-            int new_rank = 255;
-            bool fast = (m <= NK);
-            if (fast) {
-                // rank = number of candidates with a strictly larger high word.  Exact whenever
-                // the high words of the ranked candidates are all distinct, which the rank sum
-                // proves (any tie makes the sum fall short of mv(mv-1)/2).
-                uint32_t ke[EPL];
-                int ce[EPL];
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) {
-                    ke[e] = sm.k32[G + e * G + li];
-                    ce[e] = 0;
-                }
+            const uint32_t kh0 = (uint32_t)__double2hiint(e0), kh1 = (uint32_t)__double2hiint(e1);
+            const uint32_t kh2 = (uint32_t)__double2hiint(e2), kh3 = (uint32_t)__double2hiint(e3);
+            const bool comp0 = alive && !(killw & 1u) && (!prune || kh0 >= tau);
+            const bool comp1 = alive && !(killw & 2u) && (!prune || kh1 >= tau);
+            const bool comp2 = alive && !(killw & 4u) && (!prune || kh2 >= tau);
+            const bool comp3 = alive && !(killw & 8u) && (!prune || kh3 >= tau);
+            bool full = __any_sync(gmask, comp0 || comp1 || comp2 || comp3);
+            bool ranks_changed = false;
+
+            if (!full && !order_ok) {
+                // copies changed order among themselves: rank them on the high words alone
+                sm.k32[li] = kc32;
+                __syncwarp(gmask);
                 int cc = 0;
                 const uint4 *kv = reinterpret_cast<const uint4 *>(sm.k32);
 #pragma unroll
-                for (int j = 0; j < NK / 4; ++j) {
+                for (int j = 0; j < G / 4; ++j) {
                     const uint4 k4 = kv[j];
                     cc += (k4.x > kc32) + (k4.y > kc32) + (k4.z > kc32) + (k4.w > kc32);
-#pragma unroll
-                    for (int e = 0; e < EPL; ++e)
-                        ce[e] += (k4.x > ke[e]) + (k4.y > ke[e]) + (k4.z > ke[e]) + (k4.w > ke[e]);
                 }
                 int ssum = alive ? cc : 0;
 #pragma unroll
-                for (int e = 0; e < EPL; ++e)
-                    if (e * G + li < n_ext) ssum += ce[e];
-#pragma unroll
                 for (int o = G / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(gmask, ssum, o);
-                const int mv = na + n_ext;
-                fast = (ssum == mv * (mv - 1) / 2);
+                if (ssum == na * (na - 1) / 2) {
+                    if (alive) rank = cc;
+                    ranks_changed = true;
+                } else {
+                    full = true;  // two copies share a high word: exact ranking below
+                }
+                __syncwarp(gmask);
+            }
+
+            if (!full) {
+                if (alive) {
+                    ptot = nptot;
+                    pnb = npnb;
+                    pb = npb;
+                }
+            } else {
+                ranks_changed = true;
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) sm.k32[G + e * G + li] = 0u;
+                __syncwarp(gmask);
+                int n_ext = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double ec = c == 0 ? e0 : c == 1 ? e1 : c == 2 ? e2 : e3;
+                    const bool comp = c == 0 ? comp0 : c == 1 ? comp1 : c == 2 ? comp2 : comp3;
+                    const unsigned bal = __ballot_sync(gmask, comp);
+                    if (comp) {
+                        const int idx = G + n_ext + __popc(bal & below);
+                        const unsigned long long kc = (unsigned long long)__double_as_longlong(ec);
+                        sm.key[idx] = kc;
+                        sm.pos[idx] = (uint16_t)(5 * rank + 1 + c);
+                        sm.src[idx] = (uint8_t)(li * 4 + c);
+                        if (idx < NK) sm.k32[idx] = (uint32_t)(kc >> 32);
+                    }
+                    n_ext += __popc(bal);
+                }
+                sm.k32[li] = kc32;
+                sm.lanerank[li] = (uint8_t)rank;
+                __syncwarp(gmask);
+                const int m = G + n_ext;
+                int new_rank = 255;
+                bool fast = (m <= NK);
                 if (fast) {
-                    new_rank = alive ? cc : 255;
+                    // rank = number of candidates with a strictly larger high word.  Exact whenever
+                    // the high words of the ranked candidates are all distinct, which the rank sum
+                    // proves (any tie makes the sum fall short of mv(mv-1)/2).
+                    uint32_t ke[EPL];
+                    int ce[EPL];
+#pragma unroll
+                    for (int e = 0; e < EPL; ++e) {
+                        ke[e] = sm.k32[G + e * G + li];
+                        ce[e] = 0;
+                    }
+                    int cc = 0;
+                    const uint4 *kv = reinterpret_cast<const uint4 *>(sm.k32);
+#pragma unroll
+                    for (int j = 0; j < NK / 4; ++j) {
+                        const uint4 k4 = kv[j];
+                        cc += (k4.x > kc32) + (k4.y > kc32) + (k4.z > kc32) + (k4.w > kc32);
+#pragma unroll
+                        for (int e = 0; e < EPL; ++e)
+                            ce[e] += (k4.x > ke[e]) + (k4.y > ke[e]) + (k4.z > ke[e]) + (k4.w > ke[e]);
+                    }
+                    int ssum = alive ? cc : 0;
 #pragma unroll
                     for (int e = 0; e < EPL; ++e)
-                        if (e * G + li < n_ext) sm.rnk[G + e * G + li] = (uint8_t)ce[e];
-                }
-            }
-            if (!fast) {
-                // exact path: (score desc, dict insertion position asc) on the full float64 bits
-                sm.key[li] = kcopy;
-                sm.pos[li] = alive ? (uint16_t)pos_copy : kPosInvalid;
-                __syncwarp(gmask);
-                for (int idx = li; idx < m; idx += G) {
-                    const uint16_t p = sm.pos[idx];
-                    if (p != kPosInvalid) {
-                        const unsigned long long k = sm.key[idx];
-                        int cnt = 0;
-                        for (int j = 0; j < m; ++j) {
-                            const uint16_t pj = sm.pos[j];
-                            const unsigned long long kj = sm.key[j];
-                            cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
-                        }
-                        sm.rnk[idx] = (uint8_t)(cnt > 255 ? 255 : cnt);
+                        if (e * G + li < n_ext) ssum += ce[e];
+#pragma unroll
+                    for (int o = G / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(gmask, ssum, o);
+                    const int mv = na + n_ext;
+                    fast = (ssum == mv * (mv - 1) / 2);
+                    if (fast) {
+                        new_rank = alive ? cc : 255;
+#pragma unroll
+                        for (int e = 0; e < EPL; ++e)
+                            if (e * G + li < n_ext) sm.rnk[G + e * G + li] = (uint8_t)ce[e];
                     }
                 }
-                __syncwarp(gmask);
-                new_rank = alive ? (int)sm.rnk[li] : 255;
-            } else {
-                __syncwarp(gmask);
-            }
-
-            const bool survive = alive && new_rank < bw;
-            const unsigned evmask = __ballot_sync(gmask, alive && !survive);
-            const unsigned survmask = __ballot_sync(gmask, survive);
-            const unsigned freemask = gmask & ~survmask;
-            int n_new = 0;
-            for (int base = G; base < m; base += G) {
-                const int idx = base + li;
-                const bool isnew = idx < m && sm.rnk[idx] < bw;
-                const unsigned bal = __ballot_sync(gmask, isnew);
-                if (isnew) sm.newlist[n_new + __popc(bal & below)] = (uint8_t)idx;
-                n_new += __popc(bal);
-            }
-
-            if (n_new > 0) {
-                __syncwarp(gmask);
-                const int ford = __popc(freemask & below);
-                const bool take = !survive && ford < n_new;
-                const int item = take ? (int)sm.newlist[ford] : 0;
-                const int s = take ? (int)sm.src[item] : li * 4;
-                const int ls = (s >> 2) + (int)gshift;
-                const int c = s & 3;
-                // parent state, read before anybody overwrites it
-                const uint32_t p_ctx = __shfl_sync(gmask, ctx, ls);
-                const int p_len = __shfl_sync(gmask, len, ls);
-                const int p_node = __shfl_sync(gmask, node, ls);
-                const unsigned long long p_h = __shfl_sync(gmask, h, ls);
-                double p_r = 0.0;
-                bool p_g = false;
-                if (LM) {
-                    const double r0 = __shfl_sync(gmask, rext0, ls);
-                    const double r1 = __shfl_sync(gmask, rext1, ls);
-                    const double r2 = __shfl_sync(gmask, rext2, ls);
-                    const double r3 = __shfl_sync(gmask, rext3, ls);
-                    p_r = c == 0 ? r0 : c == 1 ? r1 : c == 2 ? r2 : r3;
-                    p_g = __shfl_sync(gmask, (int)gext, ls) != 0;
+                if (!fast) {
+                    // exact path: (score desc, dict insertion position asc) on the full float64 bits;
+                    // a merged copy keeps the earlier of its two insertion positions
+                    int pos_copy = 5 * rank;
+                    if (alive && plane >= 0) {
+                        const int pp = 5 * (int)sm.lanerank[plane] + 1 + last;
+                        pos_copy = pp < pos_copy ? pp : pos_copy;
+                    }
+                    sm.key[li] = kcopy;
+                    sm.pos[li] = alive ? (uint16_t)pos_copy : kPosInvalid;
+                    __syncwarp(gmask);
+                    for (int idx = li; idx < m; idx += G) {
+                        const uint16_t p = sm.pos[idx];
+                        if (p != kPosInvalid) {
+                            const unsigned long long k = sm.key[idx];
+                            int cnt = 0;
+                            for (int j = 0; j < m; ++j) {
+                                const uint16_t pj = sm.pos[j];
+                                const unsigned long long kj = sm.key[j];
+                                cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
+                            }
+                            sm.rnk[idx] = (uint8_t)(cnt > 255 ? 255 : cnt);
+                        }
+                    }
+                    __syncwarp(gmask);
+                    new_rank = alive ? (int)sm.rnk[li] : 255;
+                } else {
+                    __syncwarp(gmask);
                 }
-                if (survive) {
-                    ptot = nptot;
-                    pnb = npnb;
-                    pb = npb;
-                    rank = new_rank;
-                    if (plane >= 0 && ((evmask >> (gshift + plane)) & 1u)) plane = -1;
-                } else if (take) {
-                    const double sc = __longlong_as_double((long long)sm.key[item]);
-                    ptot = sc;
-                    pnb = sc;
-                    pb = 0.0;
-                    rank = (int)sm.rnk[item];
-                    node = top + ford;
-                    len = p_len + 1;
-                    ctx = (p_ctx << 2) | (uint32_t)c;
-                    last = c;
-                    hp = p_h;
-                    h = hash_step(p_h, c);
-                    plane = ((survmask >> ls) & 1u) ? (ls - (int)gshift) : -1;
-                    alive = true;
-                    arena[node] = ((uint32_t)p_node << 2) | (uint32_t)c;
+
+                const bool survive = alive && new_rank < bw;
+                const unsigned evmask = __ballot_sync(gmask, alive && !survive);
+                const unsigned survmask = __ballot_sync(gmask, survive);
+                const unsigned freemask = gmask & ~survmask;
+                int n_new = 0;
+                for (int base = G; base < m; base += G) {
+                    const int idx = base + li;
+                    const bool isnew = idx < m && sm.rnk[idx] < bw;
+                    const unsigned bal = __ballot_sync(gmask, isnew);
+                    if (isnew) sm.newlist[n_new + __popc(bal & below)] = (uint8_t)idx;
+                    n_new += __popc(bal);
+                }
+
+                if (n_new > 0) {
+                    __syncwarp(gmask);
+                    const int ford = __popc(freemask & below);
+                    const bool take = !survive && ford < n_new;
+                    const int item = take ? (int)sm.newlist[ford] : 0;
+                    const int s = take ? (int)sm.src[item] : li * 4;
+                    const int ls = (s >> 2) + (int)gshift;
+                    const int c = s & 3;
+                    // parent state, read before anybody overwrites it
+                    const uint32_t p_ctx = __shfl_sync(gmask, ctx, ls);
+                    const int p_len = __shfl_sync(gmask, len, ls);
+                    const int p_node = __shfl_sync(gmask, node, ls);
+                    const unsigned long long p_h = __shfl_sync(gmask, h, ls);
+                    double p_r = 0.0;
+                    bool p_g = false;
                     if (LM) {
-                        gcopy = p_g;
-                        rcopy = p_r;
-                        gext = false;
-                        if (len >= L) {
-                            const uint32_t ci = ctx & ctx_mask;
-                            const uint32_t gwd = __ldg(a.gate + (ci >> 5));
-                            const double2 *row = reinterpret_cast<const double2 *>(a.table + (size_t)ci * 4);
-                            const double2 ra = __ldg(row), rb = __ldg(row + 1);
-                            gext = (gwd >> (ci & 31u)) & 1u;
-                            rext0 = ra.x;
-                            rext1 = ra.y;
-                            rext2 = rb.x;
-                            rext3 = rb.y;
-                        }
+                        const double r0 = __shfl_sync(gmask, rext0, ls);
+                        const double r1 = __shfl_sync(gmask, rext1, ls);
+                        const double r2 = __shfl_sync(gmask, rext2, ls);
+                        const double r3 = __shfl_sync(gmask, rext3, ls);
+                        p_r = c == 0 ? r0 : c == 1 ? r1 : c == 2 ? r2 : r3;
+                        p_g = __shfl_sync(gmask, (int)gext, ls) != 0;
                     }
+                    if (survive) {
+                        ptot = nptot;
+                        pnb = npnb;
+                        pb = npb;
+                        rank = new_rank;
+                        if (plane >= 0 && ((evmask >> (gshift + plane)) & 1u)) plane = -1;
+                    } else if (take) {
+                        const double sc = __longlong_as_double((long long)sm.key[item]);
+                        ptot = sc;
+                        pnb = sc;
+                        pb = 0.0;
+                        rank = (int)sm.rnk[item];
+                        node = top + ford;
+                        len = p_len + 1;
+                        ctx = (p_ctx << 2) | (uint32_t)c;
+                        last = c;
+                        hp = p_h;
+                        h = hash_step(p_h, c);
+                        plane = ((survmask >> ls) & 1u) ? (ls - (int)gshift) : -1;
+                        alive = true;
+                        arena[node] = ((uint32_t)p_node << 2) | (uint32_t)c;
+                        if (LM) {
+                            gcopy = p_g;
+                            rcopy = p_r;
+                            gext = false;
+                            if (len >= L) {
+                                const uint32_t ci = ctx & ctx_mask;
+                                const uint32_t gwd = __ldg(a.gate + (ci >> 5));
+                                const double2 *row = reinterpret_cast<const double2 *>(a.table + (size_t)ci * 4);
+                                const double2 ra = __ldg(row), rb = __ldg(row + 1);
+                                gext = (gwd >> (ci & 31u)) & 1u;
+                                rext0 = ra.x;
+                                rext1 = ra.y;
+                                rext2 = rb.x;
+                                rext3 = rb.y;
+                            }
+                        }
+                    } else {
+                        alive = false;
+                    }
+                    top += n_new;
+                    // a surviving beam whose parent labeling was just (re)created points at it
+                    // again: compare parent hash + length with every new beam
+                    unsigned nm = __ballot_sync(gmask, take);
+                    while (nm) {
+                        const int zl = __ffs(nm) - 1;
+                        nm &= nm - 1;
+                        const unsigned long long zh = __shfl_sync(gmask, h, zl);
+                        const int zlen = __shfl_sync(gmask, len, zl);
+                        if (survive && plane < 0 && len == zlen + 1 && hp == zh && len > 0) plane = zl - (int)gshift;
+                    }
+                    na = __popc(survmask) + n_new;
+                    // the beam set changed: refresh which extensions are merged into a live child
+                    sm.kill[li] = 0u;
+                    __syncwarp(gmask);
+                    if (alive && plane >= 0) reinterpret_cast<uint8_t *>(sm.kill)[plane * 4 + last] = 1;
+                    __syncwarp(gmask);
+                    {
+                        const uint32_t kw = sm.kill[li];
+                        killw = (kw & 1u) | ((kw >> 7) & 2u) | ((kw >> 14) & 4u) | ((kw >> 21) & 8u);
+                    }
+                    any_plane = __any_sync(gmask, alive && plane >= 0);
                 } else {
-                    alive = false;
+                    if (survive) {
+                        ptot = nptot;
+                        pnb = npnb;
+                        pb = npb;
+                        rank = new_rank;
+                    }
                 }
-                top += n_new;
-                // a surviving beam whose parent labeling was just (re)created points at it
-                // again: compare parent hash + length with every new beam
-                unsigned nm = __ballot_sync(gmask, take);
-                while (nm) {
-                    const int zl = __ffs(nm) - 1;
-                    nm &= nm - 1;
-                    const unsigned long long zh = __shfl_sync(gmask, h, zl);
-                    const int zlen = __shfl_sync(gmask, len, zl);
-                    if (survive && plane < 0 && len == zlen + 1 && hp == zh && len > 0) plane = zl - (int)gshift;
-                }
-                na = __popc(survmask) + n_new;
-            } else {
-                if (survive) {
-                    ptot = nptot;
-                    pnb = npnb;
-                    pb = npb;
-                    rank = new_rank;
-                    if (plane >= 0 && ((evmask >> (gshift + plane)) & 1u)) plane = -1;
-                } else {
-                    alive = false;
-                }
-                na = __popc(survmask);
+            }
+            if (ranks_changed) {
+                // successor lane of every beam, first and last lane of the order
+                if (alive) sm.newlist[rank] = (uint8_t)li;
+                __syncwarp(gmask);
+                succ = (alive && rank + 1 < na) ? (int)sm.newlist[rank + 1] : -1;
+                first_lane = (int)sm.newlist[0] + (int)gshift;
+                last_lane = (int)sm.newlist[na - 1] + (int)gshift;
+                __syncwarp(gmask);
             }
 
             // RESCALE by the exponent of the best beam (exact)
             {
-                const unsigned bb = __ballot_sync(gmask, alive && rank == 0);
-                const int bl = __ffs(bb) - 1;
-                const int hi = __shfl_sync(gmask, __double2hiint(ptot), bl);
+                const int hi = __shfl_sync(gmask, __double2hiint(ptot), first_lane);
                 const int ex = (hi >> 20) & 0x7ff;
                 if (ex != 0 && ex != 0x7ff) {
                     const double sc = __hiloint2double((2046 - ex) << 20, 0);
