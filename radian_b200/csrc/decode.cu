@@ -132,6 +132,10 @@ __device__ __forceinline__ void make_record(const float (&v)[5], double s_thr, d
     }
 }
 
+// Control flow is warp-uniform everywhere: a warp carries 32/G reads, and every branch that
+// contains a warp collective is taken by all of them together (decided by a full-mask vote), so
+// all shuffles and votes use the full mask and each group extracts its own lanes' bits.  Sub-warp
+// masks would make the compiler emit a convergence check per collective and serialise the groups.
 template <int G, bool LM, typename PT, bool COUNT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 decode_kernel(const DecodeArgs a)
@@ -140,27 +144,28 @@ decode_kernel(const DecodeArgs a)
     constexpr int REC = GroupSmem<G, LM>::REC;
     constexpr int NK = GroupSmem<G, LM>::NK;
     constexpr int EPL = (NK - G) / G;  // extension slots ranked by each lane on the fast path
+    constexpr unsigned GBITS = (G == 32) ? kFull : ((1u << G) - 1u);
     __shared__ GroupSmem<G, LM> smem[kWarpsPerBlock * GPW];
 
     const int lane = threadIdx.x & 31;
     const int li = lane % G;
     const int gw = lane / G;
-    const unsigned gshift = gw * G;
-    const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << gshift);
-    const unsigned below = gmask & ((1u << lane) - 1u);
+    const int gshift = gw * G;
+    const unsigned belowg = (1u << li) - 1u;  // lanes of my group below me, group-relative bits
     const int gib = (threadIdx.x >> 5) * GPW + gw;  // group in block
     GroupSmem<G, LM> &sm = smem[gib];
     const int slot = blockIdx.x * (kWarpsPerBlock * GPW) + gib;
+    // votes: bits of my group's lanes, group-relative
+#define GBALLOT(p) ((__ballot_sync(kFull, (p)) >> gshift) & GBITS)
 
     const int bw = a.beam_width;
     const int L = a.L;
     const uint32_t ctx_mask = LM ? (uint32_t)((1ull << (2 * L)) - 1ull) : 0u;
-    const PT *post_all = (const PT *)a.post;
     const int cap = a.arena_cap;
     uint32_t *const arena = a.arena + (size_t)slot * (size_t)(cap + kNursery);
     uint32_t *const fwd = arena + cap;
 
-    // ---- per-beam (lane) state
+    // ---- per-beam (lane) state; a dead lane keeps all three probabilities at zero
     double ptot = 0.0, pnb = 0.0, pb = 0.0;
     unsigned long long h = 0, hp = 0;
     uint32_t ctx = 0;
@@ -168,91 +173,91 @@ decode_kernel(const DecodeArgs a)
     bool alive = false;
     double rext0 = 0, rext1 = 0, rext2 = 0, rext3 = 0, rcopy = 0;
     bool gext = false, gcopy = false;
-    int succ = -1;          // lane (in group) of the beam ranked right after this one
-    uint32_t killw = 0;     // bit c: extension by c is merged into a live child's copy
+    int succ = -1;       // lane (in group) of the beam ranked right after this one
+    uint32_t killw = 0;  // bit c: extension by c is merged into a live child's copy
     // ---- per-read (group-uniform) state
-    int read = -1, top = 0, old_top = 0, na = 0, status = 0, first_lane = 0, last_lane = 0;
-    bool any_plane = false;
-    long long T = 0, t = 0, foff = 0, kacc = 0, seq_off = 0, seq_cap = 0;
+    int read = -1, top = 0, old_top = 0, na = 0, status = 0, first_lane = 0;
+    int T = 0, t = 0;
+    long long kacc = 0;
+    const PT *rp = (const PT *)a.post;
     unsigned long long n_lookup = 0, n_combine = 0;
     PT pf[5];
     bool active = true;
 
     while (true) {
         // ------------------------------------------------------------ fetch a read
-        if (active && read < 0) {
+        {
+            const bool want = active && read < 0;
             int idx = 0;
-            if (li == 0) idx = atomicAdd(a.queue, 1);
-            idx = __shfl_sync(gmask, idx, gshift);
-            if (idx >= a.n_reads) {
-                active = false;
-            } else {
-                read = a.order ? a.order[idx] : idx;
-                foff = a.frame_offsets[read];
-                T = a.frame_offsets[read + 1] - foff;
-                seq_off = a.seq_offsets[read];
-                seq_cap = a.seq_offsets[read + 1] - seq_off;
-                t = 0;
-                // initial beam: the empty labeling, pr_blank = pr_total = log 1 (decode.py:128-132)
-                alive = (li == 0);
-                ptot = alive ? 1.0 : 0.0;
-                pb = ptot;
-                pnb = 0.0;
-                h = 0x243F6A8885A308D3ull;
-                hp = 0;
-                ctx = 0;
-                len = 0;
-                node = 0;
-                rank = 0;
-                plane = -1;
-                last = 0;
-                gext = gcopy = false;
-                succ = -1;
-                killw = 0;
-                any_plane = false;
-                first_lane = last_lane = (int)gshift;
-                top = 1;  // node 0 = the empty labeling
-                old_top = 1;
-                na = 1;
-                status = 0;
-                kacc = 0;
-                n_lookup = n_combine = 0;
-                if (li < T) load_row(post_all + foff * 5, li, pf);
+            if (want && li == 0) idx = atomicAdd(a.queue, 1);
+            idx = __shfl_sync(kFull, idx, gshift);
+            if (want) {
+                if (idx >= a.n_reads) {
+                    active = false;
+                } else {
+                    read = a.order ? a.order[idx] : idx;
+                    const long long foff = a.frame_offsets[read];
+                    T = (int)(a.frame_offsets[read + 1] - foff);
+                    rp = (const PT *)a.post + foff * 5;
+                    t = 0;
+                    // initial beam: the empty labeling, pr_blank = pr_total = log 1 (decode.py:128-132)
+                    alive = (li == 0);
+                    ptot = alive ? 1.0 : 0.0;
+                    pb = ptot;
+                    pnb = 0.0;
+                    h = 0x243F6A8885A308D3ull;
+                    hp = 0;
+                    ctx = 0;
+                    len = 0;
+                    node = 0;
+                    rank = 0;
+                    plane = -1;
+                    last = 0;
+                    gext = gcopy = false;
+                    succ = -1;
+                    killw = 0;
+                    first_lane = gshift;
+                    top = 1;  // node 0 = the empty labeling
+                    old_top = 1;
+                    na = 1;
+                    status = 0;
+                    kacc = 0;
+                    n_lookup = n_combine = 0;
+                }
             }
         }
         if (!__any_sync(kFull, active)) break;
 
         // frames every active group of this warp can run before one of them finishes its read
-        int rem = 0x7fffffff;
-        if (active) rem = (T - t) > 0x7ffffffell ? 0x7ffffffe : (int)(T - t);
+        int rem = active ? (T - t) : 0x7fffffff;
         int nrun = rem;
 #pragma unroll
         for (int g = 0; g < GPW; ++g) {
             const int x = __shfl_sync(kFull, rem, g * G);
             nrun = x < nrun ? x : nrun;
         }
+        // (re)prime the frame tiles so that all groups of the warp refill at the same iterations
+        const int tb = t;
+        if (active && tb + li < T) load_row(rp, tb + li, pf);
 
         for (int it = 0; it < nrun; ++it) {
-            if (!active) continue;
-            if (status != 0) {
-                ++t;  // arena overflow: the read is reported as failed, its frames are skipped
-                continue;
-            }
+            bool run = active && status == 0;  // group-uniform
             // -------------------------------------------------------- tile refill
-            if ((t % G) == 0) {
-                __syncwarp(gmask);
-                if (t + li < T) make_record<LM>(pf, a.s_thr, &sm.rec[li * REC]);
-                if (t + G + li < T) load_row(post_all + foff * 5, t + G + li, pf);
-                __syncwarp(gmask);
+            if ((it % G) == 0) {
+                __syncwarp();
+                if (run && tb + it + li < T) make_record<LM>(pf, a.s_thr, &sm.rec[li * REC]);
+                if (run && tb + it + G + li < T) load_row(rp, tb + it + G + li, pf);
+                __syncwarp();
             }
 
             // -------------------------------------------------------- nursery collection
-            if (top + G > old_top + kNursery || top + G > cap) {
+            if (__any_sync(kFull, run && (top + G > old_top + kNursery || top + G > cap))) {
+                // every running group of the warp collects (early collection is harmless)
                 // 1. mark nursery nodes reachable from a live beam (stop at the old generation or
                 //    at a node somebody marked in an earlier step)
                 int cur = node;
-                bool walking = alive && cur >= old_top;
-                while (__any_sync(gmask, walking)) {
+                bool walking = run && alive && cur >= old_top;
+                while (__any_sync(kFull, walking)) {
                     if (walking) {
                         const uint32_t w = arena[cur];
                         if (w >> 31) {
@@ -263,48 +268,55 @@ decode_kernel(const DecodeArgs a)
                             walking = cur >= old_top;
                         }
                     }
-                    __syncwarp(gmask);
+                    __syncwarp();
                 }
                 // 2. slide marked nodes down in index order (parents always precede children);
                 //    fwd[] keeps the new index of every moved node for its children and the beams
+                int iters = run ? (top - old_top + G - 1) / G : 0;
+#pragma unroll
+                for (int o = 16; o >= G; o >>= 1) {
+                    const int x = __shfl_xor_sync(kFull, iters, o);
+                    iters = x > iters ? x : iters;
+                }
                 int cnt = old_top;
-                for (int base = old_top; base < top; base += G) {
+                for (int k = 0; k < iters; ++k) {
+                    const int base = old_top + k * G;
                     const int i = base + li;
-                    const uint32_t w = (i < top) ? arena[i] : 0u;
+                    const uint32_t w = (run && i < top) ? arena[i] : 0u;
                     const bool mk = (w >> 31) != 0;
-                    const unsigned bal = __ballot_sync(gmask, mk);
-                    const int ni = cnt + __popc(bal & below);
+                    const unsigned bal = GBALLOT(mk);
+                    const int ni = cnt + __popc(bal & belowg);
                     const int par = (int)((w & 0x7fffffffu) >> 2);
                     int npar = par;
                     if (mk && par >= old_top) {
-                        if (par >= base) {
-                            const unsigned pm = gmask & ((1u << (gshift + (par - base))) - 1u);
-                            npar = cnt + __popc(bal & pm);
-                        } else {
+                        if (par >= base)
+                            npar = cnt + __popc(bal & ((1u << (par - base)) - 1u));
+                        else
                             npar = (int)fwd[par - old_top];
-                        }
                     }
-                    __syncwarp(gmask);
+                    __syncwarp();
                     if (mk) {
                         arena[ni] = ((uint32_t)npar << 2) | (w & 3u);
                         fwd[i - old_top] = (uint32_t)ni;
                     }
                     cnt += __popc(bal);
-                    __syncwarp(gmask);
+                    __syncwarp();
                 }
-                if (alive && node >= old_top) node = (int)fwd[node - old_top];
-                __syncwarp(gmask);
-                old_top = cnt;
-                top = cnt;
-                if (top + G > cap) {
-                    status = RADIAN_READ_TRIE_OVERFLOW;
-                    ++t;
-                    continue;
+                if (run && alive && node >= old_top) node = (int)fwd[node - old_top];
+                __syncwarp();
+                if (run) {
+                    old_top = cnt;
+                    top = cnt;
+                    if (top + G > cap) {
+                        status = RADIAN_READ_TRIE_OVERFLOW;  // reported; remaining frames are skipped
+                        run = false;
+                    }
                 }
             }
+            const bool av = alive && run;  // this lane holds a beam that takes part in this frame
 
             // -------------------------------------------------------- one frame
-            const double *rec = &sm.rec[(int)(t % G) * REC];
+            const double *rec = &sm.rec[(it % G) * REC];
             const double P4 = rec[4];
             const double2 P01 = *reinterpret_cast<const double2 *>(rec);
             const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
@@ -313,19 +325,16 @@ decode_kernel(const DecodeArgs a)
             double S = 0.0;
             if (LM) {
                 fgate = rec[5] != 0.0;
-                if (fgate) {
-                    q01 = *reinterpret_cast<const double2 *>(rec + 6);
-                    q23 = *reinterpret_cast<const double2 *>(rec + 8);
-                    S = rec[10];
-                }
+                q01 = *reinterpret_cast<const double2 *>(rec + 6);
+                q23 = *reinterpret_cast<const double2 *>(rec + 8);
+                S = rec[10];
             }
-            const bool has_last = alive && len > 0;
-            const bool lm_copy = LM && alive && len >= L + 1;  // decode.py:157
-            const bool lm_ext = LM && alive && len >= L;       // decode.py:180
+            const bool has_last = av && len > 0;
+            const bool lm_copy = LM && av && len >= L + 1;  // decode.py:157
+            const bool lm_ext = LM && av && len >= L;       // decode.py:180
             if (COUNT && LM) {
-                n_lookup += __popc(__ballot_sync(gmask, lm_copy)) + __popc(__ballot_sync(gmask, lm_ext));
-                n_combine += __popc(__ballot_sync(gmask, lm_copy && gcopy && fgate)) +
-                             __popc(__ballot_sync(gmask, lm_ext && gext && fgate));
+                n_lookup += __popc(GBALLOT(lm_copy)) + __popc(GBALLOT(lm_ext));
+                n_combine += __popc(GBALLOT(lm_copy && gcopy && fgate)) + __popc(GBALLOT(lm_ext && gext && fgate));
             }
 
             // COPY (decode.py:150-175)
@@ -346,26 +355,23 @@ decode_kernel(const DecodeArgs a)
                 d2 = __dmul_rn(__dmul_rn(__dadd_rn(rext2, q23.x), 0.5), S);
                 d3 = __dmul_rn(__dmul_rn(__dadd_rn(rext3, q23.y), 0.5), S);
             }
-            double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-            if (alive) {
-                e0 = __dmul_rn((has_last && last == 0) ? pb : ptot, d0);  // decode.py:192-195
-                e1 = __dmul_rn((has_last && last == 1) ? pb : ptot, d1);
-                e2 = __dmul_rn((has_last && last == 2) ? pb : ptot, d2);
-                e3 = __dmul_rn((has_last && last == 3) ? pb : ptot, d3);
-            }
+            // a repeated symbol continues only paths that ended in a blank (decode.py:192-195)
+            const int lrep = has_last ? last : -1;
+            const double e0 = __dmul_rn(lrep == 0 ? pb : ptot, d0);
+            const double e1 = __dmul_rn(lrep == 1 ? pb : ptot, d1);
+            const double e2 = __dmul_rn(lrep == 2 ? pb : ptot, d2);
+            const double e3 = __dmul_rn(lrep == 3 ? pb : ptot, d3);
 
             // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference.
             // Which pairs merge only changes when the beam set changes, so the pairing (plane,
             // killw) is state; per frame only the parent's extension score has to be fetched.
-            if (any_plane) {
-                *reinterpret_cast<double2 *>(&sm.ex[li * 4]) = make_double2(e0, e1);
-                *reinterpret_cast<double2 *>(&sm.ex[li * 4 + 2]) = make_double2(e2, e3);
-                __syncwarp(gmask);
-                if (alive && plane >= 0) {
-                    const double v = sm.ex[plane * 4 + last];
-                    npnb = __dadd_rn(npnb, v);
-                    nptot = __dadd_rn(nptot, v);
-                }
+            *reinterpret_cast<double2 *>(&sm.ex[li * 4]) = make_double2(e0, e1);
+            *reinterpret_cast<double2 *>(&sm.ex[li * 4 + 2]) = make_double2(e2, e3);
+            __syncwarp();
+            if (av && plane >= 0) {
+                const double v = sm.ex[plane * 4 + last];
+                npnb = __dadd_rn(npnb, v);
+                nptot = __dadd_rn(nptot, v);
             }
 
             // SELECT the best beam_width candidates (decode.py:145, 35-39).
@@ -373,34 +379,27 @@ decode_kernel(const DecodeArgs a)
             // lane of the next-ranked beam) and re-validated with one compare per beam; an
             // extension matters only if it is not below the worst copy of a full beam.
             const unsigned long long kcopy = (unsigned long long)__double_as_longlong(nptot);
-            const uint32_t kc32 = alive ? (uint32_t)(kcopy >> 32) : 0u;
-            const uint32_t ksucc = __shfl_sync(gmask, kc32, succ >= 0 ? succ + (int)gshift : lane);
-            const bool order_ok = __all_sync(gmask, !alive || succ < 0 || kc32 > ksucc);
+            const uint32_t kc32 = av ? (uint32_t)(kcopy >> 32) : 0u;
+            const uint32_t ksucc = __shfl_sync(kFull, kc32, succ >= 0 ? succ + gshift : lane);
+            const bool order_ok = GBALLOT(!av || succ < 0 || kc32 > ksucc) == GBITS;
             const bool prune = (na >= bw);
-            uint32_t tau;
-            if (order_ok) {
-                tau = __shfl_sync(gmask, kc32, last_lane);
-            } else {
-                tau = alive ? kc32 : 0xffffffffu;
+            uint32_t tau = av ? kc32 : 0xffffffffu;
 #pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) {
-                    const uint32_t x = __shfl_xor_sync(gmask, tau, o);
-                    tau = x < tau ? x : tau;
-                }
+            for (int o = G / 2; o > 0; o >>= 1) {
+                const uint32_t x = __shfl_xor_sync(kFull, tau, o);
+                tau = x < tau ? x : tau;
             }
-            const uint32_t kh0 = (uint32_t)__double2hiint(e0), kh1 = (uint32_t)__double2hiint(e1);
-            const uint32_t kh2 = (uint32_t)__double2hiint(e2), kh3 = (uint32_t)__double2hiint(e3);
-            const bool comp0 = alive && !(killw & 1u) && (!prune || kh0 >= tau);
-            const bool comp1 = alive && !(killw & 2u) && (!prune || kh1 >= tau);
-            const bool comp2 = alive && !(killw & 4u) && (!prune || kh2 >= tau);
-            const bool comp3 = alive && !(killw & 8u) && (!prune || kh3 >= tau);
-            bool full = __any_sync(gmask, comp0 || comp1 || comp2 || comp3);
+            const bool comp0 = av && !(killw & 1u) && (!prune || (uint32_t)__double2hiint(e0) >= tau);
+            const bool comp1 = av && !(killw & 2u) && (!prune || (uint32_t)__double2hiint(e1) >= tau);
+            const bool comp2 = av && !(killw & 4u) && (!prune || (uint32_t)__double2hiint(e2) >= tau);
+            const bool comp3 = av && !(killw & 8u) && (!prune || (uint32_t)__double2hiint(e3) >= tau);
+            bool full = GBALLOT(comp0 || comp1 || comp2 || comp3) != 0u;  // my group needs a full ranking
             bool ranks_changed = false;
 
-            if (!full && !order_ok) {
+            if (__any_sync(kFull, !full && !order_ok)) {
                 // copies changed order among themselves: rank them on the high words alone
                 sm.k32[li] = kc32;
-                __syncwarp(gmask);
+                __syncwarp();
                 int cc = 0;
                 const uint4 *kv = reinterpret_cast<const uint4 *>(sm.k32);
 #pragma unroll
@@ -408,37 +407,41 @@ decode_kernel(const DecodeArgs a)
                     const uint4 k4 = kv[j];
                     cc += (k4.x > kc32) + (k4.y > kc32) + (k4.z > kc32) + (k4.w > kc32);
                 }
-                int ssum = alive ? cc : 0;
+                int ssum = av ? cc : 0;
 #pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(gmask, ssum, o);
-                if (ssum == na * (na - 1) / 2) {
-                    if (alive) rank = cc;
-                    ranks_changed = true;
-                } else {
-                    full = true;  // two copies share a high word: exact ranking below
+                for (int o = G / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(kFull, ssum, o);
+                if (!full && !order_ok) {
+                    if (ssum == na * (na - 1) / 2) {
+                        if (av) rank = cc;
+                        ranks_changed = true;
+                    } else {
+                        full = true;  // two copies share a high word: exact ranking below
+                    }
                 }
-                __syncwarp(gmask);
+                __syncwarp();
             }
 
-            if (!full) {
-                if (alive) {
+            if (!__any_sync(kFull, full)) {
+                if (av) {
                     ptot = nptot;
                     pnb = npnb;
                     pb = npb;
                 }
             } else {
-                ranks_changed = true;
+                // all groups of the warp go through the ranking; one that did not ask for it has no
+                // extension candidates and gets its current order back
+                ranks_changed = ranks_changed || run;
 #pragma unroll
                 for (int e = 0; e < EPL; ++e) sm.k32[G + e * G + li] = 0u;
-                __syncwarp(gmask);
+                __syncwarp();
                 int n_ext = 0;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const double ec = c == 0 ? e0 : c == 1 ? e1 : c == 2 ? e2 : e3;
-                    const bool comp = c == 0 ? comp0 : c == 1 ? comp1 : c == 2 ? comp2 : comp3;
-                    const unsigned bal = __ballot_sync(gmask, comp);
+                    const bool comp = full && (c == 0 ? comp0 : c == 1 ? comp1 : c == 2 ? comp2 : comp3);
+                    const unsigned bal = GBALLOT(comp);
                     if (comp) {
-                        const int idx = G + n_ext + __popc(bal & below);
+                        const int idx = G + n_ext + __popc(bal & belowg);
                         const unsigned long long kc = (unsigned long long)__double_as_longlong(ec);
                         sm.key[idx] = kc;
                         sm.pos[idx] = (uint16_t)(5 * rank + 1 + c);
@@ -449,11 +452,11 @@ decode_kernel(const DecodeArgs a)
                 }
                 sm.k32[li] = kc32;
                 sm.lanerank[li] = (uint8_t)rank;
-                __syncwarp(gmask);
+                __syncwarp();
                 const int m = G + n_ext;
                 int new_rank = 255;
                 bool fast = (m <= NK);
-                if (fast) {
+                {
                     // rank = number of candidates with a strictly larger high word.  Exact whenever
                     // the high words of the ranked candidates are all distinct, which the rank sum
                     // proves (any tie makes the sum fall short of mv(mv-1)/2).
@@ -474,93 +477,103 @@ decode_kernel(const DecodeArgs a)
                         for (int e = 0; e < EPL; ++e)
                             ce[e] += (k4.x > ke[e]) + (k4.y > ke[e]) + (k4.z > ke[e]) + (k4.w > ke[e]);
                     }
-                    int ssum = alive ? cc : 0;
+                    int ssum = av ? cc : 0;
 #pragma unroll
                     for (int e = 0; e < EPL; ++e)
                         if (e * G + li < n_ext) ssum += ce[e];
 #pragma unroll
-                    for (int o = G / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(gmask, ssum, o);
+                    for (int o = G / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(kFull, ssum, o);
                     const int mv = na + n_ext;
-                    fast = (ssum == mv * (mv - 1) / 2);
+                    fast = fast && (ssum == mv * (mv - 1) / 2);
                     if (fast) {
-                        new_rank = alive ? cc : 255;
+                        new_rank = av ? cc : 255;
 #pragma unroll
                         for (int e = 0; e < EPL; ++e)
                             if (e * G + li < n_ext) sm.rnk[G + e * G + li] = (uint8_t)ce[e];
                     }
                 }
-                if (!fast) {
+                if (__any_sync(kFull, run && !fast)) {
                     // exact path: (score desc, dict insertion position asc) on the full float64 bits;
                     // a merged copy keeps the earlier of its two insertion positions
-                    int pos_copy = 5 * rank;
-                    if (alive && plane >= 0) {
-                        const int pp = 5 * (int)sm.lanerank[plane] + 1 + last;
-                        pos_copy = pp < pos_copy ? pp : pos_copy;
+                    if (run && !fast) {
+                        int pos_copy = 5 * rank;
+                        if (av && plane >= 0) {
+                            const int pp = 5 * (int)sm.lanerank[plane] + 1 + last;
+                            pos_copy = pp < pos_copy ? pp : pos_copy;
+                        }
+                        sm.key[li] = kcopy;
+                        sm.pos[li] = av ? (uint16_t)pos_copy : kPosInvalid;
                     }
-                    sm.key[li] = kcopy;
-                    sm.pos[li] = alive ? (uint16_t)pos_copy : kPosInvalid;
-                    __syncwarp(gmask);
-                    for (int idx = li; idx < m; idx += G) {
-                        const uint16_t p = sm.pos[idx];
-                        if (p != kPosInvalid) {
-                            const unsigned long long k = sm.key[idx];
-                            int cnt = 0;
-                            for (int j = 0; j < m; ++j) {
-                                const uint16_t pj = sm.pos[j];
-                                const unsigned long long kj = sm.key[j];
-                                cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
+                    __syncwarp();
+                    if (run && !fast) {
+                        for (int idx = li; idx < m; idx += G) {
+                            const uint16_t p = sm.pos[idx];
+                            if (p != kPosInvalid) {
+                                const unsigned long long k = sm.key[idx];
+                                int cnt = 0;
+                                for (int j = 0; j < m; ++j) {
+                                    const uint16_t pj = sm.pos[j];
+                                    const unsigned long long kj = sm.key[j];
+                                    cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
+                                }
+                                sm.rnk[idx] = (uint8_t)(cnt > 255 ? 255 : cnt);
                             }
-                            sm.rnk[idx] = (uint8_t)(cnt > 255 ? 255 : cnt);
                         }
                     }
-                    __syncwarp(gmask);
-                    new_rank = alive ? (int)sm.rnk[li] : 255;
+                    __syncwarp();
+                    if (run && !fast) new_rank = av ? (int)sm.rnk[li] : 255;
                 } else {
-                    __syncwarp(gmask);
+                    __syncwarp();
                 }
 
-                const bool survive = alive && new_rank < bw;
-                const unsigned evmask = __ballot_sync(gmask, alive && !survive);
-                const unsigned survmask = __ballot_sync(gmask, survive);
-                const unsigned freemask = gmask & ~survmask;
+                const bool survive = av && new_rank < bw;
+                const unsigned evb = GBALLOT(av && !survive);
+                const unsigned survb = GBALLOT(survive);
+                const unsigned freeb = GBITS & ~survb;
+                int mmax = m;
+#pragma unroll
+                for (int o = 16; o >= G; o >>= 1) {
+                    const int x = __shfl_xor_sync(kFull, mmax, o);
+                    mmax = x > mmax ? x : mmax;
+                }
                 int n_new = 0;
-                for (int base = G; base < m; base += G) {
+                for (int base = G; base < mmax; base += G) {
                     const int idx = base + li;
-                    const bool isnew = idx < m && sm.rnk[idx] < bw;
-                    const unsigned bal = __ballot_sync(gmask, isnew);
-                    if (isnew) sm.newlist[n_new + __popc(bal & below)] = (uint8_t)idx;
+                    const bool isnew = run && idx < m && sm.rnk[idx] < bw;
+                    const unsigned bal = GBALLOT(isnew);
+                    if (isnew) sm.newlist[n_new + __popc(bal & belowg)] = (uint8_t)idx;
                     n_new += __popc(bal);
                 }
 
-                if (n_new > 0) {
-                    __syncwarp(gmask);
-                    const int ford = __popc(freemask & below);
-                    const bool take = !survive && ford < n_new;
+                if (__any_sync(kFull, n_new > 0)) {
+                    __syncwarp();
+                    const int ford = __popc(freeb & belowg);
+                    const bool take = run && !survive && ford < n_new;
                     const int item = take ? (int)sm.newlist[ford] : 0;
                     const int s = take ? (int)sm.src[item] : li * 4;
-                    const int ls = (s >> 2) + (int)gshift;
+                    const int ls = (s >> 2) + gshift;
                     const int c = s & 3;
                     // parent state, read before anybody overwrites it
-                    const uint32_t p_ctx = __shfl_sync(gmask, ctx, ls);
-                    const int p_len = __shfl_sync(gmask, len, ls);
-                    const int p_node = __shfl_sync(gmask, node, ls);
-                    const unsigned long long p_h = __shfl_sync(gmask, h, ls);
+                    const uint32_t p_ctx = __shfl_sync(kFull, ctx, ls);
+                    const int p_len = __shfl_sync(kFull, len, ls);
+                    const int p_node = __shfl_sync(kFull, node, ls);
+                    const unsigned long long p_h = __shfl_sync(kFull, h, ls);
                     double p_r = 0.0;
                     bool p_g = false;
                     if (LM) {
-                        const double r0 = __shfl_sync(gmask, rext0, ls);
-                        const double r1 = __shfl_sync(gmask, rext1, ls);
-                        const double r2 = __shfl_sync(gmask, rext2, ls);
-                        const double r3 = __shfl_sync(gmask, rext3, ls);
+                        const double r0 = __shfl_sync(kFull, rext0, ls);
+                        const double r1 = __shfl_sync(kFull, rext1, ls);
+                        const double r2 = __shfl_sync(kFull, rext2, ls);
+                        const double r3 = __shfl_sync(kFull, rext3, ls);
                         p_r = c == 0 ? r0 : c == 1 ? r1 : c == 2 ? r2 : r3;
-                        p_g = __shfl_sync(gmask, (int)gext, ls) != 0;
+                        p_g = __shfl_sync(kFull, (int)gext, ls) != 0;
                     }
                     if (survive) {
                         ptot = nptot;
                         pnb = npnb;
                         pb = npb;
                         rank = new_rank;
-                        if (plane >= 0 && ((evmask >> (gshift + plane)) & 1u)) plane = -1;
+                        if (plane >= 0 && ((evb >> plane) & 1u)) plane = -1;
                     } else if (take) {
                         const double sc = __longlong_as_double((long long)sm.key[item]);
                         ptot = sc;
@@ -573,7 +586,7 @@ decode_kernel(const DecodeArgs a)
                         last = c;
                         hp = p_h;
                         h = hash_step(p_h, c);
-                        plane = ((survmask >> ls) & 1u) ? (ls - (int)gshift) : -1;
+                        plane = ((survb >> (ls - gshift)) & 1u) ? (ls - gshift) : -1;
                         alive = true;
                         arena[node] = ((uint32_t)p_node << 2) | (uint32_t)c;
                         if (LM) {
@@ -592,55 +605,64 @@ decode_kernel(const DecodeArgs a)
                                 rext3 = rb.y;
                             }
                         }
-                    } else {
+                    } else if (run) {
                         alive = false;
+                        ptot = pnb = pb = 0.0;
                     }
-                    top += n_new;
+                    if (run) {
+                        top += n_new;
+                        na = __popc(survb) + n_new;
+                    }
                     // a surviving beam whose parent labeling was just (re)created points at it
                     // again: compare parent hash + length with every new beam
-                    unsigned nm = __ballot_sync(gmask, take);
-                    while (nm) {
-                        const int zl = __ffs(nm) - 1;
-                        nm &= nm - 1;
-                        const unsigned long long zh = __shfl_sync(gmask, h, zl);
-                        const int zlen = __shfl_sync(gmask, len, zl);
-                        if (survive && plane < 0 && len == zlen + 1 && hp == zh && len > 0) plane = zl - (int)gshift;
+                    unsigned nm = GBALLOT(take);
+                    int nmax = __popc(nm);
+#pragma unroll
+                    for (int o = 16; o >= G; o >>= 1) {
+                        const int x = __shfl_xor_sync(kFull, nmax, o);
+                        nmax = x > nmax ? x : nmax;
                     }
-                    na = __popc(survmask) + n_new;
+                    for (int k = 0; k < nmax; ++k) {
+                        const bool have = nm != 0u;
+                        const int zl = have ? __ffs(nm) - 1 : li;
+                        nm &= nm - 1;
+                        const unsigned long long zh = __shfl_sync(kFull, h, zl + gshift);
+                        const int zlen = __shfl_sync(kFull, len, zl + gshift);
+                        if (have && survive && plane < 0 && len == zlen + 1 && hp == zh && len > 0) plane = zl;
+                    }
                     // the beam set changed: refresh which extensions are merged into a live child
                     sm.kill[li] = 0u;
-                    __syncwarp(gmask);
-                    if (alive && plane >= 0) reinterpret_cast<uint8_t *>(sm.kill)[plane * 4 + last] = 1;
-                    __syncwarp(gmask);
-                    {
+                    __syncwarp();
+                    if (run && alive && plane >= 0) reinterpret_cast<uint8_t *>(sm.kill)[plane * 4 + last] = 1;
+                    __syncwarp();
+                    if (run) {
                         const uint32_t kw = sm.kill[li];
                         killw = (kw & 1u) | ((kw >> 7) & 2u) | ((kw >> 14) & 4u) | ((kw >> 21) & 8u);
                     }
-                    any_plane = __any_sync(gmask, alive && plane >= 0);
-                } else {
-                    if (survive) {
-                        ptot = nptot;
-                        pnb = npnb;
-                        pb = npb;
-                        rank = new_rank;
-                    }
+                } else if (survive) {
+                    ptot = nptot;
+                    pnb = npnb;
+                    pb = npb;
+                    rank = new_rank;
                 }
             }
-            if (ranks_changed) {
-                // successor lane of every beam, first and last lane of the order
-                if (alive) sm.newlist[rank] = (uint8_t)li;
-                __syncwarp(gmask);
-                succ = (alive && rank + 1 < na) ? (int)sm.newlist[rank + 1] : -1;
-                first_lane = (int)sm.newlist[0] + (int)gshift;
-                last_lane = (int)sm.newlist[na - 1] + (int)gshift;
-                __syncwarp(gmask);
+            if (__any_sync(kFull, ranks_changed)) {
+                // successor lane of every beam and the lane of the best one
+                __syncwarp();
+                if (run && alive) sm.newlist[rank] = (uint8_t)li;
+                __syncwarp();
+                if (run) {
+                    succ = (alive && rank + 1 < na) ? (int)sm.newlist[rank + 1] : -1;
+                    first_lane = (int)sm.newlist[0] + gshift;
+                }
+                __syncwarp();
             }
 
             // RESCALE by the exponent of the best beam (exact)
             {
-                const int hi = __shfl_sync(gmask, __double2hiint(ptot), first_lane);
+                const int hi = __shfl_sync(kFull, __double2hiint(ptot), first_lane);
                 const int ex = (hi >> 20) & 0x7ff;
-                if (ex != 0 && ex != 0x7ff) {
+                if (run && ex != 0 && ex != 0x7ff) {
                     const double sc = __hiloint2double((2046 - ex) << 20, 0);
                     ptot *= sc;
                     pnb *= sc;
@@ -648,15 +670,16 @@ decode_kernel(const DecodeArgs a)
                     kacc += ex - 1023;
                 }
             }
-            ++t;
         }
+        if (active) t += nrun;
 
         // ------------------------------------------------------------ end of read
+        const int succ_first = __shfl_sync(kFull, succ, first_lane);
         if (active && t >= T) {
-            const unsigned b0 = __ballot_sync(gmask, alive && rank == 0);
-            const unsigned b1 = __ballot_sync(gmask, alive && rank == 1);
-            const int l0 = __ffs(b0) - 1;
-            if (status == 0 && lane == l0) {
+            const long long seq_off = a.seq_offsets[read];
+            const long long seq_cap = a.seq_offsets[read + 1] - seq_off;
+            const double ln2 = 0.693147180559945309417;
+            if (status == 0 && lane == first_lane) {
                 const long long n = len;
                 if (n > seq_cap) status = RADIAN_READ_SEQ_OVERFLOW;
                 int c = node;
@@ -666,16 +689,16 @@ decode_kernel(const DecodeArgs a)
                     c = (int)(w >> 2);
                 }
                 a.out_len[read] = n;
-                a.out_score[2 * read] = (ptot > 0.0) ? log(ptot) + (double)kacc * 0.693147180559945309417 : -INFINITY;
-                if (!b1) a.out_score[2 * read + 1] = NAN;
+                a.out_score[2 * read] = (ptot > 0.0) ? log(ptot) + (double)kacc * ln2 : -INFINITY;
+                if (succ_first < 0) a.out_score[2 * read + 1] = NAN;
                 a.out_status[read] = status;
                 if (a.out_counters) {
                     a.out_counters[2 * read] = n_lookup;
                     a.out_counters[2 * read + 1] = n_combine;
                 }
             }
-            if (status == 0 && b1 && lane == __ffs(b1) - 1)
-                a.out_score[2 * read + 1] = (ptot > 0.0) ? log(ptot) + (double)kacc * 0.693147180559945309417 : -INFINITY;
+            if (status == 0 && succ_first >= 0 && li == succ_first)
+                a.out_score[2 * read + 1] = (ptot > 0.0) ? log(ptot) + (double)kacc * ln2 : -INFINITY;
             if (status == RADIAN_READ_TRIE_OVERFLOW && li == 0) {
                 a.out_len[read] = 0;
                 a.out_score[2 * read] = NAN;
@@ -685,6 +708,7 @@ decode_kernel(const DecodeArgs a)
             read = -1;
         }
     }
+#undef GBALLOT
 }
 
 // ------------------------------------------------------------------------------ host side
