@@ -15,7 +15,7 @@ NVCC_FLAGS = [
     "-fmad=false",            # the decode arithmetic is written with explicit roundings
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-]
+] + os.environ.get("RADIAN_NVCC_EXTRA", "").split()
 
 
 def nvcc_path() -> str:

@@ -35,6 +35,9 @@
 namespace radian {
 
 constexpr int kWarpsPerBlock = 4;
+#ifndef RADIAN_MIN_BLOCKS
+#define RADIAN_MIN_BLOCKS 1
+#endif
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint16_t kPosInvalid = 0xffff;
 constexpr int kNursery = 4096;  // arena nodes between two collections
@@ -137,7 +140,7 @@ __device__ __forceinline__ void make_record(const float (&v)[5], double s_thr, d
 // all shuffles and votes use the full mask and each group extracts its own lanes' bits.  Sub-warp
 // masks would make the compiler emit a convergence check per collective and serialise the groups.
 template <int G, bool LM, typename PT, bool COUNT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, RADIAN_MIN_BLOCKS)
 decode_kernel(const DecodeArgs a)
 {
     constexpr int GPW = 32 / G;  // groups (reads) per warp
@@ -758,6 +761,8 @@ int decode_pick(int device, int beam_width, bool lm, bool f64, bool count, Decod
     const int G = group_size(beam_width);
     const void *k = pick_kernel(G, lm, f64, count);
     int blocks = 0;
+    // the kernel streams its global loads once; give shared memory the whole L1 carve-out
+    RADIAN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     RADIAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k, kWarpsPerBlock * 32, 0));
     if (blocks < 1) blocks = 1;
     out->grid = di.sm_count * blocks;
