@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--f64", action="store_true", help="float64 posteriors (assembled global matrices)")
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--e2e-reads", type=int, default=2048, help="reads in the host-buffer end-to-end leg")
-    ap.add_argument("--cpu-reads", type=int, default=16, help="reads in the CPU baseline sample")
+    ap.add_argument("--cpu-reads", type=int, default=512, help="reads in the CPU baseline sample (also parity-checked)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--check-reads", type=int, default=4, help="reads re-decoded by the oracle after timing")
@@ -319,8 +319,8 @@ def main():
 
         nc = max(a.check_reads, 0 if a.no_cpu else a.cpu_reads)
         nc = min(nc, a.reads)
-        # the shortest reads of the batch keep the oracle leg bounded
-        idx = torch.argsort(T)[:nc].cpu().numpy()
+        # the first reads of the batch: an unbiased sample of the length distribution
+        idx = np.arange(nc)
         sub = [post[int(fo[i]):int(fo[i + 1])].cpu().numpy() for i in idx]
         fo_s = np.zeros(nc + 1, dtype=np.int64)
         fo_s[1:] = np.cumsum([m.shape[0] for m in sub])

@@ -93,11 +93,11 @@ int radian_table_entropies(const radian_table_t *t, double *out_host);
  */
 /*
  *  arena_nodes   capacity of the per-read back-pointer arena; 0 picks a default from max_frames
- *                (exact worst case for small problems, else beam lanes x max_frames/8).  A read
+ *                (exact worst case for small problems, else beam lanes x max_frames/16).  A read
  *                that needs more gets RADIAN_READ_TRIE_OVERFLOW; lanes x (T+1) always suffices.
  *                The _host entry point retries such reads by itself.
  */
-size_t radian_decode_workspace_bytes(int device, int beam_width, int64_t max_frames,
+size_t radian_decode_workspace_bytes(int device, int beam_width, int n_reads, int64_t max_frames,
                                      int64_t arena_nodes);
 
 int radian_decode_batch_dev(const void *post, int post_is_f64, const int64_t *frame_offsets,

@@ -216,6 +216,32 @@ def gen_assembly(n_cases, seed):
     }
 
 
+def gen_sequence_assembly(n_cases, seed):
+    """Chunk-mode stitching (sequence_assembly.py:19-48,90-97) on overlapping noisy fragments."""
+    _, _, sa = ref_loader.load()
+    rng = np.random.default_rng(seed)
+    cases = []
+    for _ in range(n_cases):
+        n = int(rng.integers(40, 400))
+        truth = "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+        frags = []
+        start = 0
+        while start < n:
+            ln = int(rng.integers(15, 40))
+            f = list(truth[start:start + ln])
+            for j in range(len(f)):
+                if rng.random() < 0.03:
+                    f[j] = "ACGT"[rng.integers(0, 4)]
+            frags.append("".join(f))
+            start += int(rng.integers(3, 12))
+        if len(frags) == 1 or rng.random() < 0.1:
+            frags = frags[:1]
+        cons = sa.simple_assembly(frags)
+        cases.append({"fragments": frags, "consensus": sa.index2base(np.argmax(cons, axis=0)),
+                      "votes_shape": list(cons.shape), "votes_sum": float(cons.sum())})
+    return cases
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--long", action="store_true", help="also the slow full-length reads")
@@ -225,6 +251,11 @@ def main():
 
     np.savez_compressed(os.path.join(GOLDEN, "assembly.npz"), **gen_assembly(120, 2024))
     print("assembly.npz written")
+    import json
+
+    with open(os.path.join(GOLDEN, "sequence_assembly.json"), "w") as f:
+        json.dump(gen_sequence_assembly(40, 5), f)
+    print("sequence_assembly.json written")
 
     sets = {
         "decode_kat": gen_decode_kat(),

@@ -44,7 +44,7 @@ def _load():
     lib.radian_table_entropies.restype = c_int
     lib.radian_table_entropies.argtypes = [c_void_p, c_void_p]
     lib.radian_decode_workspace_bytes.restype = c_size_t
-    lib.radian_decode_workspace_bytes.argtypes = [c_int, c_int, c_int64, c_int64]
+    lib.radian_decode_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int64, c_int64]
     lib.radian_decode_batch_dev.restype = c_int
     lib.radian_decode_batch_dev.argtypes = [
         c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_double, c_double,

@@ -48,6 +48,22 @@ int device_info(int device, DeviceInfo *out)
     return 0;
 }
 
+// The _host entry points allocate with cudaMallocAsync; keep freed blocks in the device pool so
+// that repeated calls do not pay for fresh allocations every time.
+int keep_pool(int device)
+{
+    static std::mutex mu;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64 || done[device]) return 0;
+    cudaMemPool_t pool;
+    RADIAN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long thr = ~0ull;
+    RADIAN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    done[device] = true;
+    return 0;
+}
+
 // gate bit of context i: entropy(lm[context]) < r_threshold (decode.py:93, strict)
 __global__ void gate_kernel(const double *__restrict__ entropy, size_t rows, double thr, uint32_t *__restrict__ gate)
 {
@@ -167,12 +183,16 @@ extern "C" int radian_table_entropies(const radian_table_t *t, double *out_host)
     return RADIAN_OK;
 }
 
-extern "C" size_t radian_decode_workspace_bytes(int device, int beam_width, int64_t max_frames,
+extern "C" size_t radian_decode_workspace_bytes(int device, int beam_width, int n_reads, int64_t max_frames,
                                                 int64_t arena_nodes)
 {
-    if (beam_width < 1 || beam_width > RADIAN_MAX_BEAM_WIDTH) return 0;
-    const int slots = decode_max_slots(device, beam_width);
+    if (beam_width < 1 || beam_width > RADIAN_MAX_BEAM_WIDTH || n_reads < 0) return 0;
+    int slots = decode_max_slots(device, beam_width);
     if (slots <= 0) return 0;
+    // one arena per resident read group; a launch never uses more groups than reads (rounded up to
+    // whole CTAs of at most 16 groups)
+    const int64_t need = ((int64_t)n_reads + 15) / 16 * 16;
+    if (need < slots) slots = (int)(need < 16 ? 16 : need);
     const size_t cap = (size_t)decode_arena_cap(beam_width, max_frames, arena_nodes);
     return 256 + (size_t)slots * (cap + (size_t)decode_nursery()) * sizeof(uint32_t);
 }
@@ -216,7 +236,7 @@ extern "C" int radian_decode_batch_dev(const void *post, int post_is_f64, const 
         set_error("radian_decode_batch_dev: table lives on device %d, current device is %d", table->device, device);
         return RADIAN_E_ARG;
     }
-    const size_t need = radian_decode_workspace_bytes(device, beam_width, max_frames, arena_nodes);
+    const size_t need = radian_decode_workspace_bytes(device, beam_width, n_reads, max_frames, arena_nodes);
     const int64_t cap = decode_arena_cap(beam_width, max_frames, arena_nodes);
     if (cap >= (1ll << 29)) {
         set_error("radian_decode_batch_dev: arena of %lld nodes exceeds the 2^29 node limit", (long long)cap);
@@ -281,7 +301,11 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     std::stable_sort(order.begin(), order.end(),
                      [&](int32_t x, int32_t y) { return fo[x + 1] - fo[x] > fo[y + 1] - fo[y]; });
     const int64_t frames = fo[n], seq_bytes = so[n];
-    const size_t ws_bytes = radian_decode_workspace_bytes(device, beam_width, max_frames, arena_nodes);
+    const size_t ws_bytes = radian_decode_workspace_bytes(device, beam_width, n, max_frames, arena_nodes);
+    {
+        int krc = keep_pool(device);
+        if (krc) return krc;
+    }
     cudaStream_t st;
     RADIAN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     void *d_post = nullptr, *d_ws = nullptr;

@@ -179,6 +179,10 @@ extern "C" int radian_assemble_batch_host(const float *chunks, const int64_t *ch
         return RADIAN_E_ARG;
     }
     RADIAN_CUDA(cudaSetDevice(device));
+    {
+        int krc = keep_pool(device);
+        if (krc) return krc;
+    }
     const int64_t n_chunks = read_chunk_ranges[n_reads];
     const int64_t in_rows = chunk_row_offsets[n_chunks];
     const int64_t out_rows = out_row_offsets[n_reads];

@@ -743,13 +743,13 @@ int decode_nursery() { return kNursery; }
 int64_t decode_arena_cap(int beam_width, int64_t max_frames, int64_t arena_nodes)
 {
     // Old generation <= beam_width x decoded length (see the header comment); decoded length <= T.
-    // Small problems get the exact worst case; large ones assume >= 8 frames per base and report
+    // Small problems get the exact worst case; large ones assume >= 16 frames per base and report
     // RADIAN_READ_TRIE_OVERFLOW otherwise (the caller retries those reads with arena_nodes set).
     const int64_t G = group_size(beam_width);
     const int64_t exact = G * (max_frames + 1) + kNursery + 64;
     if (arena_nodes > 0) return arena_nodes < exact ? arena_nodes + kNursery : exact;
     if (exact <= (1 << 16)) return exact;
-    int64_t cap = G * (max_frames / 8 + 64) + kNursery;
+    int64_t cap = G * (max_frames / 16 + 64) + kNursery;
     return cap < (1 << 16) ? (1 << 16) : cap;
 }
 

@@ -21,6 +21,7 @@ struct DeviceInfo {
     int max_smem_optin;
 };
 int device_info(int device, DeviceInfo *out);
+int keep_pool(int device);
 
 }  // namespace radian
 

@@ -243,7 +243,7 @@ def decode_batch_device(post, frame_offsets, beam_width, table=None, s_threshold
             scores=torch.empty((n, 2), dtype=torch.float64, device=post.device),
             status=torch.empty(n, dtype=torch.int32, device=post.device),
             counters=torch.zeros((n, 2), dtype=torch.int64, device=post.device) if counters else None)
-    nbytes = lib.radian_decode_workspace_bytes(dev, int(beam_width), int(max_frames), int(arena_nodes))
+    nbytes = lib.radian_decode_workspace_bytes(dev, int(beam_width), int(n), int(max_frames), int(arena_nodes))
     if nbytes == 0:
         raise _native.RadianError(f"no CUDA device / bad beam width: {_native.last_error()}")
     ws = _workspace(dev, nbytes)

@@ -1,0 +1,137 @@
+"""Host-side logic that needs no GPU: assembly planning through the C ABI, sharding, the CLI
+surface, the synthetic generators and the chunk-mode stitcher."""
+import ctypes
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import golden_io
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def plan(chunk_lens_per_read, step):
+    from radian_b200 import _native
+
+    cro = [0]
+    rcr = [0]
+    for lens in chunk_lens_per_read:
+        for ln in lens:
+            cro.append(cro[-1] + ln)
+        rcr.append(len(cro) - 1)
+    cro = np.asarray(cro, np.int64)
+    rcr = np.asarray(rcr, np.int64)
+    n = len(chunk_lens_per_read)
+    rows = np.zeros(n, np.int64)
+    ov = ctypes.c_int(0)
+    mx = ctypes.c_int32(0)
+    rc = _native.lib.radian_assemble_plan(_native.np_ptr(cro), _native.np_ptr(rcr), n, step, _native.np_ptr(rows),
+                                          ctypes.byref(ov), ctypes.byref(mx))
+    _native.check(rc)
+    return rows.tolist(), bool(ov.value), int(mx.value)
+
+
+def test_assemble_plan_matches_golden_shapes():
+    """Row counts and float64 promotion of every golden assembly case (matrix_assembly.py:12-44)."""
+    for S, mats, ref in golden_io.assembly_cases():
+        rows, ov, mx = plan([[len(m) for m in mats]], S)
+        assert rows == [ref.shape[0]]
+        assert ov == (ref.dtype == np.float64)
+        assert mx == max(len(m) for m in mats)
+
+
+def test_assemble_plan_closed_form_and_errors():
+    # reference windowing: T = (n-1)*S + len(last)  
+    rows, ov, mx = plan([[1024] * 9 + [1000], [700]], 128)
+    assert rows == [9 * 128 + 1000, 700] and ov and mx == 1024
+    rows, ov, _ = plan([[10, 10, 10]], 10)       # step == window: no overlap -> float32 result
+    assert rows == [30] and not ov
+    with pytest.raises(IndexError):               # create_vstack cannot leave a gap
+        plan([[3, 3]], 10)
+    with pytest.raises(ValueError):
+        plan([[3]], 0)
+
+
+def test_lpt_shards_are_balanced_and_complete():
+    from radian_b200 import parallel, synth
+
+    fc = synth.read_lengths(1000, 1) * 43
+    for world in (1, 2, 8):
+        shards = parallel.lpt_shards(fc, world)
+        allidx = np.sort(np.concatenate(shards))
+        assert np.array_equal(allidx, np.arange(1000))
+        loads = np.array([fc[s].sum() for s in shards])
+        assert loads.max() - loads.min() <= fc.max()
+        for s in shards:
+            assert np.all(np.diff(fc[s]) <= 0)   # longest first within a rank
+
+
+def test_cli_flags_match_reference():
+    """Names, defaults and types of basecall.py:21-35."""
+    from radian_b200 import basecall
+
+    a = basecall.build_parser().parse_args(["in", "out"])
+    assert (a.chunk_len, a.step_size, a.batch_size, a.outlier_clip) == (1024, 128, 32, 4)
+    assert (a.beam_width, a.decode_type, a.sig_threshold, a.rna_threshold, a.context_len) == (6, "global", 0.5, 0.5, 11)
+    assert a.rna_model == "models/rnamodel_12mer_pc.json"
+    b = basecall.build_parser().parse_args(["in", "out", "--beam-width", "16", "--decode-type", "chunk",
+                                           "--sig-threshold", "0.3", "--rna-threshold", "0.9", "--context-len", "12",
+                                           "--chunk-len", "512", "--step-size", "64"])
+    assert (b.beam_width, b.decode_type, b.sig_threshold, b.rna_threshold, b.context_len, b.chunk_len, b.step_size) == \
+        (16, "chunk", 0.3, 0.9, 12, 512, 64)
+    with pytest.raises(SystemExit):
+        basecall.build_parser().parse_args(["in", "out", "--decode-type", "local"])
+
+
+def test_fasta_writer_rollover(tmp_path):
+    """>{id}\\n{seq[::-1]}\\n records, a new file every 1000 reads (basecall.py:129-138)."""
+    from radian_b200.basecall import FastaWriter
+
+    w = FastaWriter(str(tmp_path), per_file=3)
+    for i in range(7):
+        w.write(f"r{i}", "ACG" + "T" * i)
+    w.close()
+    files = sorted(os.listdir(tmp_path))
+    assert files == ["reads-0.fasta", "reads-1.fasta", "reads-2.fasta"]
+    assert open(tmp_path / "reads-0.fasta").read() == ">r0\nGCA\n>r1\nTGCA\n>r2\nTTGCA\n"
+    assert open(tmp_path / "reads-2.fasta").read() == ">r6\nTTTTTTGCA\n"
+
+
+def test_synth_table_is_bit_reproducible():
+    from radian_b200 import synth
+
+    t = synth.make_table(5, 7)
+    assert t.shape == (1024, 4)
+    assert np.allclose(t.sum(1), 1.0)
+    assert hashlib.sha256(t.tobytes()).hexdigest() == hashlib.sha256(synth.make_table(5, 7, chunk=100).tobytes()).hexdigest()
+    frac = (synth.table_entropy(synth.make_table(8, 1)) < 0.5).mean()
+    assert 0.2 < frac < 0.4
+
+
+def test_synth_reads_shape():
+    from radian_b200 import synth
+
+    nb = synth.read_lengths(2000, 3)
+    assert nb.min() >= 200 and nb.max() <= 10000 and 1300 < nb.mean() < 1800
+    post, off = synth.make_reads(np.array([30, 50]), seed=1)
+    assert post.shape[1] == 5 and off[0] == 0 and off[-1] == post.shape[0]
+    p = post.numpy()
+    assert (p[:, :4] == 0).any() and p[:, 4].mean() > 0.8
+    mats = synth.split_windows(p[: off[1]], 1024, 128)
+    assert sum(len(m) for m in mats[:1]) == min(1024, off[1])
+
+
+def test_sequence_assembly_golden():
+    """Chunk-mode stitching against outputs of the reference's simple_assembly/index2base."""
+    from radian_b200.sequence_assembly import index2base, simple_assembly
+
+    cases = json.load(open(os.path.join(golden_io.GOLDEN, "sequence_assembly.json")))
+    assert len(cases) >= 30
+    for c in cases:
+        votes = simple_assembly(c["fragments"])
+        assert list(votes.shape) == c["votes_shape"]
+        assert float(votes.sum()) == c["votes_sum"]
+        assert index2base(np.argmax(votes, axis=0)) == c["consensus"]
