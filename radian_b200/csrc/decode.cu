@@ -35,8 +35,10 @@
 namespace radian {
 
 constexpr int kWarpsPerBlock = 4;
+// resident CTAs per SM asked from ptxas (A/B on B200, profiles/r1_minblocks_ab.txt): 5 with the
+// RNA model (<= 102 registers, no spills), 6 without
 #ifndef RADIAN_MIN_BLOCKS
-#define RADIAN_MIN_BLOCKS 1
+#define RADIAN_MIN_BLOCKS (LM ? 5 : 6)
 #endif
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint16_t kPosInvalid = 0xffff;
