@@ -181,7 +181,7 @@ decode_kernel(const DecodeArgs a)
     int succ = -1;       // lane (in group) of the beam ranked right after this one
     uint32_t killw = 0;  // bit c: extension by c is merged into a live child's copy
     // ---- per-read (group-uniform) state
-    int read = -1, top = 0, old_top = 0, na = 0, status = 0, first_lane = 0;
+    int read = -1, top = 0, old_top = 0, na = 0, status = 0, first_lane = 0, last_lane = 0;
     int T = 0, t = 0;
     long long kacc = 0;
     const PT *rp = (const PT *)a.post;
@@ -222,6 +222,7 @@ decode_kernel(const DecodeArgs a)
                     succ = -1;
                     killw = 0;
                     first_lane = gshift;
+                    last_lane = gshift;
                     top = 1;  // node 0 = the empty labeling
                     old_top = 1;
                     na = 1;
@@ -388,21 +389,32 @@ decode_kernel(const DecodeArgs a)
             const uint32_t ksucc = __shfl_sync(kFull, kc32, succ >= 0 ? succ + gshift : lane);
             const bool order_ok = GBALLOT(!av || succ < 0 || kc32 > ksucc) == GBITS;
             const bool prune = (na >= bw);
-            uint32_t tau = av ? kc32 : 0xffffffffu;
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) {
-                const uint32_t x = __shfl_xor_sync(kFull, tau, o);
-                tau = x < tau ? x : tau;
-            }
-            const bool comp0 = av && !(killw & 1u) && (!prune || (uint32_t)__double2hiint(e0) >= tau);
-            const bool comp1 = av && !(killw & 2u) && (!prune || (uint32_t)__double2hiint(e1) >= tau);
-            const bool comp2 = av && !(killw & 4u) && (!prune || (uint32_t)__double2hiint(e2) >= tau);
-            const bool comp3 = av && !(killw & 8u) && (!prune || (uint32_t)__double2hiint(e3) >= tau);
-            bool full = GBALLOT(comp0 || comp1 || comp2 || comp3) != 0u;  // my group needs a full ranking
+            // worst copy of the group: the last lane of the order when the order still holds
+            uint32_t tau = __shfl_sync(kFull, kc32, last_lane);
+            bool comp0 = av && !(killw & 1u) && (!prune || (uint32_t)__double2hiint(e0) >= tau);
+            bool comp1 = av && !(killw & 2u) && (!prune || (uint32_t)__double2hiint(e1) >= tau);
+            bool comp2 = av && !(killw & 4u) && (!prune || (uint32_t)__double2hiint(e2) >= tau);
+            bool comp3 = av && !(killw & 8u) && (!prune || (uint32_t)__double2hiint(e3) >= tau);
             bool ranks_changed = false;
+            bool full;
 
-            if (__any_sync(kFull, !full && !order_ok)) {
-                // copies changed order among themselves: rank them on the high words alone
+            if (__any_sync(kFull, !order_ok)) {
+                // some group's copies changed order: its worst copy is the minimum over the lanes
+                uint32_t tmin = av ? kc32 : 0xffffffffu;
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) {
+                    const uint32_t x = __shfl_xor_sync(kFull, tmin, o);
+                    tmin = x < tmin ? x : tmin;
+                }
+                if (!order_ok) {
+                    tau = tmin;
+                    comp0 = av && !(killw & 1u) && (!prune || (uint32_t)__double2hiint(e0) >= tau);
+                    comp1 = av && !(killw & 2u) && (!prune || (uint32_t)__double2hiint(e1) >= tau);
+                    comp2 = av && !(killw & 4u) && (!prune || (uint32_t)__double2hiint(e2) >= tau);
+                    comp3 = av && !(killw & 8u) && (!prune || (uint32_t)__double2hiint(e3) >= tau);
+                }
+                full = GBALLOT(comp0 || comp1 || comp2 || comp3) != 0u;  // my group needs a full ranking
+                // groups without a competing extension rank their copies on the high words alone
                 sm.k32[li] = kc32;
                 __syncwarp();
                 int cc = 0;
@@ -424,6 +436,8 @@ decode_kernel(const DecodeArgs a)
                     }
                 }
                 __syncwarp();
+            } else {
+                full = GBALLOT(comp0 || comp1 || comp2 || comp3) != 0u;
             }
 
             if (!__any_sync(kFull, full)) {
@@ -659,12 +673,15 @@ decode_kernel(const DecodeArgs a)
                 if (run) {
                     succ = (alive && rank + 1 < na) ? (int)sm.newlist[rank + 1] : -1;
                     first_lane = (int)sm.newlist[0] + gshift;
+                    last_lane = (int)sm.newlist[na - 1] + gshift;
                 }
                 __syncwarp();
             }
 
-            // RESCALE by the exponent of the best beam (exact)
-            {
+            // RESCALE by the exponent of the best beam (an exact power of two).  Every 4th frame is
+            // enough: a float32-derived probability is >= 2^-149, so the best beam loses at most
+            // 596 binades in between, far from the float64 limit.
+            if ((it & 3) == 3) {
                 const int hi = __shfl_sync(kFull, __double2hiint(ptot), first_lane);
                 const int ex = (hi >> 20) & 0x7ff;
                 if (run && ex != 0 && ex != 0x7ff) {
