@@ -35,20 +35,22 @@
 namespace radian {
 
 constexpr int kWarpsPerBlock = 4;
-// resident CTAs per SM asked from ptxas (A/B on B200, profiles/r1_minblocks_ab.txt): 5 with the
-// RNA model (<= 102 registers, no spills), 6 without
+// resident CTAs per SM asked from ptxas (A/B on B200, profiles/r1_minblocks_ab.txt): 6 CTAs =
+// 24 warps at <= 80 registers once the tile prefetch and the RNA rows moved to shared memory
 #ifndef RADIAN_MIN_BLOCKS
-#define RADIAN_MIN_BLOCKS (LM ? 5 : 6)
+#define RADIAN_MIN_BLOCKS 6
 #endif
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint16_t kPosInvalid = 0xffff;
 constexpr int kNursery = 4096;  // arena nodes between two collections
 
-template <int G, bool LM>
+template <int G, bool LM, typename PT>
 struct __align__(16) GroupSmem {
     static constexpr int REC = LM ? 12 : 6;  // doubles per frame: P0..P4, gate, q0..q3, S, pad
     static constexpr int NK = (2 * G > 32) ? 2 * G : 32;  // candidate slots of the fast ranking path
     double rec[G * REC];
+    double row[LM ? G * 4 : 4];       // RNA table row of every lane's extend-context (cp.async target)
+    PT raw[G * 5];                    // next tile of posterior rows, landed by cp.async
     double ex[G * 4];                 // extension scores of every lane, for the copy/extend merge
     unsigned long long key[5 * G];    // candidate list: [0,G) copies by lane, [G,..) extensions
     uint32_t k32[NK];                 // high words of the candidate scores (0 = empty slot)
@@ -66,12 +68,29 @@ __device__ __forceinline__ unsigned long long hash_step(unsigned long long h, in
     return h ^ (h >> 29);
 }
 
+// Asynchronous global -> shared copies (LDGSTS): no register staging, completion awaited with
+// cp_async_wait_all() by the issuing thread right before the data is needed.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// one posterior row (5 values of 4 or 8 bytes; rows are only element-aligned) -> smem
 template <typename PT>
-__device__ __forceinline__ void load_row(const PT *post, long long frame, PT (&v)[5])
+__device__ __forceinline__ void prefetch_row(PT *dst, const PT *post, long long frame)
 {
     const PT *r = post + frame * 5;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) v[i] = __ldg(r + i);
+    for (int i = 0; i < 5; ++i) cp_async<sizeof(PT)>(dst + i, r + i);
 }
 
 // Per-frame work shared by all beams of a read, done by the lane that loaded the frame.
@@ -81,8 +100,11 @@ __device__ __forceinline__ void load_row(const PT *post, long long frame, PT (&v
 // the hardware log decides it unless it lands within 1e-4 of the threshold, in which case the
 // reference's exact operation order is evaluated.
 template <bool LM>
-__device__ __forceinline__ void make_record(const double (&v)[5], double s_thr, double *rec)
+__device__ __forceinline__ void make_record(const double *raw, double s_thr, double *rec)
 {
+    double v[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v[i] = raw[i];
 #pragma unroll
     for (int i = 0; i < 5; ++i) rec[i] = v[i];
     if (LM) {
@@ -110,8 +132,11 @@ __device__ __forceinline__ void make_record(const double (&v)[5], double s_thr, 
 }
 
 template <bool LM>
-__device__ __forceinline__ void make_record(const float (&v)[5], double s_thr, double *rec)
+__device__ __forceinline__ void make_record(const float *raw, double s_thr, double *rec)
 {
+    float v[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v[i] = raw[i];
 #pragma unroll
     for (int i = 0; i < 5; ++i) rec[i] = (double)v[i];
     if (LM) {
@@ -146,11 +171,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, RADIAN_MIN_BLOCKS)
 decode_kernel(const DecodeArgs a)
 {
     constexpr int GPW = 32 / G;  // groups (reads) per warp
-    constexpr int REC = GroupSmem<G, LM>::REC;
-    constexpr int NK = GroupSmem<G, LM>::NK;
+    constexpr int REC = GroupSmem<G, LM, PT>::REC;
+    constexpr int NK = GroupSmem<G, LM, PT>::NK;
     constexpr int EPL = (NK - G) / G;  // extension slots ranked by each lane on the fast path
     constexpr unsigned GBITS = (G == 32) ? kFull : ((1u << G) - 1u);
-    __shared__ GroupSmem<G, LM> smem[kWarpsPerBlock * GPW];
+    __shared__ GroupSmem<G, LM, PT> smem[kWarpsPerBlock * GPW];
 
     const int lane = threadIdx.x & 31;
     const int li = lane % G;
@@ -158,7 +183,7 @@ decode_kernel(const DecodeArgs a)
     const int gshift = gw * G;
     const unsigned belowg = (1u << li) - 1u;  // lanes of my group below me, group-relative bits
     const int gib = (threadIdx.x >> 5) * GPW + gw;  // group in block
-    GroupSmem<G, LM> &sm = smem[gib];
+    GroupSmem<G, LM, PT> &sm = smem[gib];
     const int slot = blockIdx.x * (kWarpsPerBlock * GPW) + gib;
     // votes: bits of my group's lanes, group-relative
 #define GBALLOT(p) ((__ballot_sync(kFull, (p)) >> gshift) & GBITS)
@@ -176,7 +201,8 @@ decode_kernel(const DecodeArgs a)
     uint32_t ctx = 0;
     int len = 0, node = 0, rank = 0, plane = -1, last = 0;
     bool alive = false;
-    double rext0 = 0, rext1 = 0, rext2 = 0, rext3 = 0, rcopy = 0;
+    double rcopy = 0;  // table value of this beam's last symbol in its copy-context; the row of the
+                       // extend-context lives in sm.row[li*4..]
     bool gext = false, gcopy = false;
     int succ = -1;       // lane (in group) of the beam ranked right after this one
     uint32_t killw = 0;  // bit c: extension by c is merged into a live child's copy
@@ -186,7 +212,6 @@ decode_kernel(const DecodeArgs a)
     long long kacc = 0;
     const PT *rp = (const PT *)a.post;
     unsigned long long n_lookup = 0, n_combine = 0;
-    PT pf[5];
     bool active = true;
 
     while (true) {
@@ -244,16 +269,18 @@ decode_kernel(const DecodeArgs a)
         }
         // (re)prime the frame tiles so that all groups of the warp refill at the same iterations
         const int tb = t;
-        if (active && tb + li < T) load_row(rp, tb + li, pf);
+        __syncwarp();
+        if (active && tb + li < T) prefetch_row(&sm.raw[li * 5], rp, tb + li);
 
         for (int it = 0; it < nrun; ++it) {
             bool run = active && status == 0;  // group-uniform
             // -------------------------------------------------------- tile refill
             if ((it % G) == 0) {
+                cp_async_wait_all();
                 __syncwarp();
-                if (run && tb + it + li < T) make_record<LM>(pf, a.s_thr, &sm.rec[li * REC]);
-                if (run && tb + it + G + li < T) load_row(rp, tb + it + G + li, pf);
+                if (run && tb + it + li < T) make_record<LM>(&sm.raw[li * 5], a.s_thr, &sm.rec[li * REC]);
                 __syncwarp();
+                if (run && tb + it + G + li < T) prefetch_row(&sm.raw[li * 5], rp, tb + it + G + li);
             }
 
             // -------------------------------------------------------- nursery collection
@@ -356,10 +383,13 @@ decode_kernel(const DecodeArgs a)
             // EXTEND (decode.py:177-201)
             double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
             if (LM && lm_ext && gext && fgate) {
-                d0 = __dmul_rn(__dmul_rn(__dadd_rn(rext0, q01.x), 0.5), S);
-                d1 = __dmul_rn(__dmul_rn(__dadd_rn(rext1, q01.y), 0.5), S);
-                d2 = __dmul_rn(__dmul_rn(__dadd_rn(rext2, q23.x), 0.5), S);
-                d3 = __dmul_rn(__dmul_rn(__dadd_rn(rext3, q23.y), 0.5), S);
+                cp_async_wait_all();  // the row gathered when this beam was created
+                const double2 r01 = *reinterpret_cast<const double2 *>(&sm.row[li * 4]);
+                const double2 r23 = *reinterpret_cast<const double2 *>(&sm.row[li * 4 + 2]);
+                d0 = __dmul_rn(__dmul_rn(__dadd_rn(r01.x, q01.x), 0.5), S);
+                d1 = __dmul_rn(__dmul_rn(__dadd_rn(r01.y, q01.y), 0.5), S);
+                d2 = __dmul_rn(__dmul_rn(__dadd_rn(r23.x, q23.x), 0.5), S);
+                d3 = __dmul_rn(__dmul_rn(__dadd_rn(r23.y, q23.y), 0.5), S);
             }
             // a repeated symbol continues only paths that ended in a blank (decode.py:192-195)
             const int lrep = has_last ? last : -1;
@@ -580,12 +610,12 @@ decode_kernel(const DecodeArgs a)
                     double p_r = 0.0;
                     bool p_g = false;
                     if (LM) {
-                        const double r0 = __shfl_sync(kFull, rext0, ls);
-                        const double r1 = __shfl_sync(kFull, rext1, ls);
-                        const double r2 = __shfl_sync(kFull, rext2, ls);
-                        const double r3 = __shfl_sync(kFull, rext3, ls);
-                        p_r = c == 0 ? r0 : c == 1 ? r1 : c == 2 ? r2 : r3;
                         p_g = __shfl_sync(kFull, (int)gext, ls) != 0;
+                        // every lane waits for its own row first; the parent's row is then complete
+                        cp_async_wait_all();
+                        __syncwarp();
+                        if (take && p_g) p_r = sm.row[(ls - gshift) * 4 + c];
+                        __syncwarp();  // all reads of parent rows done before any row is replaced
                     }
                     if (survive) {
                         ptot = nptot;
@@ -615,13 +645,10 @@ decode_kernel(const DecodeArgs a)
                             if (len >= L) {
                                 const uint32_t ci = ctx & ctx_mask;
                                 const uint32_t gwd = __ldg(a.gate + (ci >> 5));
-                                const double2 *row = reinterpret_cast<const double2 *>(a.table + (size_t)ci * 4);
-                                const double2 ra = __ldg(row), rb = __ldg(row + 1);
+                                const double *row = a.table + (size_t)ci * 4;
+                                cp_async<16>(&sm.row[li * 4], row);
+                                cp_async<16>(&sm.row[li * 4 + 2], row + 2);
                                 gext = (gwd >> (ci & 31u)) & 1u;
-                                rext0 = ra.x;
-                                rext1 = ra.y;
-                                rext2 = rb.x;
-                                rext3 = rb.y;
                             }
                         }
                     } else if (run) {
