@@ -62,6 +62,15 @@ struct __align__(16) GroupSmem {
     uint8_t lanerank[G];              // previous rank of every lane
 };
 
+// all-ones if bit 7 of byte `B` of x is set, else zero (prmt with the sign-replicate selector bit)
+template <int B>
+__device__ __forceinline__ uint32_t byte_sign_mask(uint32_t x)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(x), "n"(0x8888 + 0x1111 * B));
+    return r;
+}
+
 __device__ __forceinline__ unsigned long long hash_step(unsigned long long h, int c)
 {
     h = (h ^ (unsigned long long)(c + 1)) * 0x9E3779B97F4A7C15ull;
@@ -204,8 +213,9 @@ decode_kernel(const DecodeArgs a)
     double rcopy = 0;  // table value of this beam's last symbol in its copy-context; the row of the
                        // extend-context lives in sm.row[li*4..]
     bool gext = false, gcopy = false;
-    int succ = -1;       // lane (in group) of the beam ranked right after this one
-    uint32_t killw = 0;  // bit c: extension by c is merged into a live child's copy
+    int succ = 0;        // absolute lane of the beam ranked right after this one (own lane: none)
+    uint32_t km = 0;     // byte c = 0x80: this lane holds a beam and its extension by c is a candidate
+                         // of its own (not merged into a live child's copy); 0 for a dead lane
     // ---- per-read (group-uniform) state
     int read = -1, top = 0, old_top = 0, na = 0, status = 0, first_lane = 0, last_lane = 0;
     int T = 0, t = 0;
@@ -244,8 +254,8 @@ decode_kernel(const DecodeArgs a)
                     plane = -1;
                     last = 0;
                     gext = gcopy = false;
-                    succ = -1;
-                    killw = 0;
+                    succ = lane;
+                    km = alive ? 0x80808080u : 0u;
                     first_lane = gshift;
                     last_lane = gshift;
                     top = 1;  // node 0 = the empty labeling
@@ -343,6 +353,10 @@ decode_kernel(const DecodeArgs a)
                     if (top + G > cap) {
                         status = RADIAN_READ_TRIE_OVERFLOW;  // reported; remaining frames are skipped
                         run = false;
+                        alive = false;
+                        km = 0u;
+                        succ = lane;
+                        ptot = pnb = pb = 0.0;
                     }
                 }
             }
@@ -400,7 +414,7 @@ decode_kernel(const DecodeArgs a)
 
             // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference.
             // Which pairs merge only changes when the beam set changes, so the pairing (plane,
-            // killw) is state; per frame only the parent's extension score has to be fetched.
+            // km) is state; per frame only the parent's extension score has to be fetched.
             *reinterpret_cast<double2 *>(&sm.ex[li * 4]) = make_double2(e0, e1);
             *reinterpret_cast<double2 *>(&sm.ex[li * 4 + 2]) = make_double2(e2, e3);
             __syncwarp();
@@ -416,15 +430,20 @@ decode_kernel(const DecodeArgs a)
             // extension matters only if it is not below the worst copy of a full beam.
             const unsigned long long kcopy = (unsigned long long)__double_as_longlong(nptot);
             const uint32_t kc32 = av ? (uint32_t)(kcopy >> 32) : 0u;
-            const uint32_t ksucc = __shfl_sync(kFull, kc32, succ >= 0 ? succ + gshift : lane);
-            const bool order_ok = GBALLOT(!av || succ < 0 || kc32 > ksucc) == GBITS;
-            const bool prune = (na >= bw);
-            // worst copy of the group: the last lane of the order when the order still holds
+            const uint32_t ksucc = __shfl_sync(kFull, kc32, succ);
+            const bool order_ok = GBALLOT(kc32 > ksucc || succ == lane) == GBITS;
+            // worst copy of the group: the last lane of the order when the order still holds.
+            // With room left in the beam every extension is a candidate (threshold 1: keys are
+            // or-ed with 1 so that a zero-probability extension of a live beam still counts).
             uint32_t tau = __shfl_sync(kFull, kc32, last_lane);
-            bool comp0 = av && !(killw & 1u) && (!prune || (uint32_t)__double2hiint(e0) >= tau);
-            bool comp1 = av && !(killw & 2u) && (!prune || (uint32_t)__double2hiint(e1) >= tau);
-            bool comp2 = av && !(killw & 4u) && (!prune || (uint32_t)__double2hiint(e2) >= tau);
-            bool comp3 = av && !(killw & 8u) && (!prune || (uint32_t)__double2hiint(e3) >= tau);
+            const bool prune = (na >= bw);
+            tau = (prune && tau > 1u) ? tau : 1u;
+            // extension keys, zeroed where the extension is merged into a child or the lane is dead
+            const uint32_t x0 = ((uint32_t)__double2hiint(e0) | 1u) & byte_sign_mask<0>(km);
+            const uint32_t x1 = ((uint32_t)__double2hiint(e1) | 1u) & byte_sign_mask<1>(km);
+            const uint32_t x2 = ((uint32_t)__double2hiint(e2) | 1u) & byte_sign_mask<2>(km);
+            const uint32_t x3 = ((uint32_t)__double2hiint(e3) | 1u) & byte_sign_mask<3>(km);
+            const uint32_t xmax = max(max(x0, x1), max(x2, x3));
             bool ranks_changed = false;
             bool full;
 
@@ -436,14 +455,8 @@ decode_kernel(const DecodeArgs a)
                     const uint32_t x = __shfl_xor_sync(kFull, tmin, o);
                     tmin = x < tmin ? x : tmin;
                 }
-                if (!order_ok) {
-                    tau = tmin;
-                    comp0 = av && !(killw & 1u) && (!prune || (uint32_t)__double2hiint(e0) >= tau);
-                    comp1 = av && !(killw & 2u) && (!prune || (uint32_t)__double2hiint(e1) >= tau);
-                    comp2 = av && !(killw & 4u) && (!prune || (uint32_t)__double2hiint(e2) >= tau);
-                    comp3 = av && !(killw & 8u) && (!prune || (uint32_t)__double2hiint(e3) >= tau);
-                }
-                full = GBALLOT(comp0 || comp1 || comp2 || comp3) != 0u;  // my group needs a full ranking
+                if (!order_ok) tau = (prune && tmin > 1u) ? tmin : 1u;
+                full = GBALLOT(run && xmax >= tau) != 0u;  // my group needs a full ranking
                 // groups without a competing extension rank their copies on the high words alone
                 sm.k32[li] = kc32;
                 __syncwarp();
@@ -467,7 +480,7 @@ decode_kernel(const DecodeArgs a)
                 }
                 __syncwarp();
             } else {
-                full = GBALLOT(comp0 || comp1 || comp2 || comp3) != 0u;
+                full = GBALLOT(run && xmax >= tau) != 0u;
             }
 
             if (!__any_sync(kFull, full)) {
@@ -487,7 +500,7 @@ decode_kernel(const DecodeArgs a)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const double ec = c == 0 ? e0 : c == 1 ? e1 : c == 2 ? e2 : e3;
-                    const bool comp = full && (c == 0 ? comp0 : c == 1 ? comp1 : c == 2 ? comp2 : comp3);
+                    const bool comp = full && (c == 0 ? x0 : c == 1 ? x1 : c == 2 ? x2 : x3) >= tau;
                     const unsigned bal = GBALLOT(comp);
                     if (comp) {
                         const int idx = G + n_ext + __popc(bal & belowg);
@@ -679,12 +692,9 @@ decode_kernel(const DecodeArgs a)
                     // the beam set changed: refresh which extensions are merged into a live child
                     sm.kill[li] = 0u;
                     __syncwarp();
-                    if (run && alive && plane >= 0) reinterpret_cast<uint8_t *>(sm.kill)[plane * 4 + last] = 1;
+                    if (run && alive && plane >= 0) reinterpret_cast<uint8_t *>(sm.kill)[plane * 4 + last] = 0x80;
                     __syncwarp();
-                    if (run) {
-                        const uint32_t kw = sm.kill[li];
-                        killw = (kw & 1u) | ((kw >> 7) & 2u) | ((kw >> 14) & 4u) | ((kw >> 21) & 8u);
-                    }
+                    if (run) km = alive ? (0x80808080u & ~sm.kill[li]) : 0u;
                 } else if (survive) {
                     ptot = nptot;
                     pnb = npnb;
@@ -698,7 +708,7 @@ decode_kernel(const DecodeArgs a)
                 if (run && alive) sm.newlist[rank] = (uint8_t)li;
                 __syncwarp();
                 if (run) {
-                    succ = (alive && rank + 1 < na) ? (int)sm.newlist[rank + 1] : -1;
+                    succ = (alive && rank + 1 < na) ? (int)sm.newlist[rank + 1] + gshift : lane;
                     first_lane = (int)sm.newlist[0] + gshift;
                     last_lane = (int)sm.newlist[na - 1] + gshift;
                 }
@@ -723,7 +733,7 @@ decode_kernel(const DecodeArgs a)
         if (active) t += nrun;
 
         // ------------------------------------------------------------ end of read
-        const int succ_first = __shfl_sync(kFull, succ, first_lane);
+        const int succ_first = __shfl_sync(kFull, succ, first_lane);  // lane of the second best beam
         if (active && t >= T) {
             const long long seq_off = a.seq_offsets[read];
             const long long seq_cap = a.seq_offsets[read + 1] - seq_off;
@@ -739,14 +749,14 @@ decode_kernel(const DecodeArgs a)
                 }
                 a.out_len[read] = n;
                 a.out_score[2 * read] = (ptot > 0.0) ? log(ptot) + (double)kacc * ln2 : -INFINITY;
-                if (succ_first < 0) a.out_score[2 * read + 1] = NAN;
+                if (succ_first == first_lane) a.out_score[2 * read + 1] = NAN;
                 a.out_status[read] = status;
                 if (a.out_counters) {
                     a.out_counters[2 * read] = n_lookup;
                     a.out_counters[2 * read + 1] = n_combine;
                 }
             }
-            if (status == 0 && succ_first >= 0 && li == succ_first)
+            if (status == 0 && succ_first != first_lane && lane == succ_first)
                 a.out_score[2 * read + 1] = (ptot > 0.0) ? log(ptot) + (double)kacc * ln2 : -INFINITY;
             if (status == RADIAN_READ_TRIE_OVERFLOW && li == 0) {
                 a.out_len[read] = 0;
@@ -755,6 +765,11 @@ decode_kernel(const DecodeArgs a)
                 a.out_status[read] = status;
             }
             read = -1;
+            // leave no beam behind: an idle group must look "in order, nothing competing"
+            alive = false;
+            succ = lane;
+            km = 0u;
+            ptot = pnb = pb = 0.0;
         }
     }
 #undef GBALLOT
