@@ -7,7 +7,8 @@
 Workload (BASELINE.json configs[2], the one `metric` is quoted on): RNA-LM global decode,
 beam width 16, 12-mer context, sig/rna thresholds 0.5/0.5, synthetic reads of the ~1.5 kb
 LogNormal length distribution, float32 posteriors, synthetic dense table.
-A "step" is one decode of one resident batch of `--reads` reads per GPU.  Reads are independent:
+A "step" is one decode of one resident batch of `--reads` reads per GPU (default: all 100k reads
+of the config, 132 GB of float32 posteriors).  Reads are independent:
 each rank owns its own batch and table replica, there is no collective on the data path
 (weak scaling); ranks only exchange the step time (max) and the decoded base count (sum).
 """
@@ -36,14 +37,14 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--reads", type=int, default=32768, help="reads per GPU per step")
+    ap.add_argument("--reads", type=int, default=100000, help="reads per GPU per step (config 3: 100k)")
     ap.add_argument("--beam-width", type=int, default=16)
     ap.add_argument("--context-len", type=int, default=12)
     ap.add_argument("--no-lm", action="store_true", help="config 2: pure CTC (use with --beam-width 6)")
     ap.add_argument("--fixed-len", type=int, default=None, help="bases per read instead of the LogNormal")
     ap.add_argument("--f64", action="store_true", help="float64 posteriors (assembled global matrices)")
     ap.add_argument("--seed", type=int, default=3)
-    ap.add_argument("--e2e-reads", type=int, default=2048, help="reads in the host-buffer end-to-end leg")
+    ap.add_argument("--e2e-reads", type=int, default=8192, help="reads in the host-buffer end-to-end leg")
     ap.add_argument("--cpu-reads", type=int, default=512, help="reads in the CPU baseline sample (also parity-checked)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
