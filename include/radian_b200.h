@@ -125,6 +125,9 @@ int radian_decode_batch_host(const void *post, int post_is_f64, const int64_t *f
  *                     [read_chunk_ranges[r], read_chunk_ranges[r+1]), the k-th of them starts at
  *                     global row k*step of the read (create_vstack, :12-34).
  *  out_row_offsets    n_reads+1 row offsets into `out` (row counts from radian_assemble_plan).
+ *  max_chunk_rows     as returned by radian_assemble_plan: the largest chunk, negated when the
+ *                     layout is ragged (some chunk other than a read's last is shorter), which
+ *                     selects the general lookup instead of the closed form.
  *  out_is_f64         per batch: 1 writes float64 rows (rows covered by more than one chunk are
  *                     L1-normalised in float64, others are exact casts), 0 writes float32
  *                     (only valid when no row of the batch is covered twice).

@@ -80,30 +80,51 @@ def assemble_matrices(matrices, step_size):
     return out
 
 
-def assemble_batch_device(chunks, chunk_row_offsets, read_chunk_ranges, step_size):
-    """Resident variant: ``chunks`` (rows,5) float32 CUDA tensor, the two offset arrays as host
-    numpy int64.  Returns (out CUDA tensor (sum T,5), out_row_offsets CUDA int64 tensor).  Runs on
-    the current torch stream without synchronising."""
+class AssemblePlan:
+    """Host-side planning of a batch (row counts, float64 promotion, offsets) done once and kept on
+    the device, so that the assembly itself is a single asynchronous kernel launch."""
+
+    def __init__(self, chunk_row_offsets, read_chunk_ranges, step_size, device):
+        import torch
+
+        cro = np.ascontiguousarray(chunk_row_offsets, dtype=np.int64)
+        rcr = np.ascontiguousarray(read_chunk_ranges, dtype=np.int64)
+        n = len(rcr) - 1
+        rows = np.zeros(n, dtype=np.int64)
+        any_ov = ctypes.c_int(0)
+        maxrows = ctypes.c_int32(0)
+        _native.check(lib.radian_assemble_plan(_native.np_ptr(cro), _native.np_ptr(rcr), n, int(step_size),
+                                               _native.np_ptr(rows), ctypes.byref(any_ov), ctypes.byref(maxrows)))
+        oro = np.zeros(n + 1, dtype=np.int64)
+        oro[1:] = np.cumsum(rows)
+        self.n_reads = n
+        self.step = int(step_size)
+        self.max_chunk_rows = int(maxrows.value)
+        self.total_rows = int(oro[-1])
+        self.f64 = bool(any_ov.value)
+        self.rows_in = int(cro[-1])
+        self.d_cro = torch.from_numpy(cro).to(device)
+        self.d_rcr = torch.from_numpy(rcr).to(device)
+        self.out_row_offsets = torch.from_numpy(oro).to(device)
+
+
+def assemble_batch_device(chunks, chunk_row_offsets=None, read_chunk_ranges=None, step_size=None, plan=None,
+                          out=None):
+    """Resident variant: ``chunks`` (rows,5) float32 CUDA tensor; either the two host offset arrays
+    + step (a plan is built) or a ready ``AssemblePlan``.  Returns (out CUDA tensor (sum T,5),
+    out_row_offsets CUDA int64 tensor).  Runs on the current torch stream without synchronising."""
     import torch
 
-    cro = np.ascontiguousarray(chunk_row_offsets, dtype=np.int64)
-    rcr = np.ascontiguousarray(read_chunk_ranges, dtype=np.int64)
-    n = len(rcr) - 1
-    rows = np.zeros(n, dtype=np.int64)
-    any_ov = ctypes.c_int(0)
-    maxrows = ctypes.c_int32(0)
-    _native.check(lib.radian_assemble_plan(_native.np_ptr(cro), _native.np_ptr(rcr), n, int(step_size),
-                                           _native.np_ptr(rows), ctypes.byref(any_ov), ctypes.byref(maxrows)))
-    oro = np.zeros(n + 1, dtype=np.int64)
-    oro[1:] = np.cumsum(rows)
-    dev = chunks.device
-    d_cro = torch.from_numpy(cro).to(dev, non_blocking=True)
-    d_rcr = torch.from_numpy(rcr).to(dev, non_blocking=True)
-    d_oro = torch.from_numpy(oro).to(dev, non_blocking=True)
-    f64 = bool(any_ov.value)
-    out = torch.empty((int(oro[-1]), 5), dtype=torch.float64 if f64 else torch.float32, device=dev)
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    _native.check(lib.radian_assemble_batch_dev(chunks.data_ptr(), d_cro.data_ptr(), d_rcr.data_ptr(),
-                                                d_oro.data_ptr(), n, int(step_size), int(maxrows.value),
-                                                int(oro[-1]), out.data_ptr(), int(f64), ctypes.c_void_p(stream)))
-    return out, d_oro
+    if plan is None:
+        plan = AssemblePlan(chunk_row_offsets, read_chunk_ranges, step_size, chunks.device)
+    if chunks.shape[0] != plan.rows_in:
+        raise ValueError("chunks tensor does not match the plan")
+    if out is None:
+        out = torch.empty((plan.total_rows, 5), dtype=torch.float64 if plan.f64 else torch.float32,
+                          device=chunks.device)
+    stream = torch.cuda.current_stream(chunks.device).cuda_stream
+    _native.check(lib.radian_assemble_batch_dev(chunks.data_ptr(), plan.d_cro.data_ptr(), plan.d_rcr.data_ptr(),
+                                                plan.out_row_offsets.data_ptr(), plan.n_reads, plan.step,
+                                                plan.max_chunk_rows, plan.total_rows, out.data_ptr(), int(plan.f64),
+                                                ctypes.c_void_p(stream)))
+    return out, plan.out_row_offsets
