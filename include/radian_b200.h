@@ -48,7 +48,7 @@ extern "C" {
 #define RADIAN_READ_SEQ_OVERFLOW 1   /* decoded sequence longer than the caller's slot */
 #define RADIAN_READ_TRIE_OVERFLOW 2  /* back-pointer arena too small even after compaction */
 
-#define RADIAN_MAX_BEAM_WIDTH 32
+#define RADIAN_MAX_BEAM_WIDTH 128
 #define RADIAN_MAX_CONTEXT 13
 
 typedef struct radian_table radian_table_t;

@@ -218,13 +218,12 @@ static int check_decode_args(const void *post, const int64_t *fo, int n_reads, i
     return RADIAN_OK;
 }
 
-extern "C" int radian_decode_batch_dev(const void *post, int post_is_f64, const int64_t *frame_offsets, int n_reads,
-                                       const int32_t *order, int64_t max_frames, int beam_width,
-                                       const radian_table_t *table, int len_context, double s_threshold,
-                                       double r_threshold, uint8_t *out_seq, const int64_t *seq_offsets,
-                                       int64_t *out_len, double *out_score, int32_t *out_status,
-                                       uint64_t *out_counters, int64_t arena_nodes, void *workspace,
-                                       size_t workspace_bytes, radian_stream_t stream)
+static int decode_batch_dev_impl(const void *post, int post_is_f64, const int64_t *frame_offsets, int n_reads,
+                                 const int32_t *order, int64_t max_frames, int beam_width,
+                                 const radian_table_t *table, int len_context, double s_threshold,
+                                 double r_threshold, uint8_t *out_seq, const int64_t *seq_offsets, int64_t *out_len,
+                                 double *out_score, int32_t *out_status, uint64_t *out_counters, int64_t arena_nodes,
+                                 void *workspace, size_t workspace_bytes, const int *ready, cudaStream_t st)
 {
     int rc = check_decode_args(post, frame_offsets, n_reads, beam_width, table, len_context, out_seq, seq_offsets,
                                out_len, out_score, out_status);
@@ -246,7 +245,6 @@ extern "C" int radian_decode_batch_dev(const void *post, int post_is_f64, const 
         set_error("radian_decode_batch_dev: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
         return RADIAN_E_ARG;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     if (table) {
         rc = table_prepare_gate(const_cast<radian_table_t *>(table), r_threshold, st);
         if (rc) return rc;
@@ -272,11 +270,52 @@ extern "C" int radian_decode_batch_dev(const void *post, int post_is_f64, const 
     a.queue = (int *)workspace;
     a.arena = (uint32_t *)((char *)workspace + 256);
     a.arena_cap = (int)cap;
+    a.ready = ready;
     return decode_launch(a, post_is_f64 != 0, device, st);
 }
 
-// One pass over the reads listed in `sel` (indices into the caller's batch); results are written
-// to the caller's arrays at those indices.  arena_nodes = 0 uses the default arena size.
+extern "C" int radian_decode_batch_dev(const void *post, int post_is_f64, const int64_t *frame_offsets, int n_reads,
+                                       const int32_t *order, int64_t max_frames, int beam_width,
+                                       const radian_table_t *table, int len_context, double s_threshold,
+                                       double r_threshold, uint8_t *out_seq, const int64_t *seq_offsets,
+                                       int64_t *out_len, double *out_score, int32_t *out_status,
+                                       uint64_t *out_counters, int64_t arena_nodes, void *workspace,
+                                       size_t workspace_bytes, radian_stream_t stream)
+{
+    return decode_batch_dev_impl(post, post_is_f64, frame_offsets, n_reads, order, max_frames, beam_width, table,
+                                 len_context, s_threshold, r_threshold, out_seq, seq_offsets, out_len, out_score,
+                                 out_status, out_counters, arena_nodes, workspace, workspace_bytes, nullptr,
+                                 (cudaStream_t)stream);
+}
+
+// Page-locked scratch of the calling host thread (flag values going up, results coming down);
+// grows, never shrinks, and is not returned at thread exit (the CUDA context may be gone by then).
+static void *pinned_scratch(size_t bytes)
+{
+    static thread_local void *p = nullptr;
+    static thread_local size_t cap = 0;
+    if (bytes <= cap) return p;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        p = nullptr;
+        return nullptr;
+    }
+    cap = want;
+    return p;
+}
+
+// One streamed pass over the reads listed in `sel` (indices into the caller's batch); results are
+// written to the caller's arrays at those indices.  arena_nodes = 0 uses the default arena size.
+//
+// The kernel is launched first and the posteriors follow: the reads are queued longest first, the
+// copy stream sends them over PCIe in exactly that order and publishes, every few megabytes, how
+// many reads have landed (`ready`); a read group that pops a read which is still in flight waits
+// for it.  The transfer, which is the slower of the two at ~20 B per frame, is therefore the only
+// thing on the critical path; the decode of read k overlaps the copies of reads k+1...
 static int decode_host_pass(const void *post, int post_is_f64, const int64_t *frame_offsets,
                             const std::vector<int32_t> &sel, int beam_width, const radian_table_t *table,
                             int len_context, double s_threshold, double r_threshold, uint8_t *out_seq,
@@ -285,97 +324,150 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
 {
     const int n = (int)sel.size();
     const size_t esz = post_is_f64 ? 8 : 4;
-    // compact sub-batch: offsets relative to the packed copies
+    const size_t row = 5 * esz;
+    constexpr size_t kPublishBytes = 8u << 20;  // a flag update after at most this much payload
+    // queue position k holds read sel[q[k]]: longest first, ties in caller order
+    std::vector<int32_t> q(n);
+    for (int i = 0; i < n; ++i) q[i] = i;
+    auto T_of = [&](int i) { return frame_offsets[sel[i] + 1] - frame_offsets[sel[i]]; };
+    std::stable_sort(q.begin(), q.end(), [&](int32_t x, int32_t y) { return T_of(x) > T_of(y); });
+    // the device sees the reads renumbered by queue position and packed in that order
     std::vector<int64_t> fo(n + 1, 0), so(n + 1, 0);
     int64_t max_frames = 0;
-    for (int i = 0; i < n; ++i) {
-        const int r = sel[i];
-        const int64_t T = frame_offsets[r + 1] - frame_offsets[r];
-        fo[i + 1] = fo[i] + T;
-        so[i + 1] = so[i] + (seq_offsets[r + 1] - seq_offsets[r]);
+    for (int k = 0; k < n; ++k) {
+        const int r = sel[q[k]];
+        const int64_t T = T_of(q[k]);
+        fo[k + 1] = fo[k] + T;
+        so[k + 1] = so[k] + (seq_offsets[r + 1] - seq_offsets[r]);
         max_frames = T > max_frames ? T : max_frames;
     }
-    // longest reads first: the tail of the device work queue is then made of short reads
-    std::vector<int32_t> order(n);
-    for (int i = 0; i < n; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(),
-                     [&](int32_t x, int32_t y) { return fo[x + 1] - fo[x] > fo[y + 1] - fo[y]; });
     const int64_t frames = fo[n], seq_bytes = so[n];
     const size_t ws_bytes = radian_decode_workspace_bytes(device, beam_width, n, max_frames, arena_nodes);
     {
         int krc = keep_pool(device);
         if (krc) return krc;
     }
-    cudaStream_t st;
+    // copy plan: runs of queue-adjacent reads that are also adjacent in the caller's buffer go in
+    // one transfer; `pub` = reads published after the transfer
+    struct Xfer {
+        int64_t dst_frame, src_frame, n_frames;
+        int pub;  // reads landed after this transfer, or 0 when no flag update follows it
+    };
+    std::vector<Xfer> plan;
+    size_t unpublished = 0;
+    for (int k = 0; k < n;) {
+        int j = k;
+        size_t bytes = (size_t)T_of(q[k]) * row;
+        while (j + 1 < n && sel[q[j + 1]] == sel[q[j]] + 1 && bytes < kPublishBytes) {
+            ++j;
+            bytes += (size_t)T_of(q[j]) * row;
+        }
+        unpublished += bytes;
+        const bool pub = unpublished >= kPublishBytes || j + 1 == n;
+        plan.push_back({fo[k], frame_offsets[sel[q[k]]], fo[j + 1] - fo[k], pub ? j + 1 : 0});
+        if (pub) unpublished = 0;
+        k = j + 1;
+    }
+    // page-locked scratch: flag values | len | score | status | counters | sequences
+    const size_t o_flag = 0;
+    const size_t o_len = (plan.size() * 4 + 15) & ~(size_t)15;
+    const size_t o_score = o_len + (size_t)n * 8;
+    const size_t o_status = o_score + (size_t)n * 16;
+    const size_t o_cnt = (o_status + (size_t)n * 4 + 15) & ~(size_t)15;
+    const size_t o_seq = o_cnt + (out_counters ? (size_t)n * 16 : 0);
+    char *hp = (char *)pinned_scratch(o_seq + (size_t)seq_bytes + 16);
+    if (!hp) {
+        set_error("radian_decode_batch_host: cannot page-lock %zu bytes of host scratch", o_seq + (size_t)seq_bytes);
+        return RADIAN_E_CUDA;
+    }
+    int *h_flag = (int *)(hp + o_flag);
+    int64_t *h_len = (int64_t *)(hp + o_len);
+    double *h_score = (double *)(hp + o_score);
+    int32_t *h_status = (int32_t *)(hp + o_status);
+    uint64_t *h_cnt = (uint64_t *)(hp + o_cnt);
+    uint8_t *h_seq = (uint8_t *)(hp + o_seq);
+    for (size_t i = 0; i < plan.size(); ++i) h_flag[i] = plan[i].pub;
+
+    cudaStream_t st = nullptr, cs = nullptr;
+    cudaEvent_t ev = nullptr;
     RADIAN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    RADIAN_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    RADIAN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     void *d_post = nullptr, *d_ws = nullptr;
     int64_t *d_fo = nullptr, *d_so = nullptr, *d_len = nullptr;
-    int32_t *d_order = nullptr, *d_status = nullptr;
+    int32_t *d_status = nullptr;
+    int *d_ready = nullptr;
     uint8_t *d_seq = nullptr;
     double *d_score = nullptr;
     uint64_t *d_cnt = nullptr;
-    std::vector<uint8_t> h_seq((size_t)(seq_bytes ? seq_bytes : 1));
-    std::vector<int64_t> h_len(n);
-    std::vector<double> h_score((size_t)n * 2);
-    std::vector<int32_t> h_status(n);
-    std::vector<uint64_t> h_cnt((size_t)n * 2);
     int ret = RADIAN_OK;
+    bool launched = false;
     cudaError_t e;
 #define TRY(x)                                   \
     if (ret == RADIAN_OK && (e = (x)) != cudaSuccess) ret = cuda_fail(e, #x)
-    TRY(cudaMallocAsync(&d_post, (size_t)(frames ? frames : 1) * 5 * esz, st));
+    TRY(cudaMallocAsync(&d_post, (size_t)(frames ? frames : 1) * row, st));
     TRY(cudaMallocAsync(&d_ws, ws_bytes, st));
     TRY(cudaMallocAsync(&d_fo, (size_t)(n + 1) * 8, st));
     TRY(cudaMallocAsync(&d_so, (size_t)(n + 1) * 8, st));
     TRY(cudaMallocAsync(&d_len, (size_t)n * 8, st));
-    TRY(cudaMallocAsync(&d_order, (size_t)n * 4, st));
     TRY(cudaMallocAsync(&d_status, (size_t)n * 4, st));
+    TRY(cudaMallocAsync(&d_ready, 256, st));
     TRY(cudaMallocAsync(&d_seq, (size_t)(seq_bytes ? seq_bytes : 1), st));
     TRY(cudaMallocAsync(&d_score, (size_t)n * 16, st));
     if (out_counters) TRY(cudaMallocAsync(&d_cnt, (size_t)n * 16, st));
-    // contiguous runs of selected reads are copied with one transfer each
-    for (int i = 0; i < n && ret == RADIAN_OK;) {
-        int j = i;
-        while (j + 1 < n && sel[j + 1] == sel[j] + 1) ++j;
-        const int64_t f0 = frame_offsets[sel[i]], f1 = frame_offsets[sel[j] + 1];
-        if (f1 > f0)
-            TRY(cudaMemcpyAsync((char *)d_post + (size_t)fo[i] * 5 * esz, (const char *)post + (size_t)f0 * 5 * esz,
-                                (size_t)(f1 - f0) * 5 * esz, cudaMemcpyHostToDevice, st));
-        i = j + 1;
-    }
     TRY(cudaMemcpyAsync(d_fo, fo.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_so, so.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(d_order, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    if (ret == RADIAN_OK)
-        ret = radian_decode_batch_dev(d_post, post_is_f64, d_fo, n, d_order, max_frames, beam_width, table,
-                                      len_context, s_threshold, r_threshold, d_seq, d_so, d_len, d_score, d_status,
-                                      d_cnt, arena_nodes, d_ws, ws_bytes, st);
-    TRY(cudaMemcpyAsync(h_seq.data(), d_seq, (size_t)seq_bytes, cudaMemcpyDeviceToHost, st));
-    TRY(cudaMemcpyAsync(h_len.data(), d_len, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    TRY(cudaMemcpyAsync(h_score.data(), d_score, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-    TRY(cudaMemcpyAsync(h_status.data(), d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    if (out_counters) TRY(cudaMemcpyAsync(h_cnt.data(), d_cnt, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemsetAsync(d_ready, 0, 256, st));
+    TRY(cudaEventRecord(ev, st));
+    TRY(cudaStreamWaitEvent(cs, ev, 0));  // the copies need the allocations and the cleared flag
+    if (ret == RADIAN_OK) {
+        ret = decode_batch_dev_impl(d_post, post_is_f64, d_fo, n, nullptr, max_frames, beam_width, table,
+                                    len_context, s_threshold, r_threshold, d_seq, d_so, d_len, d_score, d_status,
+                                    d_cnt, arena_nodes, d_ws, ws_bytes, d_ready, st);
+        launched = (ret == RADIAN_OK);
+    }
+    for (size_t i = 0; i < plan.size() && ret == RADIAN_OK; ++i) {
+        const Xfer &x = plan[i];
+        if (x.n_frames > 0)
+            TRY(cudaMemcpyAsync((char *)d_post + (size_t)x.dst_frame * row,
+                                (const char *)post + (size_t)x.src_frame * row, (size_t)x.n_frames * row,
+                                cudaMemcpyHostToDevice, cs));
+        if (x.pub) TRY(cudaMemcpyAsync(d_ready, &h_flag[i], 4, cudaMemcpyHostToDevice, cs));
+    }
+    if (launched && ret != RADIAN_OK) {
+        // a transfer failed while the kernel is waiting for it: release the waiters so that the
+        // launch drains (its results are discarded)
+        cudaMemsetAsync(d_ready, 0x7f, 4, cs);
+    }
+    TRY(cudaMemcpyAsync(h_seq, d_seq, (size_t)seq_bytes, cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(h_len, d_len, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(h_score, d_score, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(h_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (out_counters) TRY(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(cs));
     TRY(cudaStreamSynchronize(st));
 #undef TRY
-    void *frees[] = {d_post, d_ws, d_fo, d_so, d_len, d_order, d_status, d_seq, d_score, d_cnt};
+    void *frees[] = {d_post, d_ws, d_fo, d_so, d_len, d_status, d_ready, d_seq, d_score, d_cnt};
     for (void *p : frees)
         if (p) cudaFreeAsync(p, st);
     cudaStreamSynchronize(st);
     cudaStreamDestroy(st);
+    cudaStreamDestroy(cs);
+    cudaEventDestroy(ev);
     if (ret != RADIAN_OK) return ret;
-    for (int i = 0; i < n; ++i) {
-        const int r = sel[i];
-        out_len[r] = h_len[i];
-        out_score[2 * r] = h_score[2 * i];
-        out_score[2 * r + 1] = h_score[2 * i + 1];
-        out_status[r] = h_status[i];
+    for (int k = 0; k < n; ++k) {
+        const int r = sel[q[k]];
+        out_len[r] = h_len[k];
+        out_score[2 * r] = h_score[2 * k];
+        out_score[2 * r + 1] = h_score[2 * k + 1];
+        out_status[r] = h_status[k];
         if (out_counters) {
-            out_counters[2 * r] = h_cnt[2 * i];
-            out_counters[2 * r + 1] = h_cnt[2 * i + 1];
+            out_counters[2 * r] = h_cnt[2 * k];
+            out_counters[2 * r + 1] = h_cnt[2 * k + 1];
         }
-        const int64_t slot = so[i + 1] - so[i];
-        const int64_t ncopy = h_len[i] < slot ? h_len[i] : slot;
-        if (ncopy > 0) memcpy(out_seq + seq_offsets[r], h_seq.data() + so[i], (size_t)ncopy);
+        const int64_t slot = so[k + 1] - so[k];
+        const int64_t ncopy = h_len[k] < slot ? h_len[k] : slot;
+        if (ncopy > 0) memcpy(out_seq + seq_offsets[r], h_seq + so[k], (size_t)ncopy);
     }
     return RADIAN_OK;
 }
@@ -418,7 +510,7 @@ extern "C" int radian_decode_batch_host(const void *post, int post_is_f64, const
     if (!again.empty()) {
         rc = decode_host_pass(post, post_is_f64, frame_offsets, again, beam_width, table, len_context, s_threshold,
                               r_threshold, out_seq, seq_offsets, out_len, out_score, out_status, out_counters,
-                              32 * (worst + 1) + 64, device);
+                              (int64_t)128 * (worst + 1) + 64, device);
         if (rc) return rc;
     }
     for (int i = 0; i < n_reads; ++i)

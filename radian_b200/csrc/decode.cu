@@ -28,9 +28,7 @@
 //     live beam are slid down onto the old generation (never revisited) and the rest is dropped.
 //     Every lineage promotes each of its symbols once, so the old generation is bounded by
 //     beam_width x decoded length.  The best labeling is read back by one walk at the end.
-#include <math.h>
-
-#include "internal.h"
+#include "decode_common.cuh"
 
 namespace radian {
 
@@ -40,9 +38,6 @@ constexpr int kWarpsPerBlock = 4;
 #ifndef RADIAN_MIN_BLOCKS
 #define RADIAN_MIN_BLOCKS 6
 #endif
-constexpr unsigned kFull = 0xffffffffu;
-constexpr uint16_t kPosInvalid = 0xffff;
-constexpr int kNursery = 4096;  // arena nodes between two collections
 
 template <int G, bool LM, typename PT>
 struct __align__(16) GroupSmem {
@@ -61,115 +56,6 @@ struct __align__(16) GroupSmem {
     uint8_t newlist[G];               // candidate indices of the new beams, in list order
     uint8_t lanerank[G];              // previous rank of every lane
 };
-
-// all-ones if bit 7 of byte `B` of x is set, else zero (prmt with the sign-replicate selector bit)
-template <int B>
-__device__ __forceinline__ uint32_t byte_sign_mask(uint32_t x)
-{
-    uint32_t r;
-    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(x), "n"(0x8888 + 0x1111 * B));
-    return r;
-}
-
-__device__ __forceinline__ unsigned long long hash_step(unsigned long long h, int c)
-{
-    h = (h ^ (unsigned long long)(c + 1)) * 0x9E3779B97F4A7C15ull;
-    return h ^ (h >> 29);
-}
-
-// Asynchronous global -> shared copies (LDGSTS): no register staging, completion awaited with
-// cp_async_wait_all() by the issuing thread right before the data is needed.
-template <int BYTES>
-__device__ __forceinline__ void cp_async(void *smem_dst, const void *gmem_src)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    if (BYTES == 16)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-    else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-
-// one posterior row (5 values of 4 or 8 bytes; rows are only element-aligned) -> smem
-template <typename PT>
-__device__ __forceinline__ void prefetch_row(PT *dst, const PT *post, long long frame)
-{
-    const PT *r = post + frame * 5;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) cp_async<sizeof(PT)>(dst + i, r + i);
-}
-
-// Per-frame work shared by all beams of a read, done by the lane that loaded the frame.
-// Reference: decode.py:135-138 (s_entropies), 67-76 (normalise, entropy), 54-55 (base sum and
-// p/S of combine_dists).  float32 input follows the numpy>=2 promotion the pinned oracle uses.
-// The entropy only feeds the comparison H > s_threshold (decode.py:93): a float32 estimate with
-// the hardware log decides it unless it lands within 1e-4 of the threshold, in which case the
-// reference's exact operation order is evaluated.
-template <bool LM>
-__device__ __forceinline__ void make_record(const double *raw, double s_thr, double *rec)
-{
-    double v[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) v[i] = raw[i];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) rec[i] = v[i];
-    if (LM) {
-        const double S = __dadd_rn(__dadd_rn(__dadd_rn(v[0], v[1]), v[2]), v[3]);
-        double q[4];
-        float Ha = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            q[i] = (S == 0.0) ? v[i] : v[i] / S;
-            rec[6 + i] = q[i];
-            const float qf = (float)q[i];
-            if (qf > 0.0f) Ha -= qf * __logf(qf);
-        }
-        rec[10] = S;
-        bool gate = Ha > (float)s_thr;
-        if (!(fabsf(Ha - (float)s_thr) > 1e-4f)) {
-            double H = 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (q[i] > 0.0) H = __dadd_rn(H, __dmul_rn(q[i], log(q[i])));
-            gate = -H > s_thr;
-        }
-        rec[5] = gate ? 1.0 : 0.0;
-    }
-}
-
-template <bool LM>
-__device__ __forceinline__ void make_record(const float *raw, double s_thr, double *rec)
-{
-    float v[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) v[i] = raw[i];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) rec[i] = (double)v[i];
-    if (LM) {
-        const float S = __fadd_rn(__fadd_rn(__fadd_rn(v[0], v[1]), v[2]), v[3]);
-        float q[4];
-        float Ha = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            q[i] = (S == 0.0f) ? v[i] : __fdiv_rn(v[i], S);
-            rec[6 + i] = (double)q[i];
-            if (q[i] > 0.0f) Ha -= q[i] * __logf(q[i]);
-        }
-        rec[10] = (double)S;
-        bool gate = Ha > (float)s_thr;
-        if (!(fabsf(Ha - (float)s_thr) > 1e-4f)) {
-            float H = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (q[i] > 0.0f) H = __fadd_rn(H, __fmul_rn(q[i], __double2float_rn(log((double)q[i]))));
-            gate = -H > (float)s_thr;
-        }
-        rec[5] = gate ? 1.0 : 0.0;
-    }
-}
 
 // Control flow is warp-uniform everywhere: a warp carries 32/G reads, and every branch that
 // contains a warp collective is taken by all of them together (decided by a full-mask vote), so
@@ -218,7 +104,7 @@ decode_kernel(const DecodeArgs a)
                          // of its own (not merged into a live child's copy); 0 for a dead lane
     // ---- per-read (group-uniform) state
     int read = -1, top = 0, old_top = 0, na = 0, status = 0, first_lane = 0, last_lane = 0;
-    int T = 0, t = 0;
+    int T = 0, t = 0, pend = -1;  // pend: queue ticket of a read that has not landed yet
     long long kacc = 0;
     const PT *rp = (const PT *)a.post;
     unsigned long long n_lookup = 0, n_combine = 0;
@@ -228,13 +114,27 @@ decode_kernel(const DecodeArgs a)
         // ------------------------------------------------------------ fetch a read
         {
             const bool want = active && read < 0;
-            int idx = 0;
-            if (want && li == 0) idx = atomicAdd(a.queue, 1);
+            int idx = pend;
+            if (want && li == 0 && idx < 0) idx = atomicAdd(a.queue, 1);
             idx = __shfl_sync(kFull, idx, gshift);
+            // streamed batch: the posteriors arrive over PCIe in queue order while the kernel runs
+            // (a.ready = reads published by the copy stream so far).  A group whose read is still
+            // in flight keeps its queue ticket and polls again later; it must not block the other
+            // reads of its warp.
+            int landed = 0x7fffffff;
+            if (a.ready != nullptr) {
+                if (want && li == 0 && idx < a.n_reads) landed = *(const volatile int *)a.ready;
+                landed = __shfl_sync(kFull, landed, gshift);
+            }
             if (want) {
                 if (idx >= a.n_reads) {
                     active = false;
+                    pend = -1;
+                } else if (landed <= idx) {
+                    pend = idx;
                 } else {
+                    pend = -1;
+                    if (a.ready != nullptr) __threadfence();
                     read = a.order ? a.order[idx] : idx;
                     const long long foff = a.frame_offsets[read];
                     T = (int)(a.frame_offsets[read + 1] - foff);
@@ -268,22 +168,29 @@ decode_kernel(const DecodeArgs a)
             }
         }
         if (!__any_sync(kFull, active)) break;
+        const bool live = active && read >= 0;  // this group has a read to run
+        if (!__any_sync(kFull, live)) {
+            __nanosleep(1000);  // everything this warp could run is still in flight
+            continue;
+        }
 
-        // frames every active group of this warp can run before one of them finishes its read
-        int rem = active ? (T - t) : 0x7fffffff;
+        // frames every live group of this warp can run before one of them finishes its read
+        int rem = live ? (T - t) : 0x7fffffff;
         int nrun = rem;
 #pragma unroll
         for (int g = 0; g < GPW; ++g) {
             const int x = __shfl_sync(kFull, rem, g * G);
             nrun = x < nrun ? x : nrun;
         }
+        // a group waiting for its read gets another look at the flag after a bounded stretch
+        if (__any_sync(kFull, active && !live) && nrun > 256) nrun = 256;
         // (re)prime the frame tiles so that all groups of the warp refill at the same iterations
         const int tb = t;
         __syncwarp();
-        if (active && tb + li < T) prefetch_row(&sm.raw[li * 5], rp, tb + li);
+        if (live && tb + li < T) prefetch_row(&sm.raw[li * 5], rp, tb + li);
 
         for (int it = 0; it < nrun; ++it) {
-            bool run = active && status == 0;  // group-uniform
+            bool run = live && status == 0;  // group-uniform
             // -------------------------------------------------------- tile refill
             if ((it % G) == 0) {
                 cp_async_wait_all();
@@ -730,11 +637,11 @@ decode_kernel(const DecodeArgs a)
                 }
             }
         }
-        if (active) t += nrun;
+        if (live) t += nrun;
 
         // ------------------------------------------------------------ end of read
         const int succ_first = __shfl_sync(kFull, succ, first_lane);  // lane of the second best beam
-        if (active && t >= T) {
+        if (live && t >= T) {
             const long long seq_off = a.seq_offsets[read];
             const long long seq_cap = a.seq_offsets[read + 1] - seq_off;
             const double ln2 = 0.693147180559945309417;
@@ -777,7 +684,11 @@ decode_kernel(const DecodeArgs a)
 
 // ------------------------------------------------------------------------------ host side
 
-static int group_size(int beam_width) { return beam_width <= 8 ? 8 : beam_width <= 16 ? 16 : 32; }
+// lanes (<= 32) or beam slots (wide kernel) reserved per read
+static int group_size(int beam_width)
+{
+    return beam_width <= 8 ? 8 : beam_width <= 16 ? 16 : beam_width <= 32 ? 32 : beam_width <= 64 ? 64 : 128;
+}
 
 template <int G, bool LM, typename PT>
 static const void *kernel_ptr(bool count)
@@ -820,12 +731,30 @@ int decode_pick(int device, int beam_width, bool lm, bool f64, bool count, Decod
     int rc = device_info(device, &di);
     if (rc) return rc;
     const int G = group_size(beam_width);
-    const void *k = pick_kernel(G, lm, f64, count);
     int blocks = 0;
+    if (G > 32) {
+        // beam widths above 32: one warp per read, several beams per lane (decode_wide.cu)
+        const void *k = nullptr;
+        size_t smem = 0;
+        const int warps = wide_pick(beam_width, lm, f64, count, &k, &smem);
+        RADIAN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RADIAN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        RADIAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k, warps * 32, smem));
+        if (blocks < 1) blocks = 1;
+        out->kernel = k;
+        out->smem = smem;
+        out->grid = di.sm_count * blocks;
+        out->block = warps * 32;
+        out->groups_per_block = warps;
+        return 0;
+    }
+    const void *k = pick_kernel(G, lm, f64, count);
     // the kernel streams its global loads once; give shared memory the whole L1 carve-out
     RADIAN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     RADIAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k, kWarpsPerBlock * 32, 0));
     if (blocks < 1) blocks = 1;
+    out->kernel = k;
+    out->smem = 0;
     out->grid = di.sm_count * blocks;
     out->block = kWarpsPerBlock * 32;
     out->groups_per_block = kWarpsPerBlock * (32 / G);
@@ -850,15 +779,13 @@ int decode_launch(const DecodeArgs &a, bool f64, int device, cudaStream_t stream
     DecodeLaunch dl;
     int rc = decode_pick(device, a.beam_width, lm, f64, a.out_counters != nullptr, &dl);
     if (rc) return rc;
-    const int G = group_size(a.beam_width);
-    const void *k = pick_kernel(G, lm, f64, a.out_counters != nullptr);
     // no more groups than reads: extra CTAs would only touch the queue
     int64_t need = ((int64_t)a.n_reads + dl.groups_per_block - 1) / dl.groups_per_block;
     int grid = (int)(need < dl.grid ? need : dl.grid);
     if (grid < 1) grid = 1;
     DecodeArgs args = a;
     void *params[] = {(void *)&args};
-    RADIAN_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(dl.block), params, 0, stream));
+    RADIAN_CUDA(cudaLaunchKernel(dl.kernel, dim3(grid), dim3(dl.block), params, dl.smem, stream));
     return 0;
 }
 

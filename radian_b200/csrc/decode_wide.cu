@@ -1,0 +1,606 @@
+// CTC prefix beam search for beam widths above 32 (33..128), sm_100a.
+//
+// Same computation as decode.cu (radian/decode.py:100-212 of the reference: frame loop 141-204,
+// COPY 150-175, EXTEND 177-201, apply_rna_model 79-96, combine_dists 52-64, final pick 207-210)
+// and the same building blocks -- linear-domain float64 scores rescaled by exact powers of two,
+// frame records shared through shared memory, RNA rows gathered once per new beam, copy/extend
+// merge through a parent pointer, generational back-pointer arena -- laid out differently:
+//   * one warp owns a read; beam b lives in slot b/32 of lane b%32, so a lane carries BPL = 2 or 4
+//     beams in registers;
+//   * a frame first checks, with one compare per beam, that the rank order of the beams still
+//     holds (strictly) and that no extension reaches the worst beam; then only the scores are
+//     committed.  Otherwise all copies and the extensions that can reach the beam are ranked
+//     exactly: (float64 bit pattern desc, dict insertion position asc), the reference's stable
+//     sort over its insertion-ordered dict (decode.py:35-39, 145).
+#include "decode_common.cuh"
+
+namespace radian {
+
+constexpr int kWideWarps = 2;  // warps (reads) per CTA
+
+template <int BPL, bool LM, typename PT>
+struct __align__(16) WideSmem {
+    static constexpr int NB = 32 * BPL;
+    static constexpr int REC = LM ? 12 : 6;  // doubles per frame: P0..P4, gate, q0..q3, S, pad
+    double rec[32 * REC];
+    double row[LM ? NB * 4 : 4];      // RNA table row of every beam's extend-context (cp.async target)
+    double ex[NB * 4];                // extension scores of every beam
+    unsigned long long key[5 * NB];   // candidate scores: [0,NB) copies by beam id, then extensions
+    unsigned long long sh[NB];        // staged: labeling hash of every beam
+    PT raw[32 * 5];                   // next tile of posterior rows, landed by cp.async
+    uint32_t sctx[NB];                // staged: packed context
+    int32_t slen[NB];                 // staged: labeling length
+    int32_t snode[NB];                // staged: arena node
+    uint32_t kill[NB];                // byte c of word b: extension (b,c) merged into a live child's copy
+    uint16_t pos[5 * NB];             // dict insertion position of the candidate
+    uint16_t src[5 * NB];             // beam*4+c of an extension candidate
+    uint16_t rnk[5 * NB];             // rank of the candidate
+    uint16_t newlist[NB];             // candidate indices of the new beams
+    uint16_t newbeam[NB];             // beam ids that received them
+    uint16_t byrank[NB];              // beam id by rank
+    uint16_t srank[NB];               // staged: rank of every beam
+    uint8_t sgext[NB];                // staged: gate bit of every beam's extend-context
+};
+
+constexpr unsigned long long kHashEmpty = 0x243F6A8885A308D3ull;
+
+template <int BPL, bool LM, typename PT, bool COUNT>
+__global__ void __launch_bounds__(kWideWarps * 32)
+decode_wide_kernel(const DecodeArgs a)
+{
+    using SM = WideSmem<BPL, LM, PT>;
+    constexpr int NB = SM::NB;
+    constexpr int REC = SM::REC;
+    extern __shared__ __align__(16) unsigned char wide_smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    SM &sm = reinterpret_cast<SM *>(wide_smem_raw)[warp];
+    const unsigned below = (1u << lane) - 1u;
+    const int slot = blockIdx.x * kWideWarps + warp;
+
+    const int bw = a.beam_width;
+    const int L = a.L;
+    const uint32_t ctx_mask = LM ? (uint32_t)((1ull << (2 * L)) - 1ull) : 0u;
+    const int cap = a.arena_cap;
+    uint32_t *const arena = a.arena + (size_t)slot * (size_t)(cap + kNursery);
+    uint32_t *const fwd = arena + cap;
+
+    // ---- per-beam state, slot s of this lane is beam s*32+lane; a dead beam keeps zero scores
+    double ptot[BPL], pnb[BPL], pb[BPL], rcopy[BPL];
+    unsigned long long hp[BPL];  // hash of the parent labeling
+    uint32_t ctx[BPL], km[BPL];
+    int len[BPL], node[BPL], rank[BPL], plane[BPL], last[BPL], succ[BPL];
+    bool alive[BPL], gext[BPL], gcopy[BPL];
+
+    while (true) {
+        // ------------------------------------------------------------ fetch a read
+        int idx = 0;
+        if (lane == 0) {
+            idx = atomicAdd(a.queue, 1);
+            if (a.ready != nullptr && idx < a.n_reads) {
+                while (*(const volatile int *)a.ready <= idx) __nanosleep(400);
+                __threadfence();
+            }
+        }
+        idx = __shfl_sync(kFull, idx, 0);
+        if (idx >= a.n_reads) break;
+        const int read = a.order ? a.order[idx] : idx;
+        const long long foff = a.frame_offsets[read];
+        const int T = (int)(a.frame_offsets[read + 1] - foff);
+        const PT *rp = (const PT *)a.post + foff * 5;
+#pragma unroll
+        for (int s = 0; s < BPL; ++s) {
+            // initial beam: the empty labeling, pr_blank = pr_total = log 1 (decode.py:128-132)
+            alive[s] = (s == 0 && lane == 0);
+            ptot[s] = alive[s] ? 1.0 : 0.0;
+            pb[s] = ptot[s];
+            pnb[s] = 0.0;
+            rcopy[s] = 0.0;
+            hp[s] = 0;
+            ctx[s] = 0;
+            len[s] = 0;
+            node[s] = 0;
+            rank[s] = 0;
+            plane[s] = -1;
+            last[s] = 0;
+            succ[s] = s * 32 + lane;
+            km[s] = alive[s] ? 0x80808080u : 0u;
+            gext[s] = gcopy[s] = false;
+        }
+        int first = 0, last_b = 0;  // beam ids of the best and the worst ranked beam
+        int top = 1, old_top = 1, na = 1, status = 0;  // node 0 = the empty labeling
+        long long kacc = 0;
+        unsigned long long n_lookup = 0, n_combine = 0;
+
+        __syncwarp();
+        if (lane < T) prefetch_row(&sm.raw[lane * 5], rp, lane);
+
+        for (int t = 0; t < T && status == 0; ++t) {
+            // -------------------------------------------------------- tile refill
+            if ((t & 31) == 0) {
+                cp_async_wait_all();
+                __syncwarp();
+                if (t + lane < T) make_record<LM>(&sm.raw[lane * 5], a.s_thr, &sm.rec[lane * REC]);
+                __syncwarp();
+                if (t + 32 + lane < T) prefetch_row(&sm.raw[lane * 5], rp, t + 32 + lane);
+            }
+
+            // -------------------------------------------------------- nursery collection
+            if (top + NB > old_top + kNursery || top + NB > cap) {
+                // 1. mark the nursery nodes reachable from a live beam
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) {
+                    int cur = node[s];
+                    bool walking = alive[s] && cur >= old_top;
+                    while (walking) {
+                        const uint32_t w = arena[cur];
+                        if (w >> 31) break;
+                        arena[cur] = w | 0x80000000u;
+                        cur = (int)(w >> 2);
+                        walking = cur >= old_top;
+                    }
+                }
+                __syncwarp();
+                // 2. slide marked nodes down in index order (parents precede children); fwd[] keeps
+                //    the new index of every moved node for its children and for the beams
+                int cnt = old_top;
+                for (int base = old_top; base < top; base += 32) {
+                    const int i = base + lane;
+                    const uint32_t w = (i < top) ? arena[i] : 0u;
+                    const bool mk = (w >> 31) != 0;
+                    const unsigned bal = __ballot_sync(kFull, mk);
+                    const int ni = cnt + __popc(bal & below);
+                    const int par = (int)((w & 0x7fffffffu) >> 2);
+                    int npar = par;
+                    if (mk && par >= old_top) {
+                        if (par >= base)
+                            npar = cnt + __popc(bal & ((1u << (par - base)) - 1u));
+                        else
+                            npar = (int)fwd[par - old_top];
+                    }
+                    __syncwarp();
+                    if (mk) {
+                        arena[ni] = ((uint32_t)npar << 2) | (w & 3u);
+                        fwd[i - old_top] = (uint32_t)ni;
+                    }
+                    cnt += __popc(bal);
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int s = 0; s < BPL; ++s)
+                    if (alive[s] && node[s] >= old_top) node[s] = (int)fwd[node[s] - old_top];
+                __syncwarp();
+                old_top = cnt;
+                top = cnt;
+                if (top + NB > cap) {
+                    status = RADIAN_READ_TRIE_OVERFLOW;  // reported; remaining frames are skipped
+                    break;
+                }
+            }
+
+            // -------------------------------------------------------- one frame
+            const double *rec = &sm.rec[(t & 31) * REC];
+            const double P4 = rec[4];
+            const double2 P01 = *reinterpret_cast<const double2 *>(rec);
+            const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
+            bool fgate = false;
+            double2 q01 = make_double2(0, 0), q23 = make_double2(0, 0);
+            double S = 0.0;
+            if (LM) {
+                fgate = rec[5] != 0.0;
+                q01 = *reinterpret_cast<const double2 *>(rec + 6);
+                q23 = *reinterpret_cast<const double2 *>(rec + 8);
+                S = rec[10];
+            }
+            double nptot[BPL], npnb[BPL], npb[BPL];
+            unsigned long long ke[BPL][4];
+#pragma unroll
+            for (int s = 0; s < BPL; ++s) {
+                const int b = s * 32 + lane;
+                const bool av = alive[s];
+                const bool has_last = av && len[s] > 0;
+                const bool lm_copy = LM && av && len[s] >= L + 1;  // decode.py:157
+                const bool lm_ext = LM && av && len[s] >= L;       // decode.py:180
+                if (COUNT && LM) {
+                    n_lookup += __popc(__ballot_sync(kFull, lm_copy)) + __popc(__ballot_sync(kFull, lm_ext));
+                    n_combine += __popc(__ballot_sync(kFull, lm_copy && gcopy[s] && fgate)) +
+                                 __popc(__ballot_sync(kFull, lm_ext && gext[s] && fgate));
+                }
+                // COPY (decode.py:150-175)
+                double dl = has_last ? rec[last[s]] : 0.0;
+                if (LM && lm_copy && gcopy[s] && fgate)
+                    dl = __dmul_rn(__dmul_rn(__dadd_rn(rcopy[s], rec[6 + last[s]]), 0.5), S);  // decode.py:58-61
+                npnb[s] = has_last ? __dmul_rn(pnb[s], dl) : 0.0;
+                npb[s] = __dmul_rn(ptot[s], P4);
+                nptot[s] = __dadd_rn(npb[s], npnb[s]);
+                // EXTEND (decode.py:177-201)
+                double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
+                if (LM && lm_ext && gext[s] && fgate) {
+                    cp_async_wait_all();  // the row gathered when this beam was created
+                    const double2 r01 = *reinterpret_cast<const double2 *>(&sm.row[b * 4]);
+                    const double2 r23 = *reinterpret_cast<const double2 *>(&sm.row[b * 4 + 2]);
+                    d0 = __dmul_rn(__dmul_rn(__dadd_rn(r01.x, q01.x), 0.5), S);
+                    d1 = __dmul_rn(__dmul_rn(__dadd_rn(r01.y, q01.y), 0.5), S);
+                    d2 = __dmul_rn(__dmul_rn(__dadd_rn(r23.x, q23.x), 0.5), S);
+                    d3 = __dmul_rn(__dmul_rn(__dadd_rn(r23.y, q23.y), 0.5), S);
+                }
+                // a repeated symbol continues only paths that ended in a blank (decode.py:192-195)
+                const int lrep = has_last ? last[s] : -1;
+                const double e0 = __dmul_rn(lrep == 0 ? pb[s] : ptot[s], d0);
+                const double e1 = __dmul_rn(lrep == 1 ? pb[s] : ptot[s], d1);
+                const double e2 = __dmul_rn(lrep == 2 ? pb[s] : ptot[s], d2);
+                const double e3 = __dmul_rn(lrep == 3 ? pb[s] : ptot[s], d3);
+                *reinterpret_cast<double2 *>(&sm.ex[b * 4]) = make_double2(e0, e1);
+                *reinterpret_cast<double2 *>(&sm.ex[b * 4 + 2]) = make_double2(e2, e3);
+                ke[s][0] = (unsigned long long)__double_as_longlong(e0);
+                ke[s][1] = (unsigned long long)__double_as_longlong(e1);
+                ke[s][2] = (unsigned long long)__double_as_longlong(e2);
+                ke[s][3] = (unsigned long long)__double_as_longlong(e3);
+            }
+            __syncwarp();
+            // MERGE copy(X) with extend(parent(X), last(X)): the same dict key in the reference
+            unsigned long long kcopy[BPL];
+#pragma unroll
+            for (int s = 0; s < BPL; ++s) {
+                if (alive[s] && plane[s] >= 0) {
+                    const double v = sm.ex[plane[s] * 4 + last[s]];
+                    npnb[s] = __dadd_rn(npnb[s], v);
+                    nptot[s] = __dadd_rn(nptot[s], v);
+                }
+                kcopy[s] = (unsigned long long)__double_as_longlong(nptot[s]);
+                sm.key[s * 32 + lane] = alive[s] ? kcopy[s] : 0ull;
+            }
+            __syncwarp();
+
+            // SELECT (decode.py:145, 35-39): does the order still hold, does any extension compete?
+            bool ok = true;
+#pragma unroll
+            for (int s = 0; s < BPL; ++s)
+                if (alive[s] && succ[s] != s * 32 + lane) ok = ok && (kcopy[s] > sm.key[succ[s]]);
+            const bool order_ok = __all_sync(kFull, ok);
+            unsigned long long tau = 0ull;  // with room left in the beam every extension is a candidate
+            if (na >= bw) {
+                if (order_ok) {
+                    tau = sm.key[last_b];
+                } else {
+                    unsigned long long mn = ~0ull;
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s)
+                        if (alive[s] && kcopy[s] < mn) mn = kcopy[s];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned long long x = __shfl_xor_sync(kFull, mn, o);
+                        mn = x < mn ? x : mn;
+                    }
+                    tau = mn;
+                }
+            }
+            bool comp[BPL][4];
+            bool anyc = false;
+#pragma unroll
+            for (int s = 0; s < BPL; ++s)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    comp[s][c] = ((km[s] >> (8 * c + 7)) & 1u) && ke[s][c] >= tau;
+                    anyc = anyc || comp[s][c];
+                }
+            const bool need = !order_ok || __any_sync(kFull, anyc);
+
+            if (!need) {
+#pragma unroll
+                for (int s = 0; s < BPL; ++s)
+                    if (alive[s]) {
+                        ptot[s] = nptot[s];
+                        pnb[s] = npnb[s];
+                        pb[s] = npb[s];
+                    }
+            } else {
+                // ---- candidate list: copies at [0,NB) by beam id, competing extensions behind
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) sm.srank[s * 32 + lane] = (uint16_t)rank[s];
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) {
+                    int pos_copy = 5 * rank[s];
+                    if (alive[s] && plane[s] >= 0) {
+                        // a merged copy keeps the earlier of its two insertion positions
+                        const int pp = 5 * (int)sm.srank[plane[s]] + 1 + last[s];
+                        pos_copy = pp < pos_copy ? pp : pos_copy;
+                    }
+                    sm.pos[s * 32 + lane] = alive[s] ? (uint16_t)pos_copy : kPosInvalid;
+                }
+                int n_ext = 0;
+#pragma unroll
+                for (int s = 0; s < BPL; ++s)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const unsigned bal = __ballot_sync(kFull, comp[s][c]);
+                        if (comp[s][c]) {
+                            const int ci = NB + n_ext + __popc(bal & below);
+                            sm.key[ci] = ke[s][c];
+                            sm.pos[ci] = (uint16_t)(5 * rank[s] + 1 + c);
+                            sm.src[ci] = (uint16_t)((s * 32 + lane) * 4 + c);
+                        }
+                        n_ext += __popc(bal);
+                    }
+                const int m = NB + n_ext;
+                __syncwarp();
+                // ---- exact ranks
+                for (int ci = lane; ci < m; ci += 32) {
+                    const uint16_t p = sm.pos[ci];
+                    int cnt = 0xffff;
+                    if (p != kPosInvalid) {
+                        const unsigned long long k = sm.key[ci];
+                        cnt = 0;
+                        for (int j = 0; j < m; ++j) {
+                            const uint16_t pj = sm.pos[j];
+                            const unsigned long long kj = sm.key[j];
+                            cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
+                        }
+                    }
+                    sm.rnk[ci] = (uint16_t)cnt;
+                }
+                __syncwarp();
+                bool survive[BPL];
+                unsigned survb[BPL], evb[BPL];
+                int new_rank[BPL];
+                int n_surv = 0;
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) {
+                    new_rank[s] = (int)sm.rnk[s * 32 + lane];
+                    survive[s] = alive[s] && new_rank[s] < bw;
+                    survb[s] = __ballot_sync(kFull, survive[s]);
+                    evb[s] = __ballot_sync(kFull, alive[s] && !survive[s]);
+                    n_surv += __popc(survb[s]);
+                }
+                int n_new = 0;
+                for (int base = NB; base < m; base += 32) {
+                    const int ci = base + lane;
+                    const bool isnew = ci < m && sm.rnk[ci] < bw;
+                    const unsigned bal = __ballot_sync(kFull, isnew);
+                    if (isnew) sm.newlist[n_new + __popc(bal & below)] = (uint16_t)ci;
+                    n_new += __popc(bal);
+                }
+
+                if (n_new > 0) {
+                    // ---- stage what the new beams inherit from their parents
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) {
+                        const int b = s * 32 + lane;
+                        sm.sctx[b] = ctx[s];
+                        sm.slen[b] = len[s];
+                        sm.snode[b] = node[s];
+                        sm.sh[b] = len[s] > 0 ? hash_step(hp[s], last[s]) : kHashEmpty;
+                        sm.sgext[b] = (uint8_t)gext[s];
+                    }
+                    if (LM) cp_async_wait_all();  // every lane's rows have landed before a child reads them
+                    __syncwarp();
+                    bool take[BPL];
+                    int ford[BPL], item[BPL];
+                    double p_r[BPL];
+                    int fbase = 0;
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) {
+                        const unsigned freeb = ~survb[s];
+                        ford[s] = fbase + __popc(freeb & below);
+                        fbase += __popc(freeb);
+                        take[s] = !survive[s] && ford[s] < n_new;
+                        item[s] = take[s] ? (int)sm.newlist[ford[s]] : 0;
+                        p_r[s] = 0.0;
+                        if (LM && take[s]) {
+                            const int sc = (int)sm.src[item[s]];
+                            if (sm.sgext[sc >> 2]) p_r[s] = sm.row[sc];  // row[parent*4 + c]
+                        }
+                    }
+                    __syncwarp();  // all reads of parent rows done before any row is replaced
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) {
+                        const int b = s * 32 + lane;
+                        if (survive[s]) {
+                            ptot[s] = nptot[s];
+                            pnb[s] = npnb[s];
+                            pb[s] = npb[s];
+                            rank[s] = new_rank[s];
+                            if (plane[s] >= 0) {
+                                unsigned ev = 0;
+#pragma unroll
+                                for (int s2 = 0; s2 < BPL; ++s2)
+                                    if ((plane[s] >> 5) == s2) ev = evb[s2];
+                                if ((ev >> (plane[s] & 31)) & 1u) plane[s] = -1;
+                            }
+                        } else if (take[s]) {
+                            const int sc = (int)sm.src[item[s]];
+                            const int pbm = sc >> 2;
+                            const int c = sc & 3;
+                            const double scv = __longlong_as_double((long long)sm.key[item[s]]);
+                            ptot[s] = scv;
+                            pnb[s] = scv;
+                            pb[s] = 0.0;
+                            rank[s] = (int)sm.rnk[item[s]];
+                            node[s] = top + ford[s];
+                            len[s] = sm.slen[pbm] + 1;
+                            ctx[s] = (sm.sctx[pbm] << 2) | (uint32_t)c;
+                            last[s] = c;
+                            hp[s] = sm.sh[pbm];
+                            unsigned sv = 0;
+#pragma unroll
+                            for (int s2 = 0; s2 < BPL; ++s2)
+                                if ((pbm >> 5) == s2) sv = survb[s2];
+                            plane[s] = ((sv >> (pbm & 31)) & 1u) ? pbm : -1;
+                            alive[s] = true;
+                            arena[node[s]] = ((uint32_t)sm.snode[pbm] << 2) | (uint32_t)c;
+                            sm.newbeam[ford[s]] = (uint16_t)b;
+                            if (LM) {
+                                gcopy[s] = sm.sgext[pbm] != 0;
+                                rcopy[s] = p_r[s];
+                                gext[s] = false;
+                                if (len[s] >= L) {
+                                    const uint32_t ci = ctx[s] & ctx_mask;
+                                    const uint32_t gwd = __ldg(a.gate + (ci >> 5));
+                                    const double *row = a.table + (size_t)ci * 4;
+                                    cp_async<16>(&sm.row[b * 4], row);
+                                    cp_async<16>(&sm.row[b * 4 + 2], row + 2);
+                                    gext[s] = (gwd >> (ci & 31u)) & 1u;
+                                }
+                            }
+                        } else {
+                            alive[s] = false;
+                            ptot[s] = pnb[s] = pb[s] = 0.0;
+                        }
+                    }
+                    top += n_new;
+                    na = n_surv + n_new;
+                    __syncwarp();  // parents' staged values have been consumed
+                    // a surviving beam whose parent labeling was just (re)created points at it again
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s)
+                        if (take[s]) {
+                            const int b = s * 32 + lane;
+                            sm.sh[b] = hash_step(hp[s], last[s]);
+                            sm.slen[b] = len[s];
+                        }
+                    __syncwarp();
+                    for (int k = 0; k < n_new; ++k) {
+                        const int zb = (int)sm.newbeam[k];
+                        const unsigned long long zh = sm.sh[zb];
+                        const int zlen = sm.slen[zb];
+#pragma unroll
+                        for (int s = 0; s < BPL; ++s)
+                            if (survive[s] && plane[s] < 0 && len[s] == zlen + 1 && hp[s] == zh) plane[s] = zb;
+                    }
+                    // the beam set changed: refresh which extensions are merged into a live child
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) sm.kill[s * 32 + lane] = 0u;
+                    __syncwarp();
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s)
+                        if (alive[s] && plane[s] >= 0)
+                            reinterpret_cast<uint8_t *>(sm.kill)[plane[s] * 4 + last[s]] = 0x80;
+                    __syncwarp();
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) km[s] = alive[s] ? (0x80808080u & ~sm.kill[s * 32 + lane]) : 0u;
+                } else {
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s)
+                        if (alive[s]) {  // nothing new entered: every beam stays
+                            ptot[s] = nptot[s];
+                            pnb[s] = npnb[s];
+                            pb[s] = npb[s];
+                            rank[s] = new_rank[s];
+                        }
+                }
+                // successor of every beam, best and worst beam
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < BPL; ++s)
+                    if (alive[s]) sm.byrank[rank[s]] = (uint16_t)(s * 32 + lane);
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < BPL; ++s)
+                    succ[s] = (alive[s] && rank[s] + 1 < na) ? (int)sm.byrank[rank[s] + 1] : s * 32 + lane;
+                first = (int)sm.byrank[0];
+                last_b = (int)sm.byrank[na - 1];
+                __syncwarp();
+            }
+
+            // RESCALE by the exponent of the best beam (an exact power of two), every 4th frame: a
+            // float32-derived probability is >= 2^-149, so at most 596 binades are lost in between
+            if ((t & 3) == 3) {
+                int hi = 0;
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) {
+                    const int x = __shfl_sync(kFull, __double2hiint(ptot[s]), first & 31);
+                    if ((first >> 5) == s) hi = x;
+                }
+                const int ex = (hi >> 20) & 0x7ff;
+                if (ex != 0 && ex != 0x7ff) {
+                    const double sc = __hiloint2double((2046 - ex) << 20, 0);
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) {
+                        ptot[s] *= sc;
+                        pnb[s] *= sc;
+                        pb[s] *= sc;
+                    }
+                    kacc += ex - 1023;
+                }
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+
+        // ------------------------------------------------------------ end of read
+        const double ln2 = 0.693147180559945309417;
+        if (status == 0) {
+            const long long seq_off = a.seq_offsets[read];
+            const long long seq_cap = a.seq_offsets[read + 1] - seq_off;
+            int second = -1;
+#pragma unroll
+            for (int s = 0; s < BPL; ++s) {
+                const int x = __shfl_sync(kFull, succ[s], first & 31);
+                if ((first >> 5) == s) second = x;
+            }
+#pragma unroll
+            for (int s = 0; s < BPL; ++s) {
+                const int b = s * 32 + lane;
+                if (b == first) {
+                    const long long n = len[s];
+                    int st = 0;
+                    if (n > seq_cap) st = RADIAN_READ_SEQ_OVERFLOW;
+                    int c = node[s];
+                    for (long long i = n - 1; i >= 0; --i) {
+                        const uint32_t w = arena[c] & 0x7fffffffu;
+                        if (i < seq_cap) a.out_seq[seq_off + i] = (uint8_t)(w & 3u);
+                        c = (int)(w >> 2);
+                    }
+                    a.out_len[read] = n;
+                    a.out_score[2 * read] = (ptot[s] > 0.0) ? log(ptot[s]) + (double)kacc * ln2 : -INFINITY;
+                    if (second == first) a.out_score[2 * read + 1] = NAN;
+                    a.out_status[read] = st;
+                    if (a.out_counters) {
+                        a.out_counters[2 * read] = n_lookup;
+                        a.out_counters[2 * read + 1] = n_combine;
+                    }
+                }
+                if (second != first && b == second)
+                    a.out_score[2 * read + 1] = (ptot[s] > 0.0) ? log(ptot[s]) + (double)kacc * ln2 : -INFINITY;
+            }
+        } else if (lane == 0) {
+            a.out_len[read] = 0;
+            a.out_score[2 * read] = NAN;
+            a.out_score[2 * read + 1] = NAN;
+            a.out_status[read] = status;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------ host side
+
+template <int BPL, bool LM, typename PT>
+static const void *wide_ptr(bool count)
+{
+    return count ? (const void *)decode_wide_kernel<BPL, LM, PT, true>
+                 : (const void *)decode_wide_kernel<BPL, LM, PT, false>;
+}
+
+int wide_pick(int beam_width, bool lm, bool f64, bool count, const void **kernel, size_t *smem_bytes)
+{
+    const int bpl = beam_width <= 64 ? 2 : 4;
+#define RADIAN_WIDE(B)                                                                           \
+    if (bpl == B) {                                                                              \
+        if (lm) {                                                                                \
+            *kernel = f64 ? wide_ptr<B, true, double>(count) : wide_ptr<B, true, float>(count);   \
+            *smem_bytes = kWideWarps * (f64 ? sizeof(WideSmem<B, true, double>) : sizeof(WideSmem<B, true, float>)); \
+        } else {                                                                                 \
+            *kernel = f64 ? wide_ptr<B, false, double>(count) : wide_ptr<B, false, float>(count); \
+            *smem_bytes = kWideWarps * (f64 ? sizeof(WideSmem<B, false, double>) : sizeof(WideSmem<B, false, float>)); \
+        }                                                                                        \
+        return kWideWarps;                                                                       \
+    }
+    RADIAN_WIDE(2)
+    RADIAN_WIDE(4)
+#undef RADIAN_WIDE
+    return 0;
+}
+
+}  // namespace radian

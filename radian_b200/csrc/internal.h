@@ -60,9 +60,14 @@ struct DecodeArgs {
     uint32_t *arena;         // slots x (arena_cap + nursery) words: nodes, then forwarding scratch
     int arena_cap;
     int *queue;              // work-queue head, zeroed before launch
+    const int *ready;        // optional: number of reads (in queue order) whose posteriors have landed in
+                             // HBM; written by the copy stream of the _host entry point while the kernel
+                             // runs.  nullptr = everything is resident at launch.
 };
 
 struct DecodeLaunch {
+    const void *kernel;
+    size_t smem;             // dynamic shared memory per CTA
     int grid;
     int block;
     int groups_per_block;
@@ -73,5 +78,7 @@ int decode_launch(const DecodeArgs &a, bool f64, int device, cudaStream_t stream
 int decode_max_slots(int device, int beam_width);
 int64_t decode_arena_cap(int beam_width, int64_t max_frames, int64_t arena_nodes);
 int decode_nursery();
+// decode_wide.cu: kernel for beam widths 33..128; returns warps (= reads) per CTA
+int wide_pick(int beam_width, bool lm, bool f64, bool count, const void **kernel, size_t *smem_bytes);
 
 }  // namespace radian

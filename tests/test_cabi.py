@@ -68,7 +68,7 @@ def test_argument_errors_need_no_gpu():
     with pytest.raises(ValueError):
         decode.beam_search(m, "ACGT", 0, None, None, None, None, None)
     with pytest.raises(ValueError):
-        decode.beam_search(m, "ACGT", 33, None, None, None, None, None)
+        decode.beam_search(m, "ACGT", 129, None, None, None, None, None)
     with pytest.raises(ValueError):
         decode.beam_search(m, "ACG", 3, None, None, None, None, None)
     with pytest.raises(ValueError):

@@ -37,7 +37,7 @@ def tables():
     return get
 
 
-@pytest.mark.parametrize("case", [c for c in CASES if c.bw <= 32], ids=lambda c: c.name)
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
 def test_golden_decode(case, tables):
     from radian_b200 import decode
 
@@ -57,7 +57,9 @@ def test_beam_width_limit():
     from radian_b200 import decode
 
     with pytest.raises(ValueError):
-        decode.beam_search(np.full((3, 5), 0.2, np.float32), "ACGT", 64, None, None, None, None, None)
+        decode.beam_search(np.full((3, 5), 0.2, np.float32), "ACGT", 129, None, None, None, None, None)
+    with pytest.raises(ValueError):
+        decode.beam_search(np.full((3, 5), 0.2, np.float32), "ACGT", 0, None, None, None, None, None)
 
 
 def test_dropin_signature_and_lm_quirks():
@@ -111,7 +113,9 @@ def test_table_entropies_match_reference_formula():
 
 
 @pytest.mark.parametrize("bw,L,f64", [(6, 0, False), (16, 6, True), (16, 11, True), (8, 4, False),
-                                      (32, 5, True), (1, 3, True), (2, 0, True), (17, 2, False)])
+                                      (32, 5, True), (1, 3, True), (2, 0, True), (17, 2, False),
+                                      (33, 0, False), (64, 6, True), (64, 11, False), (48, 3, True),
+                                      (100, 4, False), (128, 0, True), (65, 5, True)])
 def test_batch_vs_oracle(bw, L, f64):
     """A mixed-length batch through one launch against the pinned C oracle, read by read."""
     from oracle import oracle
@@ -135,21 +139,43 @@ def test_batch_vs_oracle(bw, L, f64):
         assert int(cnt[i, 0]) == nl and int(cnt[i, 1]) == nc
 
 
-def test_arena_compaction_long_read():
+@pytest.mark.parametrize("bw,nb", [(16, (3000, 2500)), (64, (1500, 900))])
+def test_arena_compaction_long_read(bw, nb):
     """A read long enough to fill the back-pointer arena many times (compaction + flush)."""
     from oracle import oracle
     from radian_b200 import decode, synth
 
-    post, off = synth.make_reads(np.array([3000, 2500]), seed=77)
+    post, off = synth.make_reads(np.array(nb), seed=77)
     post = post.numpy()
     off = off.numpy()
     mats = [post[off[i]:off[i + 1]] for i in range(2)]
     tab = synth.make_table(7, 2)
-    seqs, scores, _ = decode.beam_search_batch(mats, 16, decode.RnaTable(tab), 0.5, 0.5, 7, return_details=True)
+    seqs, scores, _ = decode.beam_search_batch(mats, bw, decode.RnaTable(tab), 0.5, 0.5, 7, return_details=True)
     for i, m in enumerate(mats):
-        oseq, osc, _, _ = oracle.beam_search(m, 16, tab, 7, 0.5, 0.5, topk=1)
+        oseq, osc, _, _ = oracle.beam_search(m, bw, tab, 7, 0.5, 0.5, topk=1)
         assert seqs[i] == "".join("ACGT"[s] for s in oseq)
         assert close(scores[i, 0], osc[0])
+
+
+def test_streamed_host_batch_order_and_results():
+    """The _host entry point queues reads longest first and streams them while the kernel runs;
+    results must come back in the caller's order, identical to one-read-at-a-time calls."""
+    from radian_b200 import decode, synth
+
+    nb = synth.read_lengths(300, 11, median=150, lo=1, hi=2500)
+    post, off = synth.make_reads(nb, seed=12)
+    post = post.numpy()
+    off = off.numpy()
+    mats = [post[off[i]:off[i + 1]] for i in range(len(nb))]
+    mats.insert(7, post[:0])
+    tab = decode.RnaTable(synth.make_table(5, 4))
+    seqs, scores, cnt = decode.beam_search_batch(mats, 16, tab, 0.5, 0.5, 5, return_details=True)
+    for i in (0, 7, 8, 100, 299, 300):
+        one, sc1, c1 = decode.beam_search_batch([mats[i]], 16, tab, 0.5, 0.5, 5, return_details=True)
+        assert one[0] == seqs[i]
+        assert sc1[0, 0] == scores[i, 0]
+        assert (c1[0] == cnt[i]).all()
+    assert seqs[7] == ""
 
 
 def test_assembly_golden():
