@@ -4,7 +4,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -325,6 +328,12 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     const int n = (int)sel.size();
     const size_t esz = post_is_f64 ? 8 : 4;
     const size_t row = 5 * esz;
+    static const bool trace = getenv("RADIAN_TRACE") != nullptr;
+    double tr[8] = {0};
+    auto stamp = [&](int i) {
+        if (trace) tr[i] = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    stamp(0);
     constexpr size_t kPublishBytes = 8u << 20;  // a flag update after at most this much payload
     // queue position k holds read sel[q[k]]: longest first, ties in caller order
     std::vector<int32_t> q(n);
@@ -426,6 +435,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
                                     d_cnt, arena_nodes, d_ws, ws_bytes, d_ready, st);
         launched = (ret == RADIAN_OK);
     }
+    stamp(1);
     for (size_t i = 0; i < plan.size() && ret == RADIAN_OK; ++i) {
         const Xfer &x = plan[i];
         if (x.n_frames > 0)
@@ -439,13 +449,16 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
         // launch drains (its results are discarded)
         cudaMemsetAsync(d_ready, 0x7f, 4, cs);
     }
+    stamp(2);
     TRY(cudaMemcpyAsync(h_seq, d_seq, (size_t)seq_bytes, cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(h_len, d_len, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(h_score, d_score, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(h_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (out_counters) TRY(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(cs));
+    stamp(3);
     TRY(cudaStreamSynchronize(st));
+    stamp(4);
 #undef TRY
     void *frees[] = {d_post, d_ws, d_fo, d_so, d_len, d_status, d_ready, d_seq, d_score, d_cnt};
     for (void *p : frees)
@@ -469,6 +482,12 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
         const int64_t ncopy = h_len[k] < slot ? h_len[k] : slot;
         if (ncopy > 0) memcpy(out_seq + seq_offsets[r], h_seq + so[k], (size_t)ncopy);
     }
+    stamp(5);
+    if (trace)
+        fprintf(stderr, "[radian] host pass: %d reads, %zu transfers, %.2f GB | plan+alloc+launch %.1f ms, submit %.1f ms, "
+                "copies done +%.1f ms, kernel+results done +%.1f ms, scatter %.1f ms, total %.1f ms\n",
+                n, plan.size(), (double)frames * row / 1e9, 1e3 * (tr[1] - tr[0]), 1e3 * (tr[2] - tr[1]),
+                1e3 * (tr[3] - tr[2]), 1e3 * (tr[4] - tr[3]), 1e3 * (tr[5] - tr[4]), 1e3 * (tr[5] - tr[0]));
     return RADIAN_OK;
 }
 

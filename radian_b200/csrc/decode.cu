@@ -201,7 +201,8 @@ decode_kernel(const DecodeArgs a)
             }
 
             // -------------------------------------------------------- nursery collection
-            if (__any_sync(kFull, run && (top + G > old_top + kNursery || top + G > cap))) {
+            // checked once per tile: a frame adds at most G nodes per read, a tile at most G*G
+            if ((it % G) == 0 && __any_sync(kFull, run && (top + G * G > old_top + kNursery || top + G * G > cap))) {
                 // every running group of the warp collects (early collection is harmless)
                 // 1. mark nursery nodes reachable from a live beam (stop at the old generation or
                 //    at a node somebody marked in an earlier step)
@@ -257,7 +258,7 @@ decode_kernel(const DecodeArgs a)
                 if (run) {
                     old_top = cnt;
                     top = cnt;
-                    if (top + G > cap) {
+                    if (top + G * G > cap) {
                         status = RADIAN_READ_TRIE_OVERFLOW;  // reported; remaining frames are skipped
                         run = false;
                         alive = false;
@@ -322,11 +323,12 @@ decode_kernel(const DecodeArgs a)
             // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference.
             // Which pairs merge only changes when the beam set changes, so the pairing (plane,
             // km) is state; per frame only the parent's extension score has to be fetched.
-            *reinterpret_cast<double2 *>(&sm.ex[li * 4]) = make_double2(e0, e1);
-            *reinterpret_cast<double2 *>(&sm.ex[li * 4 + 2]) = make_double2(e2, e3);
+            // (two planes of G double2 each: 16-byte stride per lane, no bank conflicts)
+            *reinterpret_cast<double2 *>(&sm.ex[li * 2]) = make_double2(e0, e1);
+            *reinterpret_cast<double2 *>(&sm.ex[2 * G + li * 2]) = make_double2(e2, e3);
             __syncwarp();
             if (av && plane >= 0) {
-                const double v = sm.ex[plane * 4 + last];
+                const double v = sm.ex[(last >> 1) * (2 * G) + plane * 2 + (last & 1)];
                 npnb = __dadd_rn(npnb, v);
                 nptot = __dadd_rn(nptot, v);
             }
@@ -391,11 +393,10 @@ decode_kernel(const DecodeArgs a)
             }
 
             if (!__any_sync(kFull, full)) {
-                if (av) {
-                    ptot = nptot;
-                    pnb = npnb;
-                    pb = npb;
-                }
+                // (a dead lane's new values are zero as well)
+                ptot = nptot;
+                pnb = npnb;
+                pb = npb;
             } else {
                 // all groups of the warp go through the ranking; one that did not ask for it has no
                 // extension candidates and gets its current order back
@@ -580,21 +581,28 @@ decode_kernel(const DecodeArgs a)
                         na = __popc(survb) + n_new;
                     }
                     // a surviving beam whose parent labeling was just (re)created points at it
-                    // again: compare parent hash + length with every new beam
-                    unsigned nm = GBALLOT(take);
-                    int nmax = __popc(nm);
+                    // again: the new beams publish hash + length, every orphan compares its parent
+                    // hash with them
+                    if (__any_sync(kFull, survive && plane < 0 && len > 0)) {
+                        __syncwarp();  // this frame's readers of key / k32 / lanerank are done
+                        if (take) {
+                            sm.key[ford] = h;
+                            sm.k32[ford] = (uint32_t)len;
+                            sm.lanerank[ford] = (uint8_t)li;
+                        }
+                        int nmax = n_new;
 #pragma unroll
-                    for (int o = 16; o >= G; o >>= 1) {
-                        const int x = __shfl_xor_sync(kFull, nmax, o);
-                        nmax = x > nmax ? x : nmax;
-                    }
-                    for (int k = 0; k < nmax; ++k) {
-                        const bool have = nm != 0u;
-                        const int zl = have ? __ffs(nm) - 1 : li;
-                        nm &= nm - 1;
-                        const unsigned long long zh = __shfl_sync(kFull, h, zl + gshift);
-                        const int zlen = __shfl_sync(kFull, len, zl + gshift);
-                        if (have && survive && plane < 0 && len == zlen + 1 && hp == zh && len > 0) plane = zl;
+                        for (int o = 16; o >= G; o >>= 1) {
+                            const int x = __shfl_xor_sync(kFull, nmax, o);
+                            nmax = x > nmax ? x : nmax;
+                        }
+                        __syncwarp();
+                        for (int k = 0; k < nmax; ++k) {
+                            const unsigned long long zh = sm.key[k];
+                            const int zlen = (int)sm.k32[k];
+                            if (k < n_new && survive && plane < 0 && len == zlen + 1 && hp == zh)
+                                plane = (int)sm.lanerank[k];
+                        }
                     }
                     // the beam set changed: refresh which extensions are merged into a live child
                     sm.kill[li] = 0u;
