@@ -397,11 +397,13 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     uint8_t *h_seq = (uint8_t *)(hp + o_seq);
     for (size_t i = 0; i < plan.size(); ++i) h_flag[i] = plan[i].pub;
 
-    cudaStream_t st = nullptr, cs = nullptr;
-    cudaEvent_t ev = nullptr;
+    cudaStream_t st = nullptr, cs[2] = {nullptr, nullptr};
+    cudaEvent_t ev = nullptr, ev_last = nullptr;
     RADIAN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    RADIAN_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    RADIAN_CUDA(cudaStreamCreateWithFlags(&cs[0], cudaStreamNonBlocking));
+    RADIAN_CUDA(cudaStreamCreateWithFlags(&cs[1], cudaStreamNonBlocking));
     RADIAN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    RADIAN_CUDA(cudaEventCreateWithFlags(&ev_last, cudaEventDisableTiming));
     void *d_post = nullptr, *d_ws = nullptr;
     int64_t *d_fo = nullptr, *d_so = nullptr, *d_len = nullptr;
     int32_t *d_status = nullptr;
@@ -428,7 +430,9 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     TRY(cudaMemcpyAsync(d_so, so.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemsetAsync(d_ready, 0, 256, st));
     TRY(cudaEventRecord(ev, st));
-    TRY(cudaStreamWaitEvent(cs, ev, 0));  // the copies need the allocations and the cleared flag
+    // the copies need the allocations and the cleared counters
+    TRY(cudaStreamWaitEvent(cs[0], ev, 0));
+    TRY(cudaStreamWaitEvent(cs[1], ev, 0));
     if (ret == RADIAN_OK) {
         ret = decode_batch_dev_impl(d_post, post_is_f64, d_fo, n, nullptr, max_frames, beam_width, table,
                                     len_context, s_threshold, r_threshold, d_seq, d_so, d_len, d_score, d_status,
@@ -436,18 +440,31 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
         launched = (ret == RADIAN_OK);
     }
     stamp(1);
+    // Segments (the transfers up to and including a publishing one) alternate between two copy
+    // streams, so that the fixed gap between stream-ordered copies of one stream is covered by
+    // the other stream's transfer; stream s publishes into d_ready[s].
+    int which = 0;
     for (size_t i = 0; i < plan.size() && ret == RADIAN_OK; ++i) {
         const Xfer &x = plan[i];
         if (x.n_frames > 0)
             TRY(cudaMemcpyAsync((char *)d_post + (size_t)x.dst_frame * row,
                                 (const char *)post + (size_t)x.src_frame * row, (size_t)x.n_frames * row,
-                                cudaMemcpyHostToDevice, cs));
-        if (x.pub) TRY(cudaMemcpyAsync(d_ready, &h_flag[i], 4, cudaMemcpyHostToDevice, cs));
+                                cudaMemcpyHostToDevice, cs[which]));
+        if (x.pub) {
+            TRY(cudaMemcpyAsync(d_ready + which, &h_flag[i], 4, cudaMemcpyHostToDevice, cs[which]));
+            if (i + 1 == plan.size()) {
+                // the other stream's counter stops short of n: let it catch up once everything landed
+                TRY(cudaEventRecord(ev_last, cs[which]));
+                TRY(cudaStreamWaitEvent(cs[which ^ 1], ev_last, 0));
+                TRY(cudaMemcpyAsync(d_ready + (which ^ 1), &h_flag[i], 4, cudaMemcpyHostToDevice, cs[which ^ 1]));
+            }
+            which ^= 1;
+        }
     }
     if (launched && ret != RADIAN_OK) {
         // a transfer failed while the kernel is waiting for it: release the waiters so that the
         // launch drains (its results are discarded)
-        cudaMemsetAsync(d_ready, 0x7f, 4, cs);
+        cudaMemsetAsync(d_ready, 0x7f, 8, cs[0]);
     }
     stamp(2);
     TRY(cudaMemcpyAsync(h_seq, d_seq, (size_t)seq_bytes, cudaMemcpyDeviceToHost, st));
@@ -455,7 +472,8 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     TRY(cudaMemcpyAsync(h_score, d_score, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(h_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (out_counters) TRY(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-    TRY(cudaStreamSynchronize(cs));
+    TRY(cudaStreamSynchronize(cs[0]));
+    TRY(cudaStreamSynchronize(cs[1]));
     stamp(3);
     TRY(cudaStreamSynchronize(st));
     stamp(4);
@@ -465,8 +483,10 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
         if (p) cudaFreeAsync(p, st);
     cudaStreamSynchronize(st);
     cudaStreamDestroy(st);
-    cudaStreamDestroy(cs);
+    cudaStreamDestroy(cs[0]);
+    cudaStreamDestroy(cs[1]);
     cudaEventDestroy(ev);
+    cudaEventDestroy(ev_last);
     if (ret != RADIAN_OK) return ret;
     for (int k = 0; k < n; ++k) {
         const int r = sel[q[k]];

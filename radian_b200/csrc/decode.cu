@@ -123,7 +123,12 @@ decode_kernel(const DecodeArgs a)
             // reads of its warp.
             int landed = 0x7fffffff;
             if (a.ready != nullptr) {
-                if (want && li == 0 && idx < a.n_reads) landed = *(const volatile int *)a.ready;
+                if (want && li == 0 && idx < a.n_reads) {
+                    // two copy streams publish alternating segments; both counters must have passed
+                    const unsigned long long v = *(const volatile unsigned long long *)a.ready;
+                    const int r0 = (int)(unsigned)v, r1 = (int)(unsigned)(v >> 32);
+                    landed = r0 < r1 ? r0 : r1;
+                }
                 landed = __shfl_sync(kFull, landed, gshift);
             }
             if (want) {

@@ -78,7 +78,12 @@ decode_wide_kernel(const DecodeArgs a)
         if (lane == 0) {
             idx = atomicAdd(a.queue, 1);
             if (a.ready != nullptr && idx < a.n_reads) {
-                while (*(const volatile int *)a.ready <= idx) __nanosleep(400);
+                while (true) {
+                    const unsigned long long v = *(const volatile unsigned long long *)a.ready;
+                    const int r0 = (int)(unsigned)v, r1 = (int)(unsigned)(v >> 32);
+                    if ((r0 < r1 ? r0 : r1) > idx) break;
+                    __nanosleep(400);
+                }
                 __threadfence();
             }
         }

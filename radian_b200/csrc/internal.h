@@ -60,9 +60,10 @@ struct DecodeArgs {
     uint32_t *arena;         // slots x (arena_cap + nursery) words: nodes, then forwarding scratch
     int arena_cap;
     int *queue;              // work-queue head, zeroed before launch
-    const int *ready;        // optional: number of reads (in queue order) whose posteriors have landed in
-                             // HBM; written by the copy stream of the _host entry point while the kernel
-                             // runs.  nullptr = everything is resident at launch.
+    const int *ready;        // optional, 2 ints (8-byte aligned): reads (in queue order) whose posteriors
+                             // have landed in HBM, as published by each of the two copy streams of the
+                             // _host entry point while the kernel runs; a read is usable once both
+                             // counters have passed it.  nullptr = everything is resident at launch.
 };
 
 struct DecodeLaunch {
