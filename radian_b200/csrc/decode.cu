@@ -275,6 +275,20 @@ decode_kernel(const DecodeArgs a)
             }
             const bool av = alive && run;  // this lane holds a beam that takes part in this frame
 
+            // RESCALE by an exact power of two when the best beam (the largest value of the group)
+            // has fallen below 2^-256.  Checked every frame: a float32-derived probability is
+            // >= 2^-149, so nothing gets near the float64 limit in between.  Idle groups hold zeros.
+            {
+                const int exb = __shfl_sync(kFull, __double2hiint(ptot), first_lane) >> 20;
+                if (exb != 0 && exb < 1023 - 256) {
+                    const double sc = __hiloint2double((2046 - exb) << 20, 0);
+                    ptot *= sc;
+                    pnb *= sc;
+                    pb *= sc;
+                    kacc += exb - 1023;
+                }
+            }
+
             // -------------------------------------------------------- one frame
             const double *rec = &sm.rec[(it % G) * REC];
             const double P4 = rec[4];
@@ -289,21 +303,22 @@ decode_kernel(const DecodeArgs a)
                 q23 = *reinterpret_cast<const double2 *>(rec + 8);
                 S = rec[10];
             }
-            const bool has_last = av && len > 0;
-            const bool lm_copy = LM && av && len >= L + 1;  // decode.py:157
-            const bool lm_ext = LM && av && len >= L;       // decode.py:180
+            // (a dead lane computes on stale flags; all its scores are zero and stay zero)
+            const bool lm_copy = LM && (COUNT ? av : true) && len >= L + 1;  // decode.py:157
+            const bool lm_ext = LM && (COUNT ? av : true) && len >= L;       // decode.py:180
             if (COUNT && LM) {
                 n_lookup += __popc(GBALLOT(lm_copy)) + __popc(GBALLOT(lm_ext));
                 n_combine += __popc(GBALLOT(lm_copy && gcopy && fgate)) + __popc(GBALLOT(lm_ext && gext && fgate));
             }
 
             // COPY (decode.py:150-175)
-            double dl_ = has_last ? rec[last] : 0.0;
+            // the empty labeling and dead lanes have pnb == 0, so their copy needs no special case
+            double dl_ = rec[last];
             if (LM && lm_copy && gcopy && fgate) {
                 const double ql = rec[6 + last];
                 dl_ = __dmul_rn(__dmul_rn(__dadd_rn(rcopy, ql), 0.5), S);  // decode.py:58-61
             }
-            double npnb = has_last ? __dmul_rn(pnb, dl_) : 0.0;
+            double npnb = __dmul_rn(pnb, dl_);
             const double npb = __dmul_rn(ptot, P4);
             double nptot = __dadd_rn(npb, npnb);
 
@@ -318,8 +333,9 @@ decode_kernel(const DecodeArgs a)
                 d2 = __dmul_rn(__dmul_rn(__dadd_rn(r23.x, q23.x), 0.5), S);
                 d3 = __dmul_rn(__dmul_rn(__dadd_rn(r23.y, q23.y), 0.5), S);
             }
-            // a repeated symbol continues only paths that ended in a blank (decode.py:192-195)
-            const int lrep = has_last ? last : -1;
+            // a repeated symbol continues only paths that ended in a blank (decode.py:192-195); for
+            // the empty labeling (last = 0 by convention) pb == ptot, so the rule is harmless there
+            const int lrep = last;
             const double e0 = __dmul_rn(lrep == 0 ? pb : ptot, d0);
             const double e1 = __dmul_rn(lrep == 1 ? pb : ptot, d1);
             const double e2 = __dmul_rn(lrep == 2 ? pb : ptot, d2);
@@ -345,20 +361,37 @@ decode_kernel(const DecodeArgs a)
             const unsigned long long kcopy = (unsigned long long)__double_as_longlong(nptot);
             const uint32_t kc32 = av ? (uint32_t)(kcopy >> 32) : 0u;
             const uint32_t ksucc = __shfl_sync(kFull, kc32, succ);
+            const uint32_t kworst = __shfl_sync(kFull, kc32, last_lane);
+            const bool prune = (na >= bw);
+            bool ranks_changed = false;
+            {
+                // QUIET frame (the common case, one vote): in every group of the warp the order of
+                // the copies holds strictly, the beam is full and no extension, merged ones
+                // excepted, reaches the high word of the worst copy.
+                const uint32_t y0 = (uint32_t)__double2hiint(e0) & byte_sign_mask<0>(km);
+                const uint32_t y1 = (uint32_t)__double2hiint(e1) & byte_sign_mask<1>(km);
+                const uint32_t y2 = (uint32_t)__double2hiint(e2) & byte_sign_mask<2>(km);
+                const uint32_t y3 = (uint32_t)__double2hiint(e3) & byte_sign_mask<3>(km);
+                const uint32_t ymax = max(max(y0, y1), max(y2, y3));
+                const bool quiet = !run || ((kc32 > ksucc || succ == lane) && prune && ymax < kworst);
+                if (__all_sync(kFull, quiet)) {
+                    ptot = nptot;  // (a dead lane's new values are zero as well)
+                    pnb = npnb;
+                    pb = npb;
+                    continue;
+                }
+            }
             const bool order_ok = GBALLOT(kc32 > ksucc || succ == lane) == GBITS;
             // worst copy of the group: the last lane of the order when the order still holds.
             // With room left in the beam every extension is a candidate (threshold 1: keys are
             // or-ed with 1 so that a zero-probability extension of a live beam still counts).
-            uint32_t tau = __shfl_sync(kFull, kc32, last_lane);
-            const bool prune = (na >= bw);
-            tau = (prune && tau > 1u) ? tau : 1u;
+            uint32_t tau = (prune && kworst > 1u) ? kworst : 1u;
             // extension keys, zeroed where the extension is merged into a child or the lane is dead
             const uint32_t x0 = ((uint32_t)__double2hiint(e0) | 1u) & byte_sign_mask<0>(km);
             const uint32_t x1 = ((uint32_t)__double2hiint(e1) | 1u) & byte_sign_mask<1>(km);
             const uint32_t x2 = ((uint32_t)__double2hiint(e2) | 1u) & byte_sign_mask<2>(km);
             const uint32_t x3 = ((uint32_t)__double2hiint(e3) | 1u) & byte_sign_mask<3>(km);
             const uint32_t xmax = max(max(x0, x1), max(x2, x3));
-            bool ranks_changed = false;
             bool full;
 
             if (__any_sync(kFull, !order_ok)) {
@@ -633,21 +666,6 @@ decode_kernel(const DecodeArgs a)
                     last_lane = (int)sm.newlist[na - 1] + gshift;
                 }
                 __syncwarp();
-            }
-
-            // RESCALE by the exponent of the best beam (an exact power of two).  Every 4th frame is
-            // enough: a float32-derived probability is >= 2^-149, so the best beam loses at most
-            // 596 binades in between, far from the float64 limit.
-            if ((it & 3) == 3) {
-                const int hi = __shfl_sync(kFull, __double2hiint(ptot), first_lane);
-                const int ex = (hi >> 20) & 0x7ff;
-                if (run && ex != 0 && ex != 0x7ff) {
-                    const double sc = __hiloint2double((2046 - ex) << 20, 0);
-                    ptot *= sc;
-                    pnb *= sc;
-                    pb *= sc;
-                    kacc += ex - 1023;
-                }
             }
         }
         if (live) t += nrun;
