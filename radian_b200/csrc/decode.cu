@@ -314,7 +314,8 @@ decode_kernel(const DecodeArgs a)
             // COPY (decode.py:150-175)
             // the empty labeling and dead lanes have pnb == 0, so their copy needs no special case
             double dl_ = rec[last];
-            if (LM && lm_copy && gcopy && fgate) {
+            // (gcopy implies len >= L+1 and gext implies len >= L: both are set when the beam is created)
+            if (LM && gcopy && fgate) {
                 const double ql = rec[6 + last];
                 dl_ = __dmul_rn(__dmul_rn(__dadd_rn(rcopy, ql), 0.5), S);  // decode.py:58-61
             }
@@ -324,7 +325,7 @@ decode_kernel(const DecodeArgs a)
 
             // EXTEND (decode.py:177-201)
             double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
-            if (LM && lm_ext && gext && fgate) {
+            if (LM && gext && fgate) {
                 cp_async_wait_all();  // the row gathered when this beam was created
                 const double2 r01 = *reinterpret_cast<const double2 *>(&sm.row[li * 4]);
                 const double2 r23 = *reinterpret_cast<const double2 *>(&sm.row[li * 4 + 2]);
@@ -359,7 +360,7 @@ decode_kernel(const DecodeArgs a)
             // lane of the next-ranked beam) and re-validated with one compare per beam; an
             // extension matters only if it is not below the worst copy of a full beam.
             const unsigned long long kcopy = (unsigned long long)__double_as_longlong(nptot);
-            const uint32_t kc32 = av ? (uint32_t)(kcopy >> 32) : 0u;
+            const uint32_t kc32 = (uint32_t)(kcopy >> 32);  // zero on a dead lane: its scores are zero
             const uint32_t ksucc = __shfl_sync(kFull, kc32, succ);
             const uint32_t kworst = __shfl_sync(kFull, kc32, last_lane);
             const bool prune = (na >= bw);
