@@ -35,6 +35,14 @@ namespace radian {
 constexpr int kWarpsPerBlock = 4;
 // resident CTAs per SM asked from ptxas (A/B on B200, profiles/r1_minblocks_ab.txt): 6 CTAs =
 // 24 warps at <= 80 registers once the tile prefetch and the RNA rows moved to shared memory
+// A/B on B200 (scripts/ab_variants.sh): replacing the pb/ptot selects of the extension scores by
+// one more float64 multiply is slower (8.47e9 vs 9.01e9 frames/s): the FP64 pipe is the scarce unit
+#ifndef RADIAN_EREP
+#define RADIAN_EREP 0
+#endif
+#ifndef RADIAN_EX_ASM
+#define RADIAN_EX_ASM 1
+#endif
 #ifndef RADIAN_MIN_BLOCKS
 #define RADIAN_MIN_BLOCKS 6
 #endif
@@ -79,6 +87,12 @@ decode_kernel(const DecodeArgs a)
     const unsigned belowg = (1u << li) - 1u;  // lanes of my group below me, group-relative bits
     const int gib = (threadIdx.x >> 5) * GPW + gw;  // group in block
     GroupSmem<G, LM, PT> &sm = smem[gib];
+    // shared-memory address of this lane's extension scores, pinned in a register (the compiler
+    // would otherwise rebuild it from the lane and group indices every frame)
+#if RADIAN_EX_ASM
+    unsigned ex_addr = (unsigned)__cvta_generic_to_shared(&sm.ex[li * 2]);
+    asm volatile("" : "+r"(ex_addr));
+#endif
     const int slot = blockIdx.x * (kWarpsPerBlock * GPW) + gib;
     // votes: bits of my group's lanes, group-relative
 #define GBALLOT(p) ((__ballot_sync(kFull, (p)) >> gshift) & GBITS)
@@ -298,7 +312,7 @@ decode_kernel(const DecodeArgs a)
             double2 q01 = make_double2(0, 0), q23 = make_double2(0, 0);
             double S = 0.0;
             if (LM) {
-                fgate = rec[5] != 0.0;
+                fgate = __double2hiint(rec[5]) != 0;  // 1.0 or 0.0: an integer test is enough
                 q01 = *reinterpret_cast<const double2 *>(rec + 6);
                 q23 = *reinterpret_cast<const double2 *>(rec + 8);
                 S = rec[10];
@@ -313,7 +327,8 @@ decode_kernel(const DecodeArgs a)
 
             // COPY (decode.py:150-175)
             // the empty labeling and dead lanes have pnb == 0, so their copy needs no special case
-            double dl_ = rec[last];
+            const double plast = rec[last];
+            double dl_ = plast;
             // (gcopy implies len >= L+1 and gext implies len >= L: both are set when the beam is created)
             if (LM && gcopy && fgate) {
                 const double ql = rec[6 + last];
@@ -325,6 +340,7 @@ decode_kernel(const DecodeArgs a)
 
             // EXTEND (decode.py:177-201)
             double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
+            double dle = plast;  // emission of the repeated symbol in this beam's extend-context
             if (LM && gext && fgate) {
                 cp_async_wait_all();  // the row gathered when this beam was created
                 const double2 r01 = *reinterpret_cast<const double2 *>(&sm.row[li * 4]);
@@ -333,21 +349,43 @@ decode_kernel(const DecodeArgs a)
                 d1 = __dmul_rn(__dmul_rn(__dadd_rn(r01.y, q01.y), 0.5), S);
                 d2 = __dmul_rn(__dmul_rn(__dadd_rn(r23.x, q23.x), 0.5), S);
                 d3 = __dmul_rn(__dmul_rn(__dadd_rn(r23.y, q23.y), 0.5), S);
+#if RADIAN_EREP
+                dle = __dmul_rn(__dmul_rn(__dadd_rn(sm.row[li * 4 + last], rec[6 + last]), 0.5), S);
+#endif
             }
-            // a repeated symbol continues only paths that ended in a blank (decode.py:192-195); for
-            // the empty labeling (last = 0 by convention) pb == ptot, so the rule is harmless there
-            const int lrep = last;
-            const double e0 = __dmul_rn(lrep == 0 ? pb : ptot, d0);
-            const double e1 = __dmul_rn(lrep == 1 ? pb : ptot, d1);
-            const double e2 = __dmul_rn(lrep == 2 ? pb : ptot, d2);
-            const double e3 = __dmul_rn(lrep == 3 ? pb : ptot, d3);
+            // A repeated symbol continues only paths that ended in a blank (decode.py:192-195): the
+            // extension by `last` starts from pb, the others from ptot.  e0..e3 are computed from
+            // ptot (for c == last an upper bound, pb <= ptot, good enough for the quiet test below)
+            // and the exact value `erep` replaces ex[last] in shared memory; the registers are fixed
+            // up on the rare path that ranks extensions.  For the empty labeling (last = 0 by
+            // convention) pb == ptot, so the rule is harmless there.
+#if RADIAN_EREP
+            double e0 = __dmul_rn(ptot, d0);
+            double e1 = __dmul_rn(ptot, d1);
+            double e2 = __dmul_rn(ptot, d2);
+            double e3 = __dmul_rn(ptot, d3);
+            const double erep = __dmul_rn(pb, dle);
+#else
+            double e0 = __dmul_rn(last == 0 ? pb : ptot, d0);
+            double e1 = __dmul_rn(last == 1 ? pb : ptot, d1);
+            double e2 = __dmul_rn(last == 2 ? pb : ptot, d2);
+            double e3 = __dmul_rn(last == 3 ? pb : ptot, d3);
+#endif
 
             // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference.
             // Which pairs merge only changes when the beam set changes, so the pairing (plane,
             // km) is state; per frame only the parent's extension score has to be fetched.
             // (two planes of G double2 each: 16-byte stride per lane, no bank conflicts)
+#if RADIAN_EX_ASM
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ex_addr), "d"(e0), "d"(e1) : "memory");
+            asm volatile("st.shared.v2.f64 [%0+%3], {%1, %2};" ::"r"(ex_addr), "d"(e2), "d"(e3), "n"(2 * G * 8) : "memory");
+#else
             *reinterpret_cast<double2 *>(&sm.ex[li * 2]) = make_double2(e0, e1);
             *reinterpret_cast<double2 *>(&sm.ex[2 * G + li * 2]) = make_double2(e2, e3);
+#endif
+#if RADIAN_EREP
+            sm.ex[(last >> 1) * (2 * G) + li * 2 + (last & 1)] = erep;
+#endif
             __syncwarp();
             if (av && plane >= 0) {
                 const double v = sm.ex[(last >> 1) * (2 * G) + plane * 2 + (last & 1)];
@@ -382,6 +420,12 @@ decode_kernel(const DecodeArgs a)
                     continue;
                 }
             }
+#if RADIAN_EREP
+            if (last == 0) e0 = erep;
+            if (last == 1) e1 = erep;
+            if (last == 2) e2 = erep;
+            if (last == 3) e3 = erep;
+#endif
             const bool order_ok = GBALLOT(kc32 > ksucc || succ == lane) == GBITS;
             // worst copy of the group: the last lane of the order when the order still holds.
             // With room left in the beam every extension is a candidate (threshold 1: keys are
@@ -478,8 +522,24 @@ decode_kernel(const DecodeArgs a)
                     }
                     int cc = 0;
                     const uint4 *kv = reinterpret_cast<const uint4 *>(sm.k32);
+                    // the copies, then only as many extension slots as some group of the warp
+                    // filled (the others hold zero and count for nothing)
+                    int jend = n_ext < NK - G ? n_ext : NK - G;
 #pragma unroll
-                    for (int j = 0; j < NK / 4; ++j) {
+                    for (int o = 16; o >= G; o >>= 1) {
+                        const int x = __shfl_xor_sync(kFull, jend, o);
+                        jend = x > jend ? x : jend;
+                    }
+                    jend = (G + jend + 3) / 4;
+#pragma unroll
+                    for (int j = 0; j < G / 4; ++j) {
+                        const uint4 k4 = kv[j];
+                        cc += (k4.x > kc32) + (k4.y > kc32) + (k4.z > kc32) + (k4.w > kc32);
+#pragma unroll
+                        for (int e = 0; e < EPL; ++e)
+                            ce[e] += (k4.x > ke[e]) + (k4.y > ke[e]) + (k4.z > ke[e]) + (k4.w > ke[e]);
+                    }
+                    for (int j = G / 4; j < jend; ++j) {
                         const uint4 k4 = kv[j];
                         cc += (k4.x > kc32) + (k4.y > kc32) + (k4.z > kc32) + (k4.w > kc32);
 #pragma unroll
