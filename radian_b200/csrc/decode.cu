@@ -35,26 +35,23 @@ namespace radian {
 constexpr int kWarpsPerBlock = 4;
 // resident CTAs per SM asked from ptxas (A/B on B200, profiles/r1_minblocks_ab.txt): 6 CTAs =
 // 24 warps at <= 80 registers once the tile prefetch and the RNA rows moved to shared memory
-// A/B on B200 (scripts/ab_variants.sh): replacing the pb/ptot selects of the extension scores by
-// one more float64 multiply is slower (8.47e9 vs 9.01e9 frames/s): the FP64 pipe is the scarce unit
-#ifndef RADIAN_EREP
-#define RADIAN_EREP 0
-#endif
-#ifndef RADIAN_EX_ASM
-#define RADIAN_EX_ASM 1
-#endif
+// (A/B on B200, scripts/ab_variants.sh: trading the pb/ptot selects of the extension scores for one
+// more float64 multiply lost 6 %: the FP64 pipe is the scarce unit, so the frame loop avoids it)
 #ifndef RADIAN_MIN_BLOCKS
 #define RADIAN_MIN_BLOCKS 6
 #endif
 
 template <int G, bool LM, typename PT>
 struct __align__(16) GroupSmem {
-    static constexpr int REC = LM ? 12 : 6;  // doubles per frame: P0..P4, gate, q0..q3, S, pad
+    // doubles per frame (decode_common.cuh, EXT layout): P0..P4, gate, q0..q3, S, S/2, then the
+    // integer words of the quiet-frame test; 144 / 80 bytes per frame keep the record stores
+    // of neighbouring lanes on different banks
+    static constexpr int REC = LM ? 18 : 10;
     static constexpr int NK = (2 * G > 32) ? 2 * G : 32;  // candidate slots of the fast ranking path
     double rec[G * REC];
     double row[LM ? G * 4 : 4];       // RNA table row of every lane's extend-context (cp.async target)
     PT raw[G * 5];                    // next tile of posterior rows, landed by cp.async
-    double ex[G * 4];                 // extension scores of every lane, for the copy/extend merge
+    double ex[G * 2];                 // {pr_total, pr_blank} of every lane before the frame (copy/extend merge)
     unsigned long long key[5 * G];    // candidate list: [0,G) copies by lane, [G,..) extensions
     uint32_t k32[NK];                 // high words of the candidate scores (0 = empty slot)
     uint32_t kill[G];                 // byte c of word l: extension (l,c) merged into a copy
@@ -89,10 +86,8 @@ decode_kernel(const DecodeArgs a)
     GroupSmem<G, LM, PT> &sm = smem[gib];
     // shared-memory address of this lane's extension scores, pinned in a register (the compiler
     // would otherwise rebuild it from the lane and group indices every frame)
-#if RADIAN_EX_ASM
     unsigned ex_addr = (unsigned)__cvta_generic_to_shared(&sm.ex[li * 2]);
     asm volatile("" : "+r"(ex_addr));
-#endif
     const int slot = blockIdx.x * (kWarpsPerBlock * GPW) + gib;
     // votes: bits of my group's lanes, group-relative
 #define GBALLOT(p) ((__ballot_sync(kFull, (p)) >> gshift) & GBITS)
@@ -109,6 +104,7 @@ decode_kernel(const DecodeArgs a)
     unsigned long long h = 0, hp = 0;
     uint32_t ctx = 0;
     int len = 0, node = 0, rank = 0, plane = -1, last = 0;
+    int prep = 0;        // 1 if the live parent (plane) ends in the same symbol as this beam
     bool alive = false;
     double rcopy = 0;  // table value of this beam's last symbol in its copy-context; the row of the
                        // extend-context lives in sm.row[li*4..]
@@ -171,6 +167,7 @@ decode_kernel(const DecodeArgs a)
                     node = 0;
                     rank = 0;
                     plane = -1;
+                    prep = 0;
                     last = 0;
                     gext = gcopy = false;
                     succ = lane;
@@ -214,7 +211,7 @@ decode_kernel(const DecodeArgs a)
             if ((it % G) == 0) {
                 cp_async_wait_all();
                 __syncwarp();
-                if (run && tb + it + li < T) make_record<LM>(&sm.raw[li * 5], a.s_thr, &sm.rec[li * REC]);
+                if (run && tb + it + li < T) make_record<LM, true>(&sm.raw[li * 5], a.s_thr, &sm.rec[li * REC]);
                 __syncwarp();
                 if (run && tb + it + G + li < T) prefetch_row(&sm.raw[li * 5], rp, tb + it + G + li);
             }
@@ -305,90 +302,42 @@ decode_kernel(const DecodeArgs a)
 
             // -------------------------------------------------------- one frame
             const double *rec = &sm.rec[(it % G) * REC];
+            const int *reci = reinterpret_cast<const int *>(rec);
             const double P4 = rec[4];
-            const double2 P01 = *reinterpret_cast<const double2 *>(rec);
-            const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
             bool fgate = false;
-            double2 q01 = make_double2(0, 0), q23 = make_double2(0, 0);
-            double S = 0.0;
+            int hS = 0;
             if (LM) {
-                fgate = __double2hiint(rec[5]) != 0;  // 1.0 or 0.0: an integer test is enough
-                q01 = *reinterpret_cast<const double2 *>(rec + 6);
-                q23 = *reinterpret_cast<const double2 *>(rec + 8);
-                S = rec[10];
+                const int2 gs = *reinterpret_cast<const int2 *>(reci + 32);
+                fgate = gs.x != 0;
+                hS = gs.y;
             }
             // (a dead lane computes on stale flags; all its scores are zero and stay zero)
-            const bool lm_copy = LM && (COUNT ? av : true) && len >= L + 1;  // decode.py:157
-            const bool lm_ext = LM && (COUNT ? av : true) && len >= L;       // decode.py:180
             if (COUNT && LM) {
+                const bool lm_copy = av && len >= L + 1;  // decode.py:157
+                const bool lm_ext = av && len >= L;       // decode.py:180
                 n_lookup += __popc(GBALLOT(lm_copy)) + __popc(GBALLOT(lm_ext));
                 n_combine += __popc(GBALLOT(lm_copy && gcopy && fgate)) + __popc(GBALLOT(lm_ext && gext && fgate));
             }
 
             // COPY (decode.py:150-175)
             // the empty labeling and dead lanes have pnb == 0, so their copy needs no special case
-            const double plast = rec[last];
-            double dl_ = plast;
+            double dl_ = rec[last];
             // (gcopy implies len >= L+1 and gext implies len >= L: both are set when the beam is created)
-            if (LM && gcopy && fgate) {
-                const double ql = rec[6 + last];
-                dl_ = __dmul_rn(__dmul_rn(__dadd_rn(rcopy, ql), 0.5), S);  // decode.py:58-61
-            }
+            if (LM && gcopy && fgate) dl_ = __dmul_rn(__dadd_rn(rcopy, rec[6 + last]), rec[11]);  // decode.py:58-61
             double npnb = __dmul_rn(pnb, dl_);
             const double npb = __dmul_rn(ptot, P4);
             double nptot = __dadd_rn(npb, npnb);
 
-            // EXTEND (decode.py:177-201)
-            double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
-            double dle = plast;  // emission of the repeated symbol in this beam's extend-context
-            if (LM && gext && fgate) {
-                cp_async_wait_all();  // the row gathered when this beam was created
-                const double2 r01 = *reinterpret_cast<const double2 *>(&sm.row[li * 4]);
-                const double2 r23 = *reinterpret_cast<const double2 *>(&sm.row[li * 4 + 2]);
-                d0 = __dmul_rn(__dmul_rn(__dadd_rn(r01.x, q01.x), 0.5), S);
-                d1 = __dmul_rn(__dmul_rn(__dadd_rn(r01.y, q01.y), 0.5), S);
-                d2 = __dmul_rn(__dmul_rn(__dadd_rn(r23.x, q23.x), 0.5), S);
-                d3 = __dmul_rn(__dmul_rn(__dadd_rn(r23.y, q23.y), 0.5), S);
-#if RADIAN_EREP
-                dle = __dmul_rn(__dmul_rn(__dadd_rn(sm.row[li * 4 + last], rec[6 + last]), 0.5), S);
-#endif
-            }
-            // A repeated symbol continues only paths that ended in a blank (decode.py:192-195): the
-            // extension by `last` starts from pb, the others from ptot.  e0..e3 are computed from
-            // ptot (for c == last an upper bound, pb <= ptot, good enough for the quiet test below)
-            // and the exact value `erep` replaces ex[last] in shared memory; the registers are fixed
-            // up on the rare path that ranks extensions.  For the empty labeling (last = 0 by
-            // convention) pb == ptot, so the rule is harmless there.
-#if RADIAN_EREP
-            double e0 = __dmul_rn(ptot, d0);
-            double e1 = __dmul_rn(ptot, d1);
-            double e2 = __dmul_rn(ptot, d2);
-            double e3 = __dmul_rn(ptot, d3);
-            const double erep = __dmul_rn(pb, dle);
-#else
-            double e0 = __dmul_rn(last == 0 ? pb : ptot, d0);
-            double e1 = __dmul_rn(last == 1 ? pb : ptot, d1);
-            double e2 = __dmul_rn(last == 2 ? pb : ptot, d2);
-            double e3 = __dmul_rn(last == 3 ? pb : ptot, d3);
-#endif
-
-            // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference.
-            // Which pairs merge only changes when the beam set changes, so the pairing (plane,
-            // km) is state; per frame only the parent's extension score has to be fetched.
-            // (two planes of G double2 each: 16-byte stride per lane, no bank conflicts)
-#if RADIAN_EX_ASM
-            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ex_addr), "d"(e0), "d"(e1) : "memory");
-            asm volatile("st.shared.v2.f64 [%0+%3], {%1, %2};" ::"r"(ex_addr), "d"(e2), "d"(e3), "n"(2 * G * 8) : "memory");
-#else
-            *reinterpret_cast<double2 *>(&sm.ex[li * 2]) = make_double2(e0, e1);
-            *reinterpret_cast<double2 *>(&sm.ex[2 * G + li * 2]) = make_double2(e2, e3);
-#endif
-#if RADIAN_EREP
-            sm.ex[(last >> 1) * (2 * G) + li * 2 + (last & 1)] = erep;
-#endif
+            // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference.  The
+            // parent's extension by last(X) is (pr_blank or pr_total of the parent) x the emission
+            // of last(X) in the parent's extend-context, and that emission is this beam's own
+            // copy emission dl_ (same context, same gate, same table value), so only the parent's
+            // two scores travel through shared memory.  Which pairs merge only changes when the
+            // beam set changes: the pairing (plane, prep, km) is state.
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ex_addr), "d"(ptot), "d"(pb) : "memory");
             __syncwarp();
             if (av && plane >= 0) {
-                const double v = sm.ex[(last >> 1) * (2 * G) + plane * 2 + (last & 1)];
+                const double v = __dmul_rn(sm.ex[plane * 2 + prep], dl_);
                 npnb = __dadd_rn(npnb, v);
                 nptot = __dadd_rn(nptot, v);
             }
@@ -406,13 +355,32 @@ decode_kernel(const DecodeArgs a)
             {
                 // QUIET frame (the common case, one vote): in every group of the warp the order of
                 // the copies holds strictly, the beam is full and no extension, merged ones
-                // excepted, reaches the high word of the worst copy.
-                const uint32_t y0 = (uint32_t)__double2hiint(e0) & byte_sign_mask<0>(km);
-                const uint32_t y1 = (uint32_t)__double2hiint(e1) & byte_sign_mask<1>(km);
-                const uint32_t y2 = (uint32_t)__double2hiint(e2) & byte_sign_mask<2>(km);
-                const uint32_t y3 = (uint32_t)__double2hiint(e3) & byte_sign_mask<3>(km);
-                const uint32_t ymax = max(max(y0, y1), max(y2, y3));
-                const bool quiet = !run || ((kc32 > ksucc || succ == lane) && prune && ymax < kworst);
+                // excepted, can reach the worst copy.  The extensions are not computed for this:
+                // with h(x) = high word of the float64 x, (h(x) >> 20) - 1023 + mantissa fraction
+                // is a lower bound of log2 x that is short by at most 0.0861, so
+                //   h(p) + h(d) - bias + slack < h(worst)  implies  p*d < worst
+                // for slack >= 2 * 0.0861 * 2^20.  The emission d of an extension is P_c, or with
+                // the model ((r_c + q_c)/2) * S <= max(r_c, q_c) * S (one more 0.0861).
+                const int4 hp = *reinterpret_cast<const int4 *>(reci + (LM ? 24 : 12));
+                int b0 = hp.x, b1 = hp.y, b2 = hp.z, b3 = hp.w;
+                if (LM && gext && fgate) {
+                    cp_async_wait_all();  // the row gathered when this beam was created
+                    const int4 hq = *reinterpret_cast<const int4 *>(reci + 28);
+                    const int4 ra = *reinterpret_cast<const int4 *>(&sm.row[li * 4]);      // r0 lo,hi r1 lo,hi
+                    const int4 rb = *reinterpret_cast<const int4 *>(&sm.row[li * 4 + 2]);  // r2, r3
+                    b0 = max(ra.y, hq.x) + hS;
+                    b1 = max(ra.w, hq.y) + hS;
+                    b2 = max(rb.y, hq.z) + hS;
+                    b3 = max(rb.w, hq.w) + hS;
+                }
+                constexpr int kSlack = 272000;  // 3 * 0.0861 * 2^20, rounded up
+                const int z0 = b0 & (int)byte_sign_mask<0>(km);
+                const int z1 = b1 & (int)byte_sign_mask<1>(km);
+                const int z2 = b2 & (int)byte_sign_mask<2>(km);
+                const int z3 = b3 & (int)byte_sign_mask<3>(km);
+                const int ub = __double2hiint(ptot) + max(max(z0, z1), max(z2, z3)) + (kSlack - 0x3ff00000);
+                const bool quiet = !run || ((kc32 > ksucc || succ == lane) && prune && kworst >= 0x00100000u &&
+                                            ub < (int)kworst);
                 if (__all_sync(kFull, quiet)) {
                     ptot = nptot;  // (a dead lane's new values are zero as well)
                     pnb = npnb;
@@ -420,12 +388,28 @@ decode_kernel(const DecodeArgs a)
                     continue;
                 }
             }
-#if RADIAN_EREP
-            if (last == 0) e0 = erep;
-            if (last == 1) e1 = erep;
-            if (last == 2) e2 = erep;
-            if (last == 3) e3 = erep;
-#endif
+
+            // EXTEND (decode.py:177-201), only when some extension may matter
+            const double2 P01 = *reinterpret_cast<const double2 *>(rec);
+            const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
+            double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
+            if (LM && gext && fgate) {
+                const double2 q01 = *reinterpret_cast<const double2 *>(rec + 6);
+                const double2 q23 = *reinterpret_cast<const double2 *>(rec + 8);
+                const double Sh = rec[11];
+                const double2 r01 = *reinterpret_cast<const double2 *>(&sm.row[li * 4]);
+                const double2 r23 = *reinterpret_cast<const double2 *>(&sm.row[li * 4 + 2]);
+                d0 = __dmul_rn(__dadd_rn(r01.x, q01.x), Sh);
+                d1 = __dmul_rn(__dadd_rn(r01.y, q01.y), Sh);
+                d2 = __dmul_rn(__dadd_rn(r23.x, q23.x), Sh);
+                d3 = __dmul_rn(__dadd_rn(r23.y, q23.y), Sh);
+            }
+            // a repeated symbol continues only paths that ended in a blank (decode.py:192-195); for
+            // the empty labeling (last = 0 by convention) pb == ptot, so the rule is harmless there
+            const double e0 = __dmul_rn(last == 0 ? pb : ptot, d0);
+            const double e1 = __dmul_rn(last == 1 ? pb : ptot, d1);
+            const double e2 = __dmul_rn(last == 2 ? pb : ptot, d2);
+            const double e3 = __dmul_rn(last == 3 ? pb : ptot, d3);
             const bool order_ok = GBALLOT(kc32 > ksucc || succ == lane) == GBITS;
             // worst copy of the group: the last lane of the order when the order still holds.
             // With room left in the beam every extension is a candidate (threshold 1: keys are
@@ -627,6 +611,7 @@ decode_kernel(const DecodeArgs a)
                     const int p_len = __shfl_sync(kFull, len, ls);
                     const int p_node = __shfl_sync(kFull, node, ls);
                     const unsigned long long p_h = __shfl_sync(kFull, h, ls);
+                    const int p_last = __shfl_sync(kFull, last, ls);
                     double p_r = 0.0;
                     bool p_g = false;
                     if (LM) {
@@ -656,6 +641,7 @@ decode_kernel(const DecodeArgs a)
                         hp = p_h;
                         h = hash_step(p_h, c);
                         plane = ((survb >> (ls - gshift)) & 1u) ? (ls - gshift) : -1;
+                        prep = (c == p_last) ? 1 : 0;
                         alive = true;
                         arena[node] = ((uint32_t)p_node << 2) | (uint32_t)c;
                         if (LM) {
@@ -686,7 +672,7 @@ decode_kernel(const DecodeArgs a)
                         __syncwarp();  // this frame's readers of key / k32 / lanerank are done
                         if (take) {
                             sm.key[ford] = h;
-                            sm.k32[ford] = (uint32_t)len;
+                            sm.k32[ford] = (uint32_t)len | ((uint32_t)last << 30);  // len < 2^29 (arena limit)
                             sm.lanerank[ford] = (uint8_t)li;
                         }
                         int nmax = n_new;
@@ -698,9 +684,12 @@ decode_kernel(const DecodeArgs a)
                         __syncwarp();
                         for (int k = 0; k < nmax; ++k) {
                             const unsigned long long zh = sm.key[k];
-                            const int zlen = (int)sm.k32[k];
-                            if (k < n_new && survive && plane < 0 && len == zlen + 1 && hp == zh)
+                            const uint32_t zw = sm.k32[k];
+                            const int zlen = (int)(zw & 0x3fffffffu);
+                            if (k < n_new && survive && plane < 0 && len == zlen + 1 && hp == zh) {
                                 plane = (int)sm.lanerank[k];
+                                prep = ((int)(zw >> 30) == last) ? 1 : 0;
+                            }
                         }
                     }
                     // the beam set changed: refresh which extensions are merged into a live child

@@ -57,7 +57,28 @@ __device__ __forceinline__ void prefetch_row(PT *dst, const PT *post, long long 
 // The entropy only feeds the comparison H > s_threshold (decode.py:93): a float32 estimate with
 // the hardware log decides it unless it lands within 1e-4 of the threshold, in which case the
 // reference's exact operation order is evaluated.
-template <bool LM>
+//
+// EXT adds what decode.cu's quiet-frame test reads instead of the float64 values: the high words
+// of P0..P3 (int4 at double index 12 with the model, 6 without), of q0..q3 (int4 at 14), and
+// {gate, high word of S minus the exponent bias} (int2 at 16); rec[11] = S/2 (exact), so that
+// combine_dists' ((r + q)/2)*S is one add and one multiply: (r + q)*(S/2) rounds identically.
+template <bool LM, bool EXT>
+__device__ __forceinline__ void record_ext(double *rec, const double *v, const double *q, double S, bool gate)
+{
+    if (EXT) {
+        int *ri = reinterpret_cast<int *>(rec);
+        *reinterpret_cast<int4 *>(ri + (LM ? 24 : 12)) =
+            make_int4(__double2hiint(v[0]), __double2hiint(v[1]), __double2hiint(v[2]), __double2hiint(v[3]));
+        if (LM) {
+            rec[11] = 0.5 * S;
+            *reinterpret_cast<int4 *>(ri + 28) =
+                make_int4(__double2hiint(q[0]), __double2hiint(q[1]), __double2hiint(q[2]), __double2hiint(q[3]));
+            *reinterpret_cast<int2 *>(ri + 32) = make_int2(gate ? 1 : 0, __double2hiint(S) - 0x3ff00000);
+        }
+    }
+}
+
+template <bool LM, bool EXT = false>
 __device__ __forceinline__ void make_record(const double *raw, double s_thr, double *rec)
 {
     double v[5];
@@ -86,10 +107,13 @@ __device__ __forceinline__ void make_record(const double *raw, double s_thr, dou
             gate = -H > s_thr;
         }
         rec[5] = gate ? 1.0 : 0.0;
+        record_ext<LM, EXT>(rec, v, q, S, gate);
+    } else {
+        record_ext<LM, EXT>(rec, v, v, 0.0, false);
     }
 }
 
-template <bool LM>
+template <bool LM, bool EXT = false>
 __device__ __forceinline__ void make_record(const float *raw, double s_thr, double *rec)
 {
     float v[5];
@@ -117,6 +141,12 @@ __device__ __forceinline__ void make_record(const float *raw, double s_thr, doub
             gate = -H > (float)s_thr;
         }
         rec[5] = gate ? 1.0 : 0.0;
+        const double vd[4] = {(double)v[0], (double)v[1], (double)v[2], (double)v[3]};
+        const double qd[4] = {(double)q[0], (double)q[1], (double)q[2], (double)q[3]};
+        record_ext<LM, EXT>(rec, vd, qd, (double)S, gate);
+    } else {
+        const double vd[4] = {(double)v[0], (double)v[1], (double)v[2], (double)v[3]};
+        record_ext<LM, EXT>(rec, vd, vd, 0.0, false);
     }
 }
 
