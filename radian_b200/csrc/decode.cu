@@ -33,6 +33,7 @@
 namespace radian {
 
 constexpr int kWarpsPerBlock = 4;
+constexpr int kNoRmax = (int)0x80000000;
 // resident CTAs per SM asked from ptxas (A/B on B200, profiles/r1_minblocks_ab.txt): 6 CTAs =
 // 24 warps at <= 80 registers once the tile prefetch and the RNA rows moved to shared memory
 // (A/B on B200, scripts/ab_variants.sh: trading the pb/ptot selects of the extension scores for one
@@ -105,6 +106,7 @@ decode_kernel(const DecodeArgs a)
     uint32_t ctx = 0;
     int len = 0, node = 0, rank = 0, plane = -1, last = 0;
     int prep = 0;        // 1 if the live parent (plane) ends in the same symbol as this beam
+    int rmax = kNoRmax;  // max high word of the unmerged entries of this beam's table row, or kNoRmax
     bool alive = false;
     double rcopy = 0;  // table value of this beam's last symbol in its copy-context; the row of the
                        // extend-context lives in sm.row[li*4..]
@@ -168,6 +170,7 @@ decode_kernel(const DecodeArgs a)
                     rank = 0;
                     plane = -1;
                     prep = 0;
+                    rmax = kNoRmax;
                     last = 0;
                     gext = gcopy = false;
                     succ = lane;
@@ -361,24 +364,27 @@ decode_kernel(const DecodeArgs a)
                 //   h(p) + h(d) - bias + slack < h(worst)  implies  p*d < worst
                 // for slack >= 2 * 0.0861 * 2^20.  The emission d of an extension is P_c, or with
                 // the model ((r_c + q_c)/2) * S <= max(r_c, q_c) * S (one more 0.0861).
-                const int4 hp = *reinterpret_cast<const int4 *>(reci + (LM ? 24 : 12));
-                int b0 = hp.x, b1 = hp.y, b2 = hp.z, b3 = hp.w;
-                if (LM && gext && fgate) {
+                // With the model the table part of the bound, max over the unmerged symbols of
+                // h(r_c), is a per-beam constant (rmax): it is rebuilt lazily from the row in shared
+                // memory after the beam was created or its merge mask changed.
+                const bool gated = LM && gext && fgate;
+                if (LM && gated && rmax == kNoRmax) {
                     cp_async_wait_all();  // the row gathered when this beam was created
-                    const int4 hq = *reinterpret_cast<const int4 *>(reci + 28);
                     const int4 ra = *reinterpret_cast<const int4 *>(&sm.row[li * 4]);      // r0 lo,hi r1 lo,hi
                     const int4 rb = *reinterpret_cast<const int4 *>(&sm.row[li * 4 + 2]);  // r2, r3
-                    b0 = max(ra.y, hq.x) + hS;
-                    b1 = max(ra.w, hq.y) + hS;
-                    b2 = max(rb.y, hq.z) + hS;
-                    b3 = max(rb.w, hq.w) + hS;
+                    rmax = max(max(ra.y & (int)byte_sign_mask<0>(km), ra.w & (int)byte_sign_mask<1>(km)),
+                               max(rb.y & (int)byte_sign_mask<2>(km), rb.w & (int)byte_sign_mask<3>(km)));
                 }
+                // high words of q0..q3 (gated lanes) or of P0..P3
+                const int4 hx = *reinterpret_cast<const int4 *>(reci + ((LM && gated) ? 28 : (LM ? 24 : 12)));
                 constexpr int kSlack = 272000;  // 3 * 0.0861 * 2^20, rounded up
-                const int z0 = b0 & (int)byte_sign_mask<0>(km);
-                const int z1 = b1 & (int)byte_sign_mask<1>(km);
-                const int z2 = b2 & (int)byte_sign_mask<2>(km);
-                const int z3 = b3 & (int)byte_sign_mask<3>(km);
-                const int ub = __double2hiint(ptot) + max(max(z0, z1), max(z2, z3)) + (kSlack - 0x3ff00000);
+                const int z0 = hx.x & (int)byte_sign_mask<0>(km);
+                const int z1 = hx.y & (int)byte_sign_mask<1>(km);
+                const int z2 = hx.z & (int)byte_sign_mask<2>(km);
+                const int z3 = hx.w & (int)byte_sign_mask<3>(km);
+                int zmax = max(max(z0, z1), max(z2, z3));
+                if (LM && gated) zmax = max(zmax, rmax) + hS;
+                const int ub = __double2hiint(ptot) + zmax + (kSlack - 0x3ff00000);
                 const bool quiet = !run || ((kc32 > ksucc || succ == lane) && prune && kworst >= 0x00100000u &&
                                             ub < (int)kworst);
                 if (__all_sync(kFull, quiet)) {
@@ -698,6 +704,7 @@ decode_kernel(const DecodeArgs a)
                     if (run && alive && plane >= 0) reinterpret_cast<uint8_t *>(sm.kill)[plane * 4 + last] = 0x80;
                     __syncwarp();
                     if (run) km = alive ? (0x80808080u & ~sm.kill[li]) : 0u;
+                    rmax = kNoRmax;  // the merge mask (or the beam) changed
                 } else if (survive) {
                     ptot = nptot;
                     pnb = npnb;
