@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--fixed-len", type=int, default=None, help="bases per read instead of the LogNormal")
     ap.add_argument("--f64", action="store_true", help="float64 posteriors (assembled global matrices)")
     ap.add_argument("--seed", type=int, default=3)
-    ap.add_argument("--e2e-reads", type=int, default=8192, help="reads in the host-buffer end-to-end leg")
+    ap.add_argument("--e2e-reads", type=int, default=16384, help="reads in the host-buffer end-to-end leg")
     ap.add_argument("--cpu-reads", type=int, default=512, help="reads in the CPU baseline sample (also parity-checked)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -363,6 +363,19 @@ def main():
         b_alg = (8 * 5 if a.f64 else 20) * frames + 16 * n_lookup
         b_min = (8 * 5 if a.f64 else 20) * frames + 16 * n_combine
         achieved = b_alg / (kernel_ms * 1e-3) / 1e9
+        # DRAM bytes of one launch from the committed ncu capture of this very workload
+        # (profiles/r1_traffic.json); null for any other configuration
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tr = json.load(f)
+            c = tr["config"]
+            if (c["reads_per_gpu_per_step"] == a.reads and c["frames_per_gpu_per_step"] == frames
+                    and c["beam_width"] == a.beam_width and c["context_len"] == a.context_len and c["seed"] == a.seed
+                    and not a.no_lm and not a.f64 and a.fixed_len is None):
+                traffic, traffic_src = tr["traffic_bytes_per_launch"], tr["source"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -374,7 +387,8 @@ def main():
                        "l2": f"inputs {post.element_size() * post.numel() / 1e9:.1f} GB per step, far larger than L2",
                        "parallelism": f"reads sharded over {world} GPU(s), table replicated, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "decode_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "decode_kernel",
                          "algorithmic_bytes_per_launch": b_alg, "bytes_min_per_launch": b_min,
                          "frames_per_s": frames / (kernel_ms * 1e-3), "kernel_ms": kernel_ms,
                          "n_lookup_per_frame": n_lookup / max(frames, 1)},
