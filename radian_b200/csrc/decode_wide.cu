@@ -27,6 +27,7 @@ struct __align__(16) WideSmem {
     double ex[NB * 4];                // extension scores of every beam
     unsigned long long key[5 * NB];   // candidate scores: [0,NB) copies by beam id, then extensions
     unsigned long long sh[NB];        // staged: labeling hash of every beam
+    uint32_t k32[5 * NB];             // high words of the candidate scores (incremental ranking)
     PT raw[32 * 5];                   // next tile of posterior rows, landed by cp.async
     uint32_t sctx[NB];                // staged: packed context
     int32_t slen[NB];                 // staged: labeling length
@@ -323,6 +324,7 @@ decode_wide_kernel(const DecodeArgs a)
                         if (comp[s][c]) {
                             const int ci = NB + n_ext + __popc(bal & below);
                             sm.key[ci] = ke[s][c];
+                            sm.k32[ci] = (uint32_t)(ke[s][c] >> 32);
                             sm.pos[ci] = (uint16_t)(5 * rank[s] + 1 + c);
                             sm.src[ci] = (uint16_t)((s * 32 + lane) * 4 + c);
                         }
@@ -330,20 +332,72 @@ decode_wide_kernel(const DecodeArgs a)
                     }
                 const int m = NB + n_ext;
                 __syncwarp();
-                // ---- exact ranks
-                for (int ci = lane; ci < m; ci += 32) {
-                    const uint16_t p = sm.pos[ci];
-                    int cnt = 0xffff;
-                    if (p != kPosInvalid) {
-                        const unsigned long long k = sm.key[ci];
-                        cnt = 0;
-                        for (int j = 0; j < m; ++j) {
-                            const uint16_t pj = sm.pos[j];
-                            const unsigned long long kj = sm.key[j];
-                            cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
+                // ---- incremental ranks: when the copies kept their order, a copy moves down by the
+                // number of extensions that outrank it, and an extension ranks behind the copies and
+                // extensions above it.  Counted on the high words; any equal pair of high words
+                // sends the frame to the exact ranking below.
+                bool inc = order_ok && n_ext <= 2 * NB;
+                if (inc) {
+                    uint32_t kc32[BPL];
+                    int add[BPL];
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) {
+                        kc32[s] = alive[s] ? (uint32_t)(kcopy[s] >> 32) : 0u;
+                        sm.k32[s * 32 + lane] = kc32[s];
+                        add[s] = 0;
+                    }
+                    __syncwarp();
+                    bool tie = false;
+                    for (int j = 0; j < n_ext; ++j) {
+                        const uint32_t kj = sm.k32[NB + j];
+#pragma unroll
+                        for (int s = 0; s < BPL; ++s) {
+                            add[s] += kj > kc32[s];
+                            tie = tie || (alive[s] && kj == kc32[s]);
                         }
                     }
-                    sm.rnk[ci] = (uint16_t)cnt;
+                    const uint4 *kv = reinterpret_cast<const uint4 *>(sm.k32);
+                    for (int ci = NB + lane; ci < m; ci += 32) {
+                        const uint32_t k = sm.k32[ci];
+                        int cnt = 0;
+#pragma unroll 4
+                        for (int j4 = 0; j4 < NB / 4; ++j4) {
+                            const uint4 q = kv[j4];
+                            cnt += (q.x > k) + (q.y > k) + (q.z > k) + (q.w > k);
+                            tie = tie || q.x == k || q.y == k || q.z == k || q.w == k;
+                        }
+                        for (int j = 0; j < n_ext; ++j) {
+                            const uint32_t kj = sm.k32[NB + j];
+                            cnt += kj > k;
+                            tie = tie || (kj == k && NB + j != ci);
+                        }
+                        sm.rnk[ci] = (uint16_t)cnt;
+                    }
+                    if (__any_sync(kFull, tie)) {
+                        inc = false;
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < BPL; ++s)
+                            sm.rnk[s * 32 + lane] = alive[s] ? (uint16_t)(rank[s] + add[s]) : (uint16_t)0xffff;
+                    }
+                    __syncwarp();
+                }
+                // ---- exact ranks: (float64 bits desc, dict insertion position asc)
+                if (!inc) {
+                    for (int ci = lane; ci < m; ci += 32) {
+                        const uint16_t p = sm.pos[ci];
+                        int cnt = 0xffff;
+                        if (p != kPosInvalid) {
+                            const unsigned long long k = sm.key[ci];
+                            cnt = 0;
+                            for (int j = 0; j < m; ++j) {
+                                const uint16_t pj = sm.pos[j];
+                                const unsigned long long kj = sm.key[j];
+                                cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
+                            }
+                        }
+                        sm.rnk[ci] = (uint16_t)cnt;
+                    }
                 }
                 __syncwarp();
                 bool survive[BPL];
