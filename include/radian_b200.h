@@ -9,6 +9,9 @@
  *   radian_assemble_batch_*  replaces  matrix_assembly.assemble_matrices
  *                                                                    radian/matrix_assembly.py:6-53
  *                            (call site radian/basecall.py:100)
+ *   radian_stitch_batch_*    replaces  sequence_assembly.simple_assembly + argmax + index2base
+ *                                                                    radian/sequence_assembly.py:19-48,90-97
+ *                            (call site radian/basecall.py:122-123)
  *   radian_table_*           replaces  the dict built from the RNA model JSON
  *                                                                    radian/basecall.py:47-57
  *                            and the entropy memo `entr_cache`       radian/decode.py:86-90
@@ -47,6 +50,8 @@ extern "C" {
 #define RADIAN_READ_OK 0
 #define RADIAN_READ_SEQ_OVERFLOW 1   /* decoded sequence longer than the caller's slot */
 #define RADIAN_READ_TRIE_OVERFLOW 2  /* back-pointer arena too small even after compaction */
+#define RADIAN_READ_INDEX_ERROR 3    /* stitching: a fragment does not fit the reference's vote buffer
+                                       (IndexError in add_count, sequence_assembly.py:47) */
 
 #define RADIAN_MAX_BEAM_WIDTH 128
 #define RADIAN_MAX_CONTEXT 13
@@ -145,6 +150,34 @@ int radian_assemble_batch_dev(const float *chunks, const int64_t *chunk_row_offs
 int radian_assemble_batch_host(const float *chunks, const int64_t *chunk_row_offsets,
                                const int64_t *read_chunk_ranges, const int64_t *out_row_offsets,
                                int n_reads, int step, void *out, int out_is_f64, int device);
+
+/*
+ * Chunk-mode stitching for a batch of reads: replaces sequence_assembly.simple_assembly
+ * (radian/sequence_assembly.py:19-48) followed by np.argmax(consensus, axis=0) and index2base
+ * (:90-97), call site radian/basecall.py:122-123.  Consecutive fragments of a read are aligned
+ * on the first largest matching block of difflib.SequenceMatcher(None, previous, current)
+ * (including its autojunk rule for fragments of 200 symbols and more), every fragment votes for
+ * its symbols at its position, and every consensus column takes the first maximum.
+ *
+ *  frag_sym          symbols 0..3 (A,C,G,T) of all fragments of all reads back to back, i.e. the
+ *                    out_seq of a chunk-mode radian_decode_batch_* call.
+ *  frag_offsets      n_frags+1 offsets into frag_sym.
+ *  read_frag_ranges  n_reads+1 fragment indices: read r owns fragments
+ *                    [read_frag_ranges[r], read_frag_ranges[r+1]) in chunk order.
+ *  out_seq           consensus symbols of read r at out_seq[out_offsets[r] ...]; a slot as large as
+ *                    the sum of the read's fragment lengths always suffices.
+ *  out_len           consensus length per read.  As in the reference it only counts columns
+ *                    reached by the second and later fragments: a read with a single fragment
+ *                    yields an empty consensus (sequence_assembly.py:39).
+ *  out_status        RADIAN_READ_OK, or RADIAN_READ_INDEX_ERROR where the reference raises
+ *                    IndexError (the call then returns RADIAN_E_GAP).
+ *  out_votes         optional: 4 int32 vote counts (A,C,G,T) per consensus column, at
+ *                    out_votes[4 * (out_offsets[r] + column)].
+ */
+int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *frag_offsets,
+                             const int64_t *read_frag_ranges, int n_reads, uint8_t *out_seq,
+                             const int64_t *out_offsets, int64_t *out_len, int32_t *out_status,
+                             int32_t *out_votes, int device);
 
 #ifdef __cplusplus
 }

@@ -279,3 +279,86 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def gen_sequence_assembly_ext(seed=9):
+    """More stitching cases for the GPU path: long fragments (difflib's
+    'popular element' rule at len(b) >= 200), unrelated and empty fragments, drifting
+    positions, and the reference's IndexError when a fragment outgrows the vote buffer.
+    Run on its own:  python -c "from oracle import make_golden as m; m.write_sequence_assembly_ext()" """
+    _, _, sa = ref_loader.load()
+    rng = np.random.default_rng(seed)
+
+    def noisy(s, p):
+        f = list(s)
+        for j in range(len(f)):
+            if rng.random() < p:
+                f[j] = "ACGT"[rng.integers(0, 4)]
+        return "".join(f)
+
+    def rand_seq(n, probs=None):
+        return "".join("ACGT"[i] for i in rng.choice(4, n, p=probs))
+
+    lists = []
+    for _ in range(60):  # typical chunk-mode fragments
+        n = int(rng.integers(30, 500))
+        truth = rand_seq(n)
+        frags, start = [], 0
+        while start < n:
+            frags.append(noisy(truth[start:start + int(rng.integers(10, 45))], 0.04))
+            start += int(rng.integers(1, 14))
+        lists.append(frags)
+    for _ in range(12):  # long fragments: every base is 'popular' in b
+        n = int(rng.integers(600, 1500))
+        truth = rand_seq(n)
+        frags, start = [], 0
+        while start < n:
+            frags.append(noisy(truth[start:start + int(rng.integers(180, 330))], 0.02))
+            start += int(rng.integers(20, 120))
+        lists.append(frags)
+    for _ in range(8):  # long fragments with one or two rare letters (mixed popular / not)
+        n = int(rng.integers(500, 900))
+        truth = list(rand_seq(n, [0.5, 0.5, 0.0, 0.0]))
+        for j in rng.choice(n, size=max(2, n // 90), replace=False):
+            truth[j] = "GT"[rng.integers(0, 2)]
+        truth = "".join(truth)
+        frags, start = [], 0
+        while start < n:
+            frags.append(truth[start:start + int(rng.integers(190, 260))])
+            start += int(rng.integers(30, 90))
+        lists.append(frags)
+    for _ in range(10):  # unrelated / empty / tiny fragments
+        k = int(rng.integers(1, 9))
+        frags = []
+        for _ in range(k):
+            r = rng.random()
+            frags.append("" if r < 0.2 else rand_seq(int(rng.integers(1, 4))) if r < 0.4 else rand_seq(int(rng.integers(5, 40))))
+        lists.append(frags)
+    lists.append(["ACGT"])
+    lists.append([])
+    lists.append(["", ""])
+    lists.append(["AAAAAAAAAA", "AAAAAAAAAA", "AAAAA", "CAAAAAAAAAAG"])
+    lists.append([rand_seq(30)] + [rand_seq(12) + "GATTACAGATTACA" + rand_seq(3) for _ in range(5)])  # drifts left
+    lists.append([rand_seq(1200), rand_seq(20)])      # first fragment outgrows the 1000-column buffer
+    lists.append([rand_seq(400), rand_seq(700), rand_seq(900)])
+    big = rand_seq(2600)
+    lists.append([big[i:i + 300] for i in range(0, 2300, 100)])  # buffer growth several times
+    cases = []
+    for frags in lists:
+        try:
+            cons = sa.simple_assembly(frags)
+            cases.append({"fragments": frags, "consensus": sa.index2base(np.argmax(cons, axis=0)) if cons.shape[1] else "",
+                          "votes": cons.astype(int).tolist()})
+        except Exception as e:  # the reference's own failure modes are part of its behaviour
+            cases.append({"fragments": frags, "error": type(e).__name__})
+    return cases
+
+
+def write_sequence_assembly_ext():
+    import json
+
+    os.makedirs(GOLDEN, exist_ok=True)
+    cases = gen_sequence_assembly_ext()
+    with open(os.path.join(GOLDEN, "sequence_assembly_ext.json"), "w") as f:
+        json.dump(cases, f)
+    print("sequence_assembly_ext.json:", len(cases), "cases,", sum("error" in c for c in cases), "raising")

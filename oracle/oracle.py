@@ -123,3 +123,29 @@ def assemble(matrices, step):
     if rc:
         raise RuntimeError(f"oracle assemble rc={rc}")
     return out
+
+
+def stitch(fragments):
+    """simple_assembly + argmax + index2base restatement -> (consensus str, votes int32[4, length]).
+    Raises IndexError where the reference does."""
+    code = {"A": 0, "C": 1, "G": 2, "T": 3, "a": 0, "c": 1, "g": 2, "t": 3}
+    n = len(fragments)
+    off = np.zeros(n + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(f) for f in fragments])
+    sym = np.array([code[ch] for f in fragments for ch in f], dtype=np.uint8)
+    if sym.size == 0:
+        sym = np.zeros(1, dtype=np.uint8)
+    cap = 1000 * (n + 1)
+    votes = np.zeros((4, cap), dtype=np.int32)
+    cons = np.zeros(cap, dtype=np.uint8)
+    out_len = ctypes.c_int64(0)
+    L_ = lib()
+    L_.radian_oracle_stitch.restype = ctypes.c_int
+    rc = L_.radian_oracle_stitch(_p(sym), _p(off), ctypes.c_int(n), _p(votes), ctypes.c_int64(cap), _p(cons),
+                                 ctypes.byref(out_len))
+    if rc == -6:
+        raise IndexError("index out of bounds for the vote buffer")
+    if rc:
+        raise RuntimeError(f"oracle stitch rc={rc}")
+    ln = out_len.value
+    return "".join("ACGT"[s] for s in cons[:ln]), votes[:, :ln].copy()

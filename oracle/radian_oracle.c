@@ -469,3 +469,162 @@ int radian_oracle_assemble(const float *chunks, const int32_t *chunk_len, int n_
     free(cover);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Chunk-mode stitching: sequence_assembly.py:19-48 (simple_assembly, add_count) followed by
+ * np.argmax(consensus, axis=0) + index2base (basecall.py:122-123, sequence_assembly.py:90-97).
+ *
+ * The alignment of consecutive fragments is difflib.SequenceMatcher(None, prev, cur) of the
+ * Python standard library (third-party to the reference; CPython 3.12 Lib/difflib.py), restated
+ * here: __chain_b with the autojunk "popular element" rule (len(b) >= 200: elements occurring
+ * more than len(b)//100 + 1 times are left out of b2j), find_longest_match (the j2len dynamic
+ * programme, first strictly longer match wins, then extension over equal elements on both
+ * sides), get_matching_blocks (recursion left and right of every block, sort, collapse of
+ * adjacent blocks, sentinel), and max(blocks, key=size) = first block of maximal size.
+ * Symbols are 0..3.  Returns 0, or -6 where the reference raises IndexError (a fragment that
+ * does not fit the vote buffer after its single 1000-column growth step).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int i, j, k;
+} blk_t;
+
+static blk_t longest_match(const uint8_t *a, const uint8_t *b, int alo, int ahi, int blo, int bhi,
+                           const uint8_t *popular, int *row0, int *row1)
+{
+    int besti = alo, bestj = blo, bestsize = 0;
+    int *old = row0, *cur = row1; /* indexed j + 1 */
+    for (int j = blo; j <= bhi; ++j) old[j] = 0;
+    for (int i = alo; i < ahi; ++i) {
+        cur[blo] = 0;
+        for (int j = blo; j < bhi; ++j) {
+            int k = 0;
+            if (a[i] == b[j] && !popular[b[j]]) {
+                k = old[j] + 1; /* j2len.get(j - 1, 0) + 1 */
+                if (k > bestsize) {
+                    besti = i - k + 1;
+                    bestj = j - k + 1;
+                    bestsize = k;
+                }
+            }
+            cur[j + 1] = k;
+        }
+        int *t = old;
+        old = cur;
+        cur = t;
+    }
+    while (besti > alo && bestj > blo && a[besti - 1] == b[bestj - 1]) {
+        --besti;
+        --bestj;
+        ++bestsize;
+    }
+    while (besti + bestsize < ahi && bestj + bestsize < bhi && a[besti + bestsize] == b[bestj + bestsize]) ++bestsize;
+    blk_t r = {besti, bestj, bestsize};
+    return r;
+}
+
+static int blk_cmp(const void *x, const void *y)
+{
+    const blk_t *p = (const blk_t *)x, *q = (const blk_t *)y;
+    if (p->i != q->i) return p->i < q->i ? -1 : 1;
+    if (p->j != q->j) return p->j < q->j ? -1 : 1;
+    return (p->k > q->k) - (p->k < q->k);
+}
+
+/* displacement block[0] - block[1] of the first largest matching block */
+static int stitch_disp(const uint8_t *a, int la, const uint8_t *b, int lb)
+{
+    uint8_t popular[4] = {0, 0, 0, 0};
+    if (lb >= 200) {
+        int cnt[4] = {0, 0, 0, 0};
+        for (int j = 0; j < lb; ++j) cnt[b[j]]++;
+        for (int c = 0; c < 4; ++c) popular[c] = cnt[c] > lb / 100 + 1;
+    }
+    int nmax = (la < lb ? la : lb) + 2;
+    blk_t *blocks = (blk_t *)malloc(sizeof(blk_t) * (size_t)nmax);
+    int *queue = (int *)malloc(sizeof(int) * 4 * (size_t)(2 * nmax + 2));
+    int *row0 = (int *)malloc(sizeof(int) * (size_t)(lb + 2));
+    int *row1 = (int *)malloc(sizeof(int) * (size_t)(lb + 2));
+    int nb = 0, qh = 0, qt = 0;
+    queue[0] = 0, queue[1] = la, queue[2] = 0, queue[3] = lb;
+    qt = 1;
+    while (qh < qt) {
+        const int alo = queue[4 * qh], ahi = queue[4 * qh + 1], blo = queue[4 * qh + 2], bhi = queue[4 * qh + 3];
+        ++qh;
+        const blk_t x = longest_match(a, b, alo, ahi, blo, bhi, popular, row0, row1);
+        if (x.k) {
+            blocks[nb++] = x;
+            if (alo < x.i && blo < x.j) {
+                queue[4 * qt] = alo, queue[4 * qt + 1] = x.i, queue[4 * qt + 2] = blo, queue[4 * qt + 3] = x.j;
+                ++qt;
+            }
+            if (x.i + x.k < ahi && x.j + x.k < bhi) {
+                queue[4 * qt] = x.i + x.k, queue[4 * qt + 1] = ahi, queue[4 * qt + 2] = x.j + x.k, queue[4 * qt + 3] = bhi;
+                ++qt;
+            }
+        }
+    }
+    qsort(blocks, (size_t)nb, sizeof(blk_t), blk_cmp);
+    /* collapse adjacent blocks, append the sentinel, take the first block of maximal size */
+    int bi = la, bj = lb, bk = 0, have = 0;
+    int i1 = 0, j1 = 0, k1 = 0;
+    for (int n = 0; n <= nb; ++n) {
+        const int last = (n == nb);
+        if (!last && i1 + k1 == blocks[n].i && j1 + k1 == blocks[n].j) {
+            k1 += blocks[n].k;
+        } else {
+            if (k1 && (!have || k1 > bk)) {
+                bi = i1, bj = j1, bk = k1;
+                have = 1;
+            }
+            if (!last) i1 = blocks[n].i, j1 = blocks[n].j, k1 = blocks[n].k;
+        }
+    }
+    if (!have) bi = la, bj = lb; /* only the (la, lb, 0) sentinel */
+    free(blocks);
+    free(queue);
+    free(row0);
+    free(row1);
+    return bi - bj;
+}
+
+int radian_oracle_stitch(const uint8_t *sym, const int64_t *frag_off, int n_frags, int32_t *votes, int64_t cap,
+                         uint8_t *consensus, int64_t *out_len)
+{
+    /* votes: 4 x cap int32, zeroed here; cap >= 1000 * (n_frags + 1) is always enough */
+    int64_t census_len = 1000, pos = 0, length = 0;
+    memset(votes, 0, sizeof(int32_t) * 4 * (size_t)cap);
+    *out_len = 0;
+    for (int f = 0; f < n_frags; ++f) {
+        const uint8_t *cur = sym + frag_off[f];
+        const int64_t len = frag_off[f + 1] - frag_off[f];
+        int64_t start = 0;
+        if (f > 0) {
+            const uint8_t *prev = sym + frag_off[f - 1];
+            const int64_t disp = stitch_disp(prev, (int)(frag_off[f] - frag_off[f - 1]), cur, (int)len);
+            if (disp + pos + len > census_len) census_len += 1000;
+            start = pos + disp;
+            pos += disp;
+        }
+        int64_t skip = 0;
+        if (start < 0) {
+            skip = -start;
+            start = 0;
+        }
+        for (int64_t i = skip; i < len; ++i) {
+            const int64_t col = start + (i - skip);
+            if (col >= census_len || col >= cap) return -6; /* IndexError in add_count */
+            votes[(int64_t)cur[i] * cap + col]++;
+        }
+        if (f > 0 && pos + len > length) length = pos + len;
+    }
+    if (length > census_len) length = census_len;
+    if (length < 0) length = 0;
+    for (int64_t c = 0; c < length; ++c) {
+        int best = 0;
+        for (int s = 1; s < 4; ++s)
+            if (votes[(int64_t)s * cap + c] > votes[(int64_t)best * cap + c]) best = s;
+        consensus[c] = (uint8_t)best;
+    }
+    *out_len = length;
+    return 0;
+}

@@ -20,6 +20,7 @@ EXPORTS = [
     "radian_table_create", "radian_table_destroy", "radian_table_context_len", "radian_table_entropies",
     "radian_decode_workspace_bytes", "radian_decode_batch_dev", "radian_decode_batch_host",
     "radian_assemble_plan", "radian_assemble_batch_dev", "radian_assemble_batch_host",
+    "radian_stitch_batch_host",
 ]
 
 
@@ -61,6 +62,9 @@ def _load():
     lib.radian_assemble_batch_host.restype = c_int
     lib.radian_assemble_batch_host.argtypes = [
         c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int]
+    lib.radian_stitch_batch_host.restype = c_int
+    lib.radian_stitch_batch_host.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]
     return lib
 
 

@@ -87,19 +87,17 @@ def basecall_batch(read_ids, chunk_lists, args, table):
         mats = assemble_batch(chunk_lists, args.step_size)
         return beam_search_batch(mats, args.beam_width, table, args.sig_threshold, args.rna_threshold,
                                  args.context_len)
-    # chunk mode: every window decoded with the model off, fragments stitched on the host
-    from .sequence_assembly import index2base, simple_assembly
+    # chunk mode (basecall.py:110-123): every window decoded with the model off, then all reads'
+    # fragments stitched in one call
+    from .sequence_assembly import stitch_batch
 
     flat = [m for mats in chunk_lists for m in mats]
     frags = beam_search_batch(flat, args.beam_width, None, None, None, None)
-    out = []
-    k = 0
+    per_read, k = [], 0
     for mats in chunk_lists:
-        read_fragments = frags[k:k + len(mats)]
+        per_read.append(frags[k:k + len(mats)])
         k += len(mats)
-        consensus = simple_assembly(read_fragments)
-        out.append(index2base(np.argmax(consensus, axis=0)))
-    return out
+    return stitch_batch(per_read)
 
 
 def main(argv=None):

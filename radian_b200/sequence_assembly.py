@@ -1,47 +1,74 @@
-"""Chunk-mode fragment stitching on the host.
+"""Drop-in for the chunk-mode stitching of the reference (``radian/sequence_assembly.py``),
+running on the GPU.
 
-Behaviour of the reference's ``simple_assembly`` / ``index2base`` (radian/sequence_assembly.py:19-48,
-90-97; call site basecall.py:122-123): consecutive fragments are aligned on their longest common
-block (difflib) and every consensus column takes a vote.  Host string work, kept on the CPU.
+``simple_assembly`` and ``index2base`` keep the reference's names, arguments and results
+(sequence_assembly.py:19-48, 90-97; call site basecall.py:122-123).  A read's fragments only
+depend on each other through a running position, so the batched entry point ``stitch_batch``
+aligns all consecutive fragment pairs of all reads in one launch, places and votes in three more
+(radian_b200/csrc/stitch.cu).  Nothing here computes; the library fails loudly without a GPU.
 """
 from __future__ import annotations
 
-import difflib
-
 import numpy as np
 
-_BASE = {"A": 0, "C": 1, "G": 2, "T": 3, "a": 0, "c": 1, "g": 2, "t": 3}
+from . import _native
+from ._native import lib
+
+_CODE = np.full(256, 255, dtype=np.uint8)
+for _i, _pair in enumerate(("Aa", "Cc", "Gg", "Tt")):  # base_dict of sequence_assembly.py:42
+    for _ch in _pair:
+        _CODE[ord(_ch)] = _i
 
 
-def _add_votes(votes: np.ndarray, start: int, fragment: str) -> None:
-    if start < 0:
-        fragment = fragment[-start:]
-        start = 0
-    for i, b in enumerate(fragment):
-        votes[_BASE[b], start + i] += 1
+def _encode(fragment) -> np.ndarray:
+    if isinstance(fragment, np.ndarray):
+        return np.ascontiguousarray(fragment, dtype=np.uint8)
+    raw = np.frombuffer(str(fragment).encode("latin-1", "replace"), dtype=np.uint8)
+    sym = _CODE[raw]
+    if sym.size and sym.max() > 3:
+        raise KeyError(str(fragment)[int(np.argmax(sym > 3))])  # base_dict[base], sequence_assembly.py:47
+    return sym
 
 
-def simple_assembly(fragments):
-    """-> (4, length) vote counts, same values as the reference for the same fragments."""
-    width = 1000
-    votes = np.zeros([4, width])
-    pos = 0
-    length = 0
-    for k, frag in enumerate(fragments):
-        if k == 0:
-            _add_votes(votes, 0, frag)
-            continue
-        sm = difflib.SequenceMatcher(None, fragments[k - 1], frag)
-        block = max(sm.get_matching_blocks(), key=lambda x: x[2])
-        shift = block[0] - block[1]
-        if shift + pos + len(frag) > width:
-            votes = np.pad(votes, ((0, 0), (0, 1000)), mode="constant", constant_values=0)
-            width += 1000
-        _add_votes(votes, pos + shift, frag)
-        pos += shift
-        length = max(length, pos + len(frag))
-    return votes[:, :length]
+def stitch_batch(fragment_lists, device=None, return_votes=False, bases="ACGT"):
+    """Consensus string of every read from its chunk-mode fragments (strings over ACGT, or uint8
+    arrays of symbols 0..3 as the decoder returns them).  With ``return_votes`` also the
+    ``(4, length)`` vote counts of every read, the array the reference's simple_assembly returns."""
+    from .decode import _current_device
+
+    device = _current_device() if device is None else int(device)
+    n = len(fragment_lists)
+    frags = [[_encode(f) for f in fl] for fl in fragment_lists]
+    rfr = np.zeros(n + 1, dtype=np.int64)
+    rfr[1:] = np.cumsum([len(fl) for fl in frags])
+    flat = [f for fl in frags for f in fl]
+    foff = np.zeros(len(flat) + 1, dtype=np.int64)
+    foff[1:] = np.cumsum([f.size for f in flat]) if flat else 0
+    sym = np.concatenate(flat) if flat and foff[-1] else np.zeros(1, dtype=np.uint8)
+    slots = np.zeros(n + 1, dtype=np.int64)
+    slots[1:] = np.cumsum([max(1, int(sum(f.size for f in fl))) for fl in frags])
+    seq = np.zeros(int(slots[-1]) if n else 1, dtype=np.uint8)
+    ln = np.zeros(max(n, 1), dtype=np.int64)
+    status = np.zeros(max(n, 1), dtype=np.int32)
+    votes = np.zeros((int(slots[-1]) if n else 1, 4), dtype=np.int32) if return_votes else None
+    if n:
+        rc = lib.radian_stitch_batch_host(_native.np_ptr(sym), _native.np_ptr(foff), _native.np_ptr(rfr), n,
+                                          _native.np_ptr(seq), _native.np_ptr(slots), _native.np_ptr(ln),
+                                          _native.np_ptr(status), _native.np_ptr(votes), device)
+        _native.check(rc)
+    lut = np.frombuffer(bases.encode("ascii"), dtype=np.uint8)
+    out = [lut[seq[slots[r]:slots[r] + ln[r]]].tobytes().decode("ascii") for r in range(n)]
+    if return_votes:
+        return out, [votes[slots[r]:slots[r] + ln[r]].T.astype(np.float64) for r in range(n)]
+    return out
 
 
-def index2base(indices) -> str:
-    return "".join("ACGT"[int(x)] for x in indices)
+def simple_assembly(bpreads):
+    """Same call and result as the reference (sequence_assembly.py:19-39): the ``(4, length)``
+    float64 vote counts of one read's fragments."""
+    return stitch_batch([list(bpreads)], return_votes=True)[1][0]
+
+
+def index2base(read) -> str:
+    """sequence_assembly.py:90-97: symbols 0..3 -> string over ACGT."""
+    return "".join("ACGT"[int(x)] for x in read)

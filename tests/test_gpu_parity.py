@@ -248,3 +248,52 @@ def test_device_resident_path():
     o = off.cpu().numpy()
     host = decode.beam_search_batch([p[o[i]:o[i + 1]] for i in range(len(nb))], 16, lm, 0.5, 0.5, 6)
     assert dev == host
+
+
+def test_stitch_golden():
+    """Chunk-mode stitching (sequence_assembly.py:19-48, 90-97) against outputs of the reference:
+    votes bit-exact, consensus identical, the reference's IndexError reproduced."""
+    import json
+    import os
+
+    from radian_b200.sequence_assembly import index2base, simple_assembly, stitch_batch
+
+    batch, want = [], []
+    for fn in ("sequence_assembly.json", "sequence_assembly_ext.json"):
+        for c in json.load(open(os.path.join(golden_io.GOLDEN, fn))):
+            if "error" in c:
+                with pytest.raises(IndexError):
+                    simple_assembly(c["fragments"])
+                continue
+            votes = simple_assembly(c["fragments"])
+            assert votes.dtype == np.float64
+            if "votes" in c:
+                ref = np.array(c["votes"], dtype=np.float64).reshape(4, -1)
+                assert votes.shape == ref.shape and np.array_equal(votes, ref)
+            else:
+                assert list(votes.shape) == c["votes_shape"] and float(votes.sum()) == c["votes_sum"]
+            assert index2base(np.argmax(votes, axis=0)) == c["consensus"]
+            batch.append(c["fragments"])
+            want.append(c["consensus"])
+    assert len(batch) > 130
+    assert stitch_batch(batch) == want  # all reads in one call
+    with pytest.raises(KeyError):
+        simple_assembly(["ACGT", "ACNT"])
+
+
+def test_chunk_mode_pipeline_vs_oracle():
+    """config 4(i): per-chunk decode with the model off, then stitching, vs the oracle end to end."""
+    import types
+
+    from oracle import oracle
+    from radian_b200 import basecall, synth
+
+    post, off = synth.make_reads(np.array([90, 40, 3]), seed=21)
+    post = post.numpy()
+    off = off.numpy()
+    chunk_lists = [synth.split_windows(post[off[i]:off[i + 1]], 256, 32) for i in range(3)]
+    args = types.SimpleNamespace(decode_type="chunk", beam_width=6, step_size=32)
+    got = basecall.basecall_batch(["a", "b", "c"], chunk_lists, args, None)
+    for mats, g in zip(chunk_lists, got):
+        frags = ["".join("ACGT"[s] for s in oracle.beam_search(m, 6)[0]) for m in mats]
+        assert g == oracle.stitch(frags)[0]

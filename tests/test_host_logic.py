@@ -122,16 +122,3 @@ def test_synth_reads_shape():
     assert (p[:, :4] == 0).any() and p[:, 4].mean() > 0.8
     mats = synth.split_windows(p[: off[1]], 1024, 128)
     assert sum(len(m) for m in mats[:1]) == min(1024, off[1])
-
-
-def test_sequence_assembly_golden():
-    """Chunk-mode stitching against outputs of the reference's simple_assembly/index2base."""
-    from radian_b200.sequence_assembly import index2base, simple_assembly
-
-    cases = json.load(open(os.path.join(golden_io.GOLDEN, "sequence_assembly.json")))
-    assert len(cases) >= 30
-    for c in cases:
-        votes = simple_assembly(c["fragments"])
-        assert list(votes.shape) == c["votes_shape"]
-        assert float(votes.sum()) == c["votes_sum"]
-        assert index2base(np.argmax(votes, axis=0)) == c["consensus"]

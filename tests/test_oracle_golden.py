@@ -48,3 +48,28 @@ def test_kat_answers():
     assert kat[0].seq.tolist() == []              # all blank -> ''
     assert kat[1].seq.tolist() == [1, 1]          # 'CC'
     assert kat[2].seq.tolist() == [0]             # uniform, bw=3, T=3 -> 'A'
+
+
+def test_stitch_matches_reference():
+    """The difflib / simple_assembly restatement against both stitching fixture sets recorded from
+    the unmodified reference (sequence_assembly.py:19-48, 90-97)."""
+    import json
+    import os
+
+    n = n_err = 0
+    for fn in ("sequence_assembly.json", "sequence_assembly_ext.json"):
+        for c in json.load(open(os.path.join(golden_io.GOLDEN, fn))):
+            n += 1
+            if "error" in c:
+                n_err += 1
+                with pytest.raises(IndexError):
+                    oracle.stitch(c["fragments"])
+                continue
+            cons, votes = oracle.stitch(c["fragments"])
+            assert cons == c["consensus"]
+            if "votes" in c:
+                want = np.array(c["votes"], dtype=np.int64).reshape(4, -1)
+                assert votes.shape == want.shape and np.array_equal(votes, want)
+            else:
+                assert list(votes.shape) == c["votes_shape"] and float(votes.sum()) == c["votes_sum"]
+    assert n >= 130 and n_err >= 1
