@@ -12,6 +12,9 @@
  *   radian_stitch_batch_*    replaces  sequence_assembly.simple_assembly + argmax + index2base
  *                                                                    radian/sequence_assembly.py:19-48,90-97
  *                            (call site radian/basecall.py:122-123)
+ *   radian_normalise_batch_* replaces  preprocess.mad_normalise         radian/preprocess.py:23-49
+ *   radian_windows_*         replaces  preprocess.get_windows           radian/preprocess.py:4-21
+ *                            (call sites radian/basecall.py:78,83)
  *   radian_table_*           replaces  the dict built from the RNA model JSON
  *                                                                    radian/basecall.py:47-57
  *                            and the entropy memo `entr_cache`       radian/decode.py:86-90
@@ -52,6 +55,11 @@ extern "C" {
 #define RADIAN_READ_TRIE_OVERFLOW 2  /* back-pointer arena too small even after compaction */
 #define RADIAN_READ_INDEX_ERROR 3    /* stitching: a fragment does not fit the reference's vote buffer
                                        (IndexError in add_count, sequence_assembly.py:47) */
+
+#define RADIAN_READ_EMPTY_SIGNAL 4   /* preprocessing: ValueError("Signal must not be empty to normalise"),
+                                       preprocess.py:24-25 */
+#define RADIAN_READ_MAD_ZERO 5       /* preprocessing: ValueError("MAD is zero, issue with signal."),
+                                       preprocess.py:47-48 */
 
 #define RADIAN_MAX_BEAM_WIDTH 128
 #define RADIAN_MAX_CONTEXT 13
@@ -178,6 +186,40 @@ int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *frag_offset
                              const int64_t *read_frag_ranges, int n_reads, uint8_t *out_seq,
                              const int64_t *out_offsets, int64_t *out_len, int32_t *out_status,
                              int32_t *out_votes, int device);
+
+/*
+ * Signal preprocessing for a batch of reads: replaces preprocess.mad_normalise
+ * (radian/preprocess.py:23-49, call site radian/basecall.py:78).
+ *
+ *  signal           raw int16 samples of all reads back to back (fast5 Raw/Signal); read r owns
+ *                   [offsets[r], offsets[r+1]).
+ *  outlier_z_score  --outlier-clip; outlier_is_int says whether the caller's value is an integer
+ *                   (argparse type=int, basecall.py:25), which matters for the result type below.
+ *  out              8 bytes per sample at the same offsets: float64 modified z-scores
+ *                   (x - median) / (1.4826 * MAD) clipped to +-outlier_z_score, or, where
+ *                   out_is_int64[r] is set, int64 values truncated towards zero: np.vectorize takes
+ *                   its output type from the first element, and a clipped first sample returns the
+ *                   integer outlier_z_score itself.
+ *  out_status       RADIAN_READ_OK, RADIAN_READ_EMPTY_SIGNAL or RADIAN_READ_MAD_ZERO per read (the
+ *                   reference raises ValueError and basecall.py:79-82 skips the read); the call
+ *                   itself still returns RADIAN_OK.
+ */
+int radian_normalise_batch_host(const int16_t *signal, const int64_t *offsets, int n_reads,
+                                double outlier_z_score, int outlier_is_int, void *out,
+                                int32_t *out_is_int64, int32_t *out_status, int device);
+
+/*
+ * Windowing: replaces preprocess.get_windows (radian/preprocess.py:4-21, call site
+ * radian/basecall.py:83).  radian_windows_plan gives, per read, the number of windows (the full
+ * ones plus the zero-padded last one) and pad_end; radian_windows_batch_host writes the windows of
+ * read r, `window` values each, at out[window_offsets[r] * window ...].  Values are copied as
+ * 8-byte words, so float64 and int64 signals both work.  RADIAN_E_ARG for step <= 0 or
+ * step > window (ValueError in the reference).
+ */
+int radian_windows_plan(const int64_t *offsets, int n_reads, int window, int step, int64_t *n_windows,
+                        int32_t *pad_end);
+int radian_windows_batch_host(const double *norm, const int64_t *offsets, int n_reads, int window, int step,
+                              const int64_t *window_offsets, double *out, int device);
 
 #ifdef __cplusplus
 }

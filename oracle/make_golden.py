@@ -362,3 +362,63 @@ def write_sequence_assembly_ext():
     with open(os.path.join(GOLDEN, "sequence_assembly_ext.json"), "w") as f:
         json.dump(cases, f)
     print("sequence_assembly_ext.json:", len(cases), "cases,", sum("error" in c for c in cases), "raising")
+
+
+def write_preprocess_golden(seed=17):
+    """Fixtures for SURVEY.md 8f N2 from the unmodified reference (preprocess.py:4-49): the five raw
+    signals of the bundled radian/data/reads.fast5 (read with radian_b200/fast5.py) and synthetic
+    int16 signals incl. ties, even/odd lengths, the int64 quirk of np.vectorize, and both
+    ValueErrors.  Run on its own:
+        python -c "from oracle import make_golden as m; m.write_preprocess_golden()" """
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_preprocess", "/root/reference/radian/preprocess.py")
+    P = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(P)
+    from radian_b200 import fast5
+
+    rng = np.random.default_rng(seed)
+    cases = []  # (signal int16, outlier (python int or float))
+    for rid, sig in fast5.reads("/root/reference/radian/data/reads.fast5"):
+        cases.append((sig, 4))
+    for n in (1, 2, 3, 4, 5, 8, 31, 32, 33, 100, 255, 256, 257, 1000, 4097, 20000):
+        base = rng.normal(700, 60, n)
+        base[rng.random(n) < 0.02] += rng.normal(0, 900, int((rng.random(n) < 0.02).sum()) or 1)[0]
+        cases.append((np.clip(np.rint(base), -32768, 32767).astype(np.int16), 4))
+    for n in (10, 500, 3000):
+        cases.append((rng.integers(-32768, 32768, n).astype(np.int16), 3))           # full range
+        cases.append((rng.integers(690, 712, n).astype(np.int16), 2.5))              # many ties, float clip
+        s = rng.integers(600, 800, n).astype(np.int16)
+        s[0] = 30000                                                                 # first sample clipped: int64 result
+        cases.append((s, 4))
+        s = s.copy()
+        s[0] = -30000
+        cases.append((s, 4.0))                                                       # float clip: stays float64
+    cases.append((np.full(50, 123, np.int16), 4))                                    # MAD zero
+    cases.append((np.array([5, 5, 5, 6], np.int16), 4))                              # MAD zero (median of distances)
+    cases.append((np.array([1, 2], np.int16), 4))
+    cases.append((np.zeros(0, np.int16), 4))                                         # empty
+    sig_all, off, outl, is_int, res, res_int, err = [], [0], [], [], [], [], []
+    win = []
+    for sig, o in cases:
+        sig_all.append(sig)
+        off.append(off[-1] + len(sig))
+        outl.append(float(o))
+        is_int.append(isinstance(o, int))
+        try:
+            r = P.mad_normalise(sig, o)
+            err.append(0)
+            res_int.append(r.dtype == np.int64)
+            res.append(r.astype(np.int64).view(np.int64) if r.dtype == np.int64 else r.view(np.int64))
+            for (W, S) in ((1024, 128), (64, 64), (50, 7)):
+                w, pad = P.get_windows(r, W, S)
+                win.append((len(err) - 1, W, S, w.shape[0], pad, float(w.sum()), float((w * np.arange(1, w.size + 1).reshape(w.shape) % 7).sum())))
+        except ValueError as e:
+            err.append(1 if "empty" in str(e) else 2)
+            res_int.append(False)
+            res.append(np.zeros(len(sig), np.int64))
+    np.savez_compressed(os.path.join(GOLDEN, "preprocess.npz"), signal=np.concatenate(sig_all), offsets=np.array(off),
+                        outlier=np.array(outl), outlier_is_int=np.array(is_int), result_bits=np.concatenate(res),
+                        result_is_int=np.array(res_int), error=np.array(err), windows=np.array(win))
+    print("preprocess.npz:", len(cases), "cases,", sum(e != 0 for e in err), "raising,", sum(res_int), "int64 results,",
+          len(win), "window checks")

@@ -149,3 +149,43 @@ def stitch(fragments):
         raise RuntimeError(f"oracle stitch rc={rc}")
     ln = out_len.value
     return "".join("ACGT"[s] for s in cons[:ln]), votes[:, :ln].copy()
+
+
+def mad_normalise(signal, outlier_z_score):
+    """preprocess.mad_normalise restatement for int16 raw signals -> float64 or int64 array.
+    Raises ValueError with the reference's messages."""
+    sig = np.ascontiguousarray(signal, dtype=np.int16)
+    n = sig.shape[0]
+    out = np.zeros(max(n, 1), dtype=np.float64)
+    is_int = ctypes.c_int(0)
+    L_ = lib()
+    L_.radian_oracle_mad_normalise.restype = ctypes.c_int
+    rc = L_.radian_oracle_mad_normalise(_p(sig), ctypes.c_int64(n), ctypes.c_double(float(outlier_z_score)),
+                                        ctypes.c_int(isinstance(outlier_z_score, (int, np.integer))), _p(out),
+                                        ctypes.byref(is_int))
+    if rc == -7:
+        raise ValueError("Signal must not be empty to normalise")
+    if rc == -8:
+        raise ValueError("MAD is zero, issue with signal.")
+    if rc:
+        raise RuntimeError(f"oracle mad_normalise rc={rc}")
+    return out[:n].view(np.int64).copy() if is_int.value else out[:n].copy()
+
+
+def get_windows(signal, window_size, step_size):
+    """preprocess.get_windows restatement -> (windows (n, W), pad_end)."""
+    if step_size <= 0:
+        raise ValueError("Step size must be > 0")
+    if step_size > window_size:
+        raise ValueError("Step size must be <= window size")
+    sig = np.asarray(signal)
+    pad = ctypes.c_int(0)
+    L_ = lib()
+    L_.radian_oracle_windows.restype = ctypes.c_int64
+    nw = L_.radian_oracle_windows(ctypes.c_int64(sig.shape[0]), ctypes.c_int(window_size), ctypes.c_int(step_size),
+                                  ctypes.byref(pad))
+    out = np.zeros((nw, window_size), dtype=sig.dtype)
+    for w in range(nw):
+        part = sig[w * step_size:w * step_size + window_size]
+        out[w, :len(part)] = part
+    return out, pad.value

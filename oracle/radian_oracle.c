@@ -628,3 +628,69 @@ int radian_oracle_stitch(const uint8_t *sym, const int64_t *frag_off, int n_frag
     *out_len = length;
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Signal preprocessing: preprocess.py:23-49 (mad_normalise and helpers) and :4-21 (get_windows),
+ * call sites basecall.py:78,83.  signal is the raw int16 array of the fast5 file.
+ *   median = np.median(signal)                       (float64, mean of the two middle values)
+ *   mad    = np.median(|signal - median|)            (float64)
+ *   z      = (x - median) / (1.4826 * mad), clipped to +-outlier
+ * np.vectorize takes its output dtype from the first element: when the first sample is clipped
+ * and outlier_z_score is a Python int (argparse type=int, basecall.py:25) the whole result is
+ * int64, every z truncated towards zero.  out holds 8 bytes per sample either way; *is_int64
+ * says which.  Returns 0, -7 (empty signal, ValueError preprocess.py:24-25) or -8 (MAD is zero,
+ * ValueError preprocess.py:47-48).
+ * ------------------------------------------------------------------------------------------ */
+static int cmp_dbl(const void *x, const void *y)
+{
+    const double a = *(const double *)x, b = *(const double *)y;
+    return (a > b) - (a < b);
+}
+
+static double median_sorted(const double *v, int64_t n)
+{
+    /* np.median: mean of the two middle elements (np.mean of two float64) */
+    return (n & 1) ? v[n / 2] : (v[n / 2 - 1] + v[n / 2]) / 2.0;
+}
+
+int radian_oracle_mad_normalise(const int16_t *signal, int64_t n, double outlier, int outlier_is_int, void *out,
+                                int *is_int64)
+{
+    if (n == 0) return -7;
+    double *tmp = (double *)malloc(sizeof(double) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) tmp[i] = (double)signal[i];
+    qsort(tmp, (size_t)n, sizeof(double), cmp_dbl);
+    const double median = median_sorted(tmp, n);
+    for (int64_t i = 0; i < n; ++i) tmp[i] = fabs((double)signal[i] - median);
+    qsort(tmp, (size_t)n, sizeof(double), cmp_dbl);
+    const double mad = median_sorted(tmp, n);
+    free(tmp);
+    if (mad == 0.0) return -8;
+    const double scale = 1.4826 * mad;
+    double *o = (double *)out;
+    for (int64_t i = 0; i < n; ++i) {
+        double z = ((double)signal[i] - median) / scale;
+        if (z > outlier) z = outlier;
+        else if (z < -1 * outlier) z = -1 * outlier;
+        o[i] = z;
+    }
+    const double z0 = ((double)signal[0] - median) / scale;
+    *is_int64 = outlier_is_int && (z0 > outlier || z0 < -1 * outlier);
+    if (*is_int64) {
+        int64_t *oi = (int64_t *)out;
+        for (int64_t i = 0; i < n; ++i) oi[i] = (int64_t)o[i]; /* C cast = truncation, as numpy's astype */
+    }
+    return 0;
+}
+
+/* get_windows: number of windows and pad_end for a signal of n samples (preprocess.py:9-20) */
+int64_t radian_oracle_windows(int64_t n, int window, int step, int *pad_end)
+{
+    int64_t start = 0, count = 0;
+    while (start + window <= n) {
+        ++count;
+        start += step;
+    }
+    *pad_end = (int)(window - (n - start));
+    return count + 1;
+}

@@ -21,6 +21,7 @@ EXPORTS = [
     "radian_decode_workspace_bytes", "radian_decode_batch_dev", "radian_decode_batch_host",
     "radian_assemble_plan", "radian_assemble_batch_dev", "radian_assemble_batch_host",
     "radian_stitch_batch_host",
+    "radian_normalise_batch_host", "radian_windows_plan", "radian_windows_batch_host",
 ]
 
 
@@ -65,6 +66,13 @@ def _load():
     lib.radian_stitch_batch_host.restype = c_int
     lib.radian_stitch_batch_host.argtypes = [
         c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]
+    lib.radian_normalise_batch_host.restype = c_int
+    lib.radian_normalise_batch_host.argtypes = [c_void_p, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p,
+                                                c_void_p, c_int]
+    lib.radian_windows_plan.restype = c_int
+    lib.radian_windows_plan.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.radian_windows_batch_host.restype = c_int
+    lib.radian_windows_batch_host.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int]
     return lib
 
 

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libradian_b200.so")
-SOURCES = ["api.cu", "decode.cu", "decode_wide.cu", "assemble.cu", "stitch.cu"]
+SOURCES = ["api.cu", "decode.cu", "decode_wide.cu", "assemble.cu", "stitch.cu", "preprocess.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",            # the decode arithmetic is written with explicit roundings

@@ -1,0 +1,235 @@
+"""Minimal fast5 (HDF5) reader for raw nanopore signals.
+
+The reference reads its input through ont_fast5_api / h5py (radian/basecall.py:70-76:
+``get_fast5_file(path).get_reads()``, ``read.read_id``, ``read.get_raw_data()``); neither exists
+on the GPU box.  This module reads the subset of HDF5 that multi- and single-read fast5 files
+written by MinKNOW use for ``Raw/Signal``: superblock version 0, version-1 object headers,
+symbol-table groups (version-1 B-trees + local heaps) and compact groups (link messages),
+integer datasets with contiguous or chunked
+(version-1 chunk B-tree) layout and no filter pipeline.  Compressed (gzip / VBZ) signals raise
+``NotImplementedError`` instead of returning garbage.
+
+    for read_id, signal in reads(path): ...          # signal: np.int16, as get_raw_data() returns it
+"""
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+
+_SIG = b"\x89HDF\r\n\x1a\n"
+_UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+class Fast5Error(ValueError):
+    pass
+
+
+class _File:
+    def __init__(self, buf: bytes):
+        if buf[:8] != _SIG:
+            raise Fast5Error("not an HDF5 file")
+        if buf[8] != 0:
+            raise NotImplementedError(f"HDF5 superblock version {buf[8]} (only version 0 is read)")
+        self.b = buf
+        self.so, self.sl = buf[13], buf[14]
+        if (self.so, self.sl) != (8, 8):
+            raise NotImplementedError("only 8-byte offsets and lengths")
+        base = self.u64(24)
+        if base != 0:
+            raise NotImplementedError("non-zero base address")
+        # root group symbol table entry follows the four addresses
+        self.root_header = self.u64(24 + 32 + 8)
+
+    def u16(self, o):
+        return struct.unpack_from("<H", self.b, o)[0]
+
+    def u32(self, o):
+        return struct.unpack_from("<I", self.b, o)[0]
+
+    def u64(self, o):
+        return struct.unpack_from("<Q", self.b, o)[0]
+
+    # ---- object headers (version 1) -> list of (type, flags, offset, size)
+    def messages(self, addr):
+        if self.b[addr] != 1:
+            raise NotImplementedError(f"object header version {self.b[addr]} (only version 1 is read)")
+        n = self.u16(addr + 2)
+        size = self.u32(addr + 8)
+        out = []
+        blocks = [(addr + 16, size)]
+        while blocks and len(out) < n:
+            o, left = blocks.pop(0)
+            end = o + left
+            while o + 8 <= end and len(out) < n:
+                mtype, msize, flags = self.u16(o), self.u16(o + 2), self.b[o + 4]
+                body = o + 8
+                if mtype == 0x10:  # continuation
+                    blocks.append((self.u64(body), self.u64(body + 8)))
+                out.append((mtype, flags, body, msize))
+                o = body + msize
+        return out
+
+    # ---- groups stored as symbol tables
+    def children(self, addr):
+        """name -> object header address of a group's members, in name order."""
+        msgs = self.messages(addr)
+        st = [m for m in msgs if m[0] == 0x11]
+        if not st:
+            return self._links(msgs)
+        btree, heap = self.u64(st[0][2]), self.u64(st[0][2] + 8)
+        if self.b[heap:heap + 4] != b"HEAP":
+            raise Fast5Error("bad local heap")
+        heap_data = self.u64(heap + 24)
+        out = {}
+
+        def name_at(off):
+            s = heap_data + off
+            return self.b[s:self.b.index(b"\0", s)].decode("utf-8")
+
+        def walk(node):
+            if self.b[node:node + 4] == b"SNOD":
+                cnt = self.u16(node + 6)
+                for k in range(cnt):
+                    e = node + 8 + 40 * k
+                    out[name_at(self.u64(e))] = self.u64(e + 8)
+                return
+            if self.b[node:node + 4] != b"TREE" or self.b[node + 4] != 0:
+                raise Fast5Error("bad group B-tree node")
+            used = self.u16(node + 6)
+            p = node + 8 + 16  # node type, level, entries used, left and right sibling
+            for k in range(used):
+                walk(self.u64(p + 8 + 16 * k))  # key k, child k, key k+1, ...
+
+        if btree != _UNDEF:
+            walk(btree)
+        return out
+
+    def _links(self, msgs):
+        """Compact new-style group: hard links stored as link messages in the object header."""
+        out = {}
+        for mtype, _, o, size in msgs:
+            if mtype == 0x02 and size >= 2:  # link info: a fractal heap address means a dense group
+                flags = self.b[o + 1]
+                p = o + 2 + (8 if flags & 1 else 0)
+                if self.u64(p) != _UNDEF:
+                    raise NotImplementedError("dense group (links in a fractal heap)")
+            if mtype != 0x06:
+                continue
+            if self.b[o] != 1:
+                raise NotImplementedError(f"link message version {self.b[o]}")
+            flags = self.b[o + 1]
+            p = o + 2
+            ltype = 0
+            if flags & 0x08:
+                ltype = self.b[p]
+                p += 1
+            if flags & 0x04:
+                p += 8
+            if flags & 0x10:
+                p += 1
+            nlen_size = 1 << (flags & 3)
+            nlen = int.from_bytes(self.b[p:p + nlen_size], "little")
+            p += nlen_size
+            name = self.b[p:p + nlen].decode("utf-8")
+            p += nlen
+            if ltype == 0:  # hard link
+                out[name] = self.u64(p)
+        return dict(sorted(out.items()))
+
+    # ---- datasets
+    def dataset(self, addr) -> np.ndarray:
+        shape = dtype = layout = None
+        for mtype, _, o, size in self.messages(addr):
+            if mtype == 0x01:  # dataspace
+                ver, rank, flags = self.b[o], self.b[o + 1], self.b[o + 2]
+                p = o + (8 if ver == 1 else 4)
+                shape = tuple(self.u64(p + 8 * k) for k in range(rank))
+            elif mtype == 0x03:  # datatype
+                cls, bits0 = self.b[o] & 0x0F, self.b[o + 1]
+                esz = self.u32(o + 4)
+                if cls == 0:  # fixed point
+                    dtype = np.dtype(("<" if not bits0 & 1 else ">") + ("i" if bits0 & 8 else "u") + str(esz))
+                elif cls == 1:
+                    dtype = np.dtype(("<" if not bits0 & 1 else ">") + "f" + str(esz))
+                else:
+                    raise NotImplementedError(f"datatype class {cls}")
+            elif mtype == 0x08:  # data layout
+                if self.b[o] != 3:
+                    raise NotImplementedError(f"data layout version {self.b[o]}")
+                layout = (self.b[o + 1], o + 2)
+            elif mtype == 0x0B and size > 0:
+                raise NotImplementedError("filtered (compressed) dataset: gzip / VBZ signals are not read")
+        if shape is None or dtype is None or layout is None:
+            raise Fast5Error("incomplete dataset header")
+        n = int(np.prod(shape)) if shape else 1
+        cls, o = layout
+        if cls == 1:  # contiguous
+            a = self.u64(o)
+            if a == _UNDEF:
+                return np.zeros(shape, dtype)
+            return np.frombuffer(self.b, dtype, n, a).reshape(shape).copy()
+        if cls == 0:  # compact
+            return np.frombuffer(self.b, dtype, n, o + 2).reshape(shape).copy()
+        if cls != 2:
+            raise NotImplementedError(f"layout class {cls}")
+        rank1 = self.b[o]  # dataset rank + 1
+        btree = self.u64(o + 1)
+        chunk = tuple(self.u32(o + 9 + 4 * k) for k in range(rank1 - 1))
+        if len(shape) != 1 or len(chunk) != 1:
+            raise NotImplementedError("only one-dimensional chunked datasets")
+        out = np.zeros(shape, dtype)
+
+        def walk(node):
+            if self.b[node:node + 4] != b"TREE" or self.b[node + 4] != 1:
+                raise Fast5Error("bad chunk B-tree node")
+            level, used = self.b[node + 5], self.u16(node + 6)
+            key = 8 + 8 * rank1
+            p = node + 8 + 16
+            for k in range(used):
+                ko = p + k * (key + 8)
+                nbytes, mask = self.u32(ko), self.u32(ko + 4)
+                start = self.u64(ko + 8)
+                child = self.u64(ko + key)
+                if level:
+                    walk(child)
+                    continue
+                if mask:
+                    raise NotImplementedError("chunk with a filter mask")
+                cnt = min(chunk[0], shape[0] - start)
+                if nbytes < cnt * dtype.itemsize:
+                    raise Fast5Error("short chunk")
+                out[start:start + cnt] = np.frombuffer(self.b, dtype, cnt, child)
+
+        if btree != _UNDEF:
+            walk(btree)
+        return out
+
+
+def reads(path):
+    """Yield ``(read_id, raw_signal)`` for every read of a multi- or single-read fast5 file, in
+    the order h5py / ont_fast5_api list them (group names, sorted)."""
+    with open(path, "rb") as f:
+        h = _File(f.read())
+    root = h.children(h.root_header)
+    multi = sorted(k for k in root if k.startswith("read_"))
+    if multi:
+        for name in multi:
+            raw = h.children(root[name]).get("Raw")
+            if raw is None:
+                continue
+            sig = h.children(raw).get("Signal")
+            if sig is not None:
+                yield name[len("read_"):], h.dataset(sig)
+        return
+    # single-read layout: /Raw/Reads/Read_<n>/Signal
+    raw = root.get("Raw")
+    if raw is None:
+        return
+    rd = h.children(raw).get("Reads")
+    if rd is None:
+        return
+    for name, addr in sorted(h.children(rd).items()):
+        sig = h.children(addr).get("Signal")
+        if sig is not None:
+            yield name, h.dataset(sig)

@@ -75,3 +75,26 @@ def table(L, seed):
             _TABLES.clear()
         _TABLES[(L, seed)] = synth.make_table(L, seed)
     return _TABLES[(L, seed)]
+
+
+def preprocess_cases():
+    """-> list of dicts: signal (int16), outlier (python int or float), error (0 ok, 1 empty, 2 MAD
+    zero), result (float64 or int64 array), windows: list of (W, S, n_windows, pad, sum, checksum)."""
+    z = np.load(os.path.join(GOLDEN, "preprocess.npz"))
+    off = z["offsets"]
+    out = []
+    for i in range(len(off) - 1):
+        o = float(z["outlier"][i])
+        bits = z["result_bits"][off[i]:off[i + 1]]
+        out.append({
+            "signal": z["signal"][off[i]:off[i + 1]],
+            "outlier": int(o) if z["outlier_is_int"][i] else o,
+            "error": int(z["error"][i]),
+            "result": bits.copy() if z["result_is_int"][i] else bits.view(np.float64).copy(),
+            "windows": [tuple(w[1:]) for w in z["windows"] if int(w[0]) == i],
+        })
+    return out
+
+
+def window_checksum(w):
+    return float(w.sum()), float((w * np.arange(1, w.size + 1).reshape(w.shape) % 7).sum())

@@ -297,3 +297,53 @@ def test_chunk_mode_pipeline_vs_oracle():
     for mats, g in zip(chunk_lists, got):
         frags = ["".join("ACGT"[s] for s in oracle.beam_search(m, 6)[0]) for m in mats]
         assert g == oracle.stitch(frags)[0]
+
+
+def test_preprocess_golden():
+    """mad_normalise / get_windows (preprocess.py:4-49) against the reference's outputs on the five
+    real signals of its bundled fast5 file and on synthetic edge cases: bit-exact, same dtypes
+    (incl. np.vectorize's int64 result), same ValueErrors; one batched call for all reads."""
+    from radian_b200 import preprocess
+
+    cases = golden_io.preprocess_cases()
+    n_int = 0
+    for c in cases:
+        if c["error"]:
+            with pytest.raises(ValueError, match="empty" if c["error"] == 1 else "MAD is zero"):
+                preprocess.mad_normalise(c["signal"], c["outlier"])
+            continue
+        r = preprocess.mad_normalise(c["signal"], c["outlier"])
+        assert r.dtype == c["result"].dtype
+        n_int += r.dtype == np.int64
+        assert np.array_equal(r.view(np.int64), c["result"].view(np.int64))
+        for W, S, nw, pad, s0, s1 in c["windows"]:
+            w, p = preprocess.get_windows(r, int(W), int(S))
+            assert w.dtype == r.dtype and w.shape == (int(nw), int(W)) and p == int(pad)
+            assert golden_io.window_checksum(w) == (s0, s1)
+    assert n_int == 3
+    ints = [c for c in cases if isinstance(c["outlier"], int) and c["outlier"] == 4]
+    res = preprocess.mad_normalise_batch([c["signal"] for c in ints], 4)
+    for c, r in zip(ints, res):
+        if c["error"]:
+            assert isinstance(r, ValueError)
+        else:
+            assert r.dtype == c["result"].dtype and np.array_equal(r.view(np.int64), c["result"].view(np.int64))
+    with pytest.raises(ValueError, match="Step size must be > 0"):
+        preprocess.get_windows(np.zeros(10), 4, 0)
+    with pytest.raises(ValueError, match="<= window size"):
+        preprocess.get_windows(np.zeros(10), 4, 5)
+    w, p = preprocess.get_windows(np.zeros(0), 4, 2)
+    assert w.shape == (1, 4) and p == 4
+
+
+def test_preprocess_large_random_vs_oracle():
+    """A long read and many short ones against the pinned oracle (medians over a wide value range)."""
+    from oracle import oracle
+    from radian_b200 import preprocess
+
+    rng = np.random.default_rng(5)
+    sigs = [np.clip(np.rint(rng.normal(650, 80, 300000)), -32768, 32767).astype(np.int16)]
+    sigs += [rng.integers(-2000, 3000, int(n)).astype(np.int16) for n in rng.integers(2, 5000, 64)]
+    for s, r in zip(sigs, preprocess.mad_normalise_batch(sigs, 4)):
+        want = oracle.mad_normalise(s, 4)
+        assert r.dtype == want.dtype and np.array_equal(r.view(np.int64), want.view(np.int64))

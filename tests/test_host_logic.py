@@ -122,3 +122,20 @@ def test_synth_reads_shape():
     assert (p[:, :4] == 0).any() and p[:, 4].mean() > 0.8
     mats = synth.split_windows(p[: off[1]], 1024, 128)
     assert sum(len(m) for m in mats[:1]) == min(1024, off[1])
+
+
+def test_fast5_reader_on_the_reference_file():
+    """radian_b200.fast5 on the reference's bundled multi-read file (tests/golden/reads.fast5 is a
+    copy of radian/data/reads.fast5): ids and int16 signals as ont_fast5_api returns them
+    (basecall.py:70-76); the signals are the ones the preprocess fixtures were recorded on."""
+    from radian_b200 import fast5
+
+    got = list(fast5.reads(os.path.join(golden_io.GOLDEN, "reads.fast5")))
+    assert [len(s) for _, s in got] == [12833, 4863, 11388, 14799, 9905]
+    assert got[0][0] == "00256416-5423-47a9-ad91-54a87a6be5e5"
+    assert all(s.dtype == np.int16 for _, s in got)
+    cases = golden_io.preprocess_cases()
+    for (rid, sig), c in zip(got, cases[:5]):
+        assert np.array_equal(sig, c["signal"])
+    with pytest.raises(fast5.Fast5Error):
+        list(fast5.reads(os.path.join(golden_io.GOLDEN, "assembly.npz")))

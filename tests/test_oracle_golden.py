@@ -73,3 +73,27 @@ def test_stitch_matches_reference():
             else:
                 assert list(votes.shape) == c["votes_shape"] and float(votes.sum()) == c["votes_sum"]
     assert n >= 130 and n_err >= 1
+
+
+def test_preprocess_matches_reference():
+    """mad_normalise / get_windows restatement (preprocess.py:4-49) against the reference's output
+    on the five real signals of its bundled fast5 file and on synthetic edge cases: bit-exact,
+    including the int64 result of np.vectorize when the first sample is clipped."""
+    cases = golden_io.preprocess_cases()
+    assert len(cases) >= 35
+    n_err = n_int = 0
+    for c in cases:
+        if c["error"]:
+            n_err += 1
+            with pytest.raises(ValueError, match="empty" if c["error"] == 1 else "MAD is zero"):
+                oracle.mad_normalise(c["signal"], c["outlier"])
+            continue
+        r = oracle.mad_normalise(c["signal"], c["outlier"])
+        assert r.dtype == c["result"].dtype
+        n_int += r.dtype == np.int64
+        assert np.array_equal(r.view(np.int64), c["result"].view(np.int64))
+        for W, S, nw, pad, s0, s1 in c["windows"]:
+            w, p = oracle.get_windows(r, int(W), int(S))
+            assert w.shape == (int(nw), int(W)) and p == int(pad)
+            assert golden_io.window_checksum(w) == (s0, s1)
+    assert n_err == 4 and n_int == 3
