@@ -24,7 +24,7 @@ import numpy as np
 
 def build_parser() -> argparse.ArgumentParser:
     parser = argparse.ArgumentParser(description="Basecall a nanopore dRNA sequencing run.")
-    parser.add_argument("fast5_dir", help="Directory of posterior .npz batches (see module docstring).")
+    parser.add_argument("fast5_dir", help="Directory of fast5 files / posterior .npz batches (see module docstring).")
     parser.add_argument("fasta_dir", help="Directory to output fasta files.")
     parser.add_argument("--local", action="store_true")
     parser.add_argument("--chunk-len", default=1024, type=int)
@@ -100,10 +100,53 @@ def basecall_batch(read_ids, chunk_lists, args, table):
     return stitch_batch(per_read)
 
 
-def main(argv=None):
+def windows_from_fast5(path, args):
+    """basecall.py:70-83 for every read of one fast5 file: raw signal -> mad_normalise ->
+    get_windows, all reads of the file in two GPU calls.  -> list of (read_id, windows, pad).
+    A read whose signal the reference refuses is reported and skipped as at basecall.py:79-82."""
+    from . import fast5, preprocess
+
+    ids, sigs = [], []
+    for rid, sig in fast5.reads(path):
+        ids.append(rid)
+        sigs.append(sig)
+    norm = preprocess.mad_normalise_batch(sigs, args.outlier_clip)
+    keep = []
+    for rid, r in zip(ids, norm):
+        if isinstance(r, ValueError):
+            print(r.args)
+            print(f"{rid} signal issue, skipping this read.")
+        else:
+            keep.append((rid, r))
+    wins = preprocess.get_windows_batch([r for _, r in keep], args.chunk_len, args.step_size)
+    return [(rid, w, pad) for (rid, _), (w, pad) in zip(keep, wins)]
+
+
+def main(argv=None, sig_model=None):
+    """``sig_model``: optional callable ``windows (n, chunk_len) -> (n, chunk_len, 5)`` posteriors
+    standing in for the reference's Keras model (basecall.py:60-61, 86-93); with it ``*.fast5``
+    files in ``fast5_dir`` are basecalled from the raw signal, without it only ``*.npz`` posterior
+    batches are."""
     args = build_parser().parse_args(argv)
     table = load_rna_model(args.rna_model, args.context_len)
     fasta = FastaWriter(args.fasta_dir)
+    for path in sorted(Path(args.fast5_dir).rglob("*.fast5")):
+        if sig_model is None:
+            print(f"{path.name}: no signal model given (out of scope of this build), skipping raw signal file.")
+            continue
+        start_t = time()
+        reads = windows_from_fast5(path, args)
+        chunk_lists = []
+        for _, windows, pad in reads:
+            mats = []
+            for i in range(0, len(windows), args.batch_size):  # basecall.py:86-93
+                mats.extend(np.asarray(sig_model(windows[i:i + args.batch_size]), dtype=np.float32))
+            mats[-1] = mats[-1][:-pad]  # basecall.py:96
+            chunk_lists.append(mats)
+        read_ids = [rid for rid, _, _ in reads]
+        for rid, seq in zip(read_ids, basecall_batch(read_ids, chunk_lists, args, table)):
+            fasta.write(rid, seq)
+        print(f"Basecalled {len(read_ids)} reads of {path.name} in {time() - start_t:.2f} sec.")
     for path in sorted(Path(args.fast5_dir).rglob("*.npz")):
         start_t = time()
         z = np.load(path, allow_pickle=True)

@@ -347,3 +347,46 @@ def test_preprocess_large_random_vs_oracle():
     for s, r in zip(sigs, preprocess.mad_normalise_batch(sigs, 4)):
         want = oracle.mad_normalise(s, 4)
         assert r.dtype == want.dtype and np.array_equal(r.view(np.int64), want.view(np.int64))
+
+
+def _toy_sig_model(windows):
+    """Deterministic stand-in for the out-of-scope signal model: (n, W) z-scores -> (n, W, 5)
+    float32 posteriors, blank last."""
+    z = np.asarray(windows, dtype=np.float64)
+    lg = np.stack([4 * np.sin(3 * z), 4 * np.cos(2 * z), 4 * np.sin(5 * z + 1), 4 * np.cos(7 * z),
+                   5.5 - np.abs(z)], axis=-1)
+    e = np.exp(lg - lg.max(-1, keepdims=True))
+    return (e / e.sum(-1, keepdims=True)).astype(np.float32)
+
+
+@pytest.mark.parametrize("mode", ["global", "chunk"])
+def test_cli_from_raw_fast5_vs_oracle(tmp_path, mode):
+    """config 1 shape from the raw signal of the reference's own fast5 file: read, normalise,
+    window, (toy) signal model, assemble + decode or per-chunk decode + stitch, FASTA; against the
+    oracle doing the same steps (basecall.py:70-141)."""
+    import shutil
+
+    from oracle import oracle
+    from radian_b200 import basecall, fast5
+
+    indir = tmp_path / "in"
+    outdir = tmp_path / "out"
+    indir.mkdir()
+    outdir.mkdir()
+    src = __import__("os").path.join(golden_io.GOLDEN, "reads.fast5")
+    shutil.copy(src, indir / "reads.fast5")
+    basecall.main([str(indir), str(outdir), "--rna-model", "None", "--decode-type", mode, "--beam-width", "6",
+                   "--chunk-len", "512", "--step-size", "64"], sig_model=_toy_sig_model)
+    got = (outdir / "reads-0.fasta").read_text().split("\n")
+    want = []
+    for rid, sig in fast5.reads(src):
+        norm = oracle.mad_normalise(sig, 4)
+        win, pad = oracle.get_windows(norm, 512, 64)
+        mats = list(_toy_sig_model(win))
+        mats[-1] = mats[-1][:-pad]
+        if mode == "global":
+            seq = "".join("ACGT"[s] for s in oracle.beam_search(oracle.assemble(mats, 64), 6)[0])
+        else:
+            seq = oracle.stitch(["".join("ACGT"[s] for s in oracle.beam_search(m, 6)[0]) for m in mats])[0]
+        want += [f">{rid}", seq[::-1]]
+    assert got[:len(want)] == want and len(want) == 10
