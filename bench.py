@@ -11,6 +11,10 @@ A "step" is one decode of one resident batch of `--reads` reads per GPU (default
 of the config, 132 GB of float32 posteriors).  Reads are independent:
 each rank owns its own batch and table replica, there is no collective on the data path
 (weak scaling); ranks only exchange the step time (max) and the decoded base count (sum).
+
+Under ncu: the end-to-end leg streams its input while the kernel runs, which a kernel-replay
+profiler cannot do; the library then copies first (it detects the injection, or set
+RADIAN_HOST_COPY_FIRST=1), and `--no-e2e` skips the leg altogether.
 """
 from __future__ import annotations
 

@@ -329,6 +329,13 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     const size_t esz = post_is_f64 ? 8 : 4;
     const size_t row = 5 * esz;
     static const bool trace = getenv("RADIAN_TRACE") != nullptr;
+    // Kernel-replay profilers (ncu) run one kernel at a time and hold back the copy streams, so a
+    // kernel that waits for its input to arrive never finishes under them: RADIAN_HOST_COPY_FIRST
+    // makes this call copy everything before it launches.
+    // (also switched on when the process runs under an injected CUDA profiler)
+    static const bool copy_first = getenv("RADIAN_HOST_COPY_FIRST") != nullptr ||
+                                   getenv("CUDA_INJECTION64_PATH") != nullptr ||
+                                   getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr;
     double tr[8] = {0};
     auto stamp = [&](int i) {
         if (trace) tr[i] = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -433,7 +440,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     // the copies need the allocations and the cleared counters
     TRY(cudaStreamWaitEvent(cs[0], ev, 0));
     TRY(cudaStreamWaitEvent(cs[1], ev, 0));
-    if (ret == RADIAN_OK) {
+    if (ret == RADIAN_OK && !copy_first) {
         ret = decode_batch_dev_impl(d_post, post_is_f64, d_fo, n, nullptr, max_frames, beam_width, table,
                                     len_context, s_threshold, r_threshold, d_seq, d_so, d_len, d_score, d_status,
                                     d_cnt, arena_nodes, d_ws, ws_bytes, d_ready, st);
@@ -465,6 +472,16 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
         // a transfer failed while the kernel is waiting for it: release the waiters so that the
         // launch drains (its results are discarded)
         cudaMemsetAsync(d_ready, 0x7f, 8, cs[0]);
+    }
+    if (copy_first) {
+        for (int k = 0; k < 2; ++k) {
+            TRY(cudaEventRecord(ev_last, cs[k]));
+            TRY(cudaStreamWaitEvent(st, ev_last, 0));
+        }
+        if (ret == RADIAN_OK)
+            ret = decode_batch_dev_impl(d_post, post_is_f64, d_fo, n, nullptr, max_frames, beam_width, table,
+                                        len_context, s_threshold, r_threshold, d_seq, d_so, d_len, d_score,
+                                        d_status, d_cnt, arena_nodes, d_ws, ws_bytes, nullptr, st);
     }
     stamp(2);
     TRY(cudaMemcpyAsync(h_seq, d_seq, (size_t)seq_bytes, cudaMemcpyDeviceToHost, st));
