@@ -207,6 +207,10 @@ int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *frag_offset
 int radian_normalise_batch_host(const int16_t *signal, const int64_t *offsets, int n_reads,
                                 double outlier_z_score, int outlier_is_int, void *out,
                                 int32_t *out_is_int64, int32_t *out_status, int device);
+/* the same on device pointers (offsets relative to `signal` / `out`), asynchronous on `stream` */
+int radian_normalise_batch_dev(const int16_t *signal, const int64_t *offsets, int n_reads,
+                               double outlier_z_score, int outlier_is_int, void *out,
+                               int32_t *out_is_int64, int32_t *out_status, radian_stream_t stream);
 
 /*
  * Windowing: replaces preprocess.get_windows (radian/preprocess.py:4-21, call site
@@ -220,6 +224,8 @@ int radian_windows_plan(const int64_t *offsets, int n_reads, int window, int ste
                         int32_t *pad_end);
 int radian_windows_batch_host(const double *norm, const int64_t *offsets, int n_reads, int window, int step,
                               const int64_t *window_offsets, double *out, int device);
+int radian_windows_batch_dev(const double *norm, const int64_t *offsets, const int64_t *window_offsets,
+                             int n_reads, int window, int step, double *out, radian_stream_t stream);
 
 #ifdef __cplusplus
 }

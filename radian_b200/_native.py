@@ -21,7 +21,8 @@ EXPORTS = [
     "radian_decode_workspace_bytes", "radian_decode_batch_dev", "radian_decode_batch_host",
     "radian_assemble_plan", "radian_assemble_batch_dev", "radian_assemble_batch_host",
     "radian_stitch_batch_host",
-    "radian_normalise_batch_host", "radian_windows_plan", "radian_windows_batch_host",
+    "radian_normalise_batch_host", "radian_normalise_batch_dev", "radian_windows_plan",
+    "radian_windows_batch_host", "radian_windows_batch_dev",
 ]
 
 
@@ -69,6 +70,11 @@ def _load():
     lib.radian_normalise_batch_host.restype = c_int
     lib.radian_normalise_batch_host.argtypes = [c_void_p, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p,
                                                 c_void_p, c_int]
+    lib.radian_normalise_batch_dev.restype = c_int
+    lib.radian_normalise_batch_dev.argtypes = [c_void_p, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p,
+                                               c_void_p, c_void_p]
+    lib.radian_windows_batch_dev.restype = c_int
+    lib.radian_windows_batch_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.radian_windows_plan.restype = c_int
     lib.radian_windows_plan.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.radian_windows_batch_host.restype = c_int

@@ -17,6 +17,8 @@ namespace radian {
 
 constexpr int kPreThreads = 256;
 constexpr int kPreWarps = kPreThreads / 32;
+constexpr int kDirectRange = 4096;                   // value span handled by one exact histogram
+constexpr int kHistWords = 2 * kDirectRange + 64;    // >= 2 * span + 1 and >= kPreWarps * 512
 
 // hist[w][bin] += 1 with one atomic per distinct bin of the warp
 __device__ __forceinline__ void hist_add(unsigned *hist, int bin, bool valid)
@@ -56,6 +58,44 @@ __device__ void select_bins(unsigned *hist /*[kPreWarps][BINS]*/, unsigned k1, u
     __syncthreads();
 }
 
+// exact values at ranks k1 <= k2 of a histogram of `bins` (<= kHistWords) consecutive integers:
+// every thread sums a contiguous slice, the slices are scanned, the owner of a rank walks its slice
+__device__ void select_direct(const unsigned *hist, int bins, unsigned k1, unsigned k2, int *red, int *sel)
+{
+    __syncthreads();
+    const int per = (bins + kPreThreads - 1) / kPreThreads;
+    const int b0 = threadIdx.x * per;
+    unsigned mine = 0;
+    for (int b = b0; b < b0 + per && b < bins; ++b) mine += hist[b];
+    // exclusive scan of the 256 slice sums: within the warp, then across the 8 warps
+    unsigned inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((threadIdx.x & 31) >= o) inc += y;
+    }
+    if ((threadIdx.x & 31) == 31) red[threadIdx.x >> 5] = (int)inc;
+    __syncthreads();
+    unsigned base = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) base += (unsigned)red[w];
+    const unsigned before = base + inc - mine;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        const unsigned k = which ? k2 : k1;
+        if (k >= before && k < before + mine) {
+            unsigned cum = before;
+            for (int b = b0; b < b0 + per && b < bins; ++b) {
+                cum += hist[b];
+                if (cum > k) {
+                    sel[which] = b;
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void hist_clear(unsigned *hist, int n)
 {
     __syncthreads();
@@ -68,9 +108,10 @@ normalise_kernel(const int16_t *__restrict__ signal, const int64_t *__restrict__
                  double outlier, int outlier_is_int, double *__restrict__ out, int32_t *__restrict__ out_is_int,
                  int32_t *__restrict__ status)
 {
-    __shared__ unsigned hist[kPreWarps * 512];
+    __shared__ unsigned hist[kHistWords];
     __shared__ int sel[4];
     __shared__ int pick[2];
+    __shared__ int red[2 * kPreWarps];
     const int warp = threadIdx.x >> 5;
     for (int r = blockIdx.x; r < n_reads; r += gridDim.x) {
         const int64_t o0 = offsets[r];
@@ -83,6 +124,39 @@ normalise_kernel(const int16_t *__restrict__ signal, const int64_t *__restrict__
         const unsigned k1 = (unsigned)((n - 1) / 2), k2 = (unsigned)(n / 2);
         const int64_t n_pad = (n + kPreThreads - 1) / kPreThreads * kPreThreads;  // whole warps for the votes
 
+        // ---- value range: raw signals span a few hundred ADC levels, so one exact histogram of
+        // the values (and one of the doubled distances) usually fits shared memory
+        int lo = 32767, hi = -32768;
+        for (int64_t i = threadIdx.x; i < n; i += kPreThreads) {
+            const int v = x[i];
+            lo = v < lo ? v : lo;
+            hi = v > hi ? v : hi;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[warp] = lo, red[kPreWarps + warp] = hi;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kPreWarps; ++w) lo = min(lo, red[w]), hi = max(hi, red[kPreWarps + w]);
+        if (hi - lo < kDirectRange) {
+            // median of the samples
+            const int nb1 = hi - lo + 1;
+            hist_clear(hist, nb1);
+            for (int64_t i = threadIdx.x; i < n; i += kPreThreads) atomicAdd(&hist[(int)x[i] - lo], 1u);
+            select_direct(hist, nb1, k1, k2, red, sel);
+            const int sum2d = sel[0] + sel[1] + 2 * lo;
+            // median of the doubled distances u = |2x - (v1 + v2)| <= 2 * (hi - lo)
+            const int nb2 = 2 * (hi - lo) + 1;
+            hist_clear(hist, nb2);
+            for (int64_t i = threadIdx.x; i < n; i += kPreThreads) atomicAdd(&hist[abs(2 * (int)x[i] - sum2d)], 1u);
+            select_direct(hist, nb2, k1, k2, red, sel);
+            if (threadIdx.x == 0) pick[0] = sum2d, pick[1] = sel[0] + sel[1];
+            __syncthreads();
+        } else {
         // ---- median of the samples: high byte, then low byte
         hist_clear(hist, kPreWarps * 256);
         for (int64_t i = threadIdx.x; i < n_pad; i += kPreThreads) {
@@ -139,7 +213,13 @@ normalise_kernel(const int16_t *__restrict__ signal, const int64_t *__restrict__
             }
             __syncthreads();
         }
-        const int usum = pick[0] + pick[1];  // mad = (u1/2 + u2/2) / 2
+        const int us = pick[0] + pick[1];
+        __syncthreads();
+        if (threadIdx.x == 0) pick[0] = sum2, pick[1] = us;
+        __syncthreads();
+        }
+        const int sum2 = pick[0];   // median = sum2 / 2 (np.median: mean of the two middle values)
+        const int usum = pick[1];   // mad = (u1/2 + u2/2) / 2
         __syncthreads();
         if (usum == 0) {  // "MAD is zero, issue with signal." (preprocess.py:47-48)
             if (threadIdx.x == 0) status[r] = RADIAN_READ_MAD_ZERO, out_is_int[r] = 0;
@@ -219,6 +299,46 @@ extern "C" int radian_windows_plan(const int64_t *offsets, int n_reads, int wind
     return RADIAN_OK;
 }
 
+extern "C" int radian_normalise_batch_dev(const int16_t *signal, const int64_t *offsets, int n_reads,
+                                          double outlier_z_score, int outlier_is_int, void *out,
+                                          int32_t *out_is_int64, int32_t *out_status, radian_stream_t stream)
+{
+    if (n_reads < 0 || !offsets || !out_is_int64 || !out_status) {
+        set_error("radian_normalise_batch_dev: null argument");
+        return RADIAN_E_ARG;
+    }
+    if (n_reads == 0) return RADIAN_OK;
+    int device = 0;
+    RADIAN_CUDA(cudaGetDevice(&device));
+    DeviceInfo di;
+    int rc = device_info(device, &di);
+    if (rc) return rc;
+    const int grid = n_reads < di.sm_count * 8 ? n_reads : di.sm_count * 8;
+    normalise_kernel<<<grid, kPreThreads, 0, (cudaStream_t)stream>>>(signal, offsets, n_reads, outlier_z_score,
+                                                                       outlier_is_int, (double *)out, out_is_int64,
+                                                                       out_status);
+    RADIAN_CUDA(cudaGetLastError());
+    return RADIAN_OK;
+}
+
+extern "C" int radian_windows_batch_dev(const double *norm, const int64_t *offsets, const int64_t *window_offsets,
+                                        int n_reads, int window, int step, double *out, radian_stream_t stream)
+{
+    if (n_reads < 0 || !offsets || !window_offsets || (n_reads > 0 && !out)) {
+        set_error("radian_windows_batch_dev: null argument");
+        return RADIAN_E_ARG;
+    }
+    if (step <= 0 || step > window) {
+        set_error(step <= 0 ? "Step size must be > 0" : "Step size must be <= window size");
+        return RADIAN_E_ARG;
+    }
+    if (n_reads == 0) return RADIAN_OK;
+    const dim3 grid(32, (unsigned)(n_reads < 4096 ? n_reads : 4096));
+    windows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(norm, offsets, window_offsets, n_reads, window, step, out);
+    RADIAN_CUDA(cudaGetLastError());
+    return RADIAN_OK;
+}
+
 extern "C" int radian_normalise_batch_host(const int16_t *signal, const int64_t *offsets, int n_reads,
                                            double outlier_z_score, int outlier_is_int, void *out,
                                            int32_t *out_is_int64, int32_t *out_status, int device)
@@ -243,9 +363,6 @@ extern "C" int radian_normalise_batch_host(const int16_t *signal, const int64_t 
         int krc = keep_pool(device);
         if (krc) return krc;
     }
-    DeviceInfo di;
-    int rc = device_info(device, &di);
-    if (rc) return rc;
     cudaStream_t st = nullptr;
     RADIAN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     int16_t *d_sig = nullptr;
@@ -265,12 +382,9 @@ extern "C" int radian_normalise_batch_host(const int16_t *signal, const int64_t 
     TRY(cudaMallocAsync(&d_status, (size_t)n_reads * 4, st));
     if (total) TRY(cudaMemcpyAsync(d_sig, signal + offsets[0], (size_t)total * 2, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_off, rel.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (ret == RADIAN_OK) {
-        const int grid = n_reads < di.sm_count * 8 ? n_reads : di.sm_count * 8;
-        normalise_kernel<<<grid, kPreThreads, 0, st>>>(d_sig, d_off, n_reads, outlier_z_score, outlier_is_int, d_out,
-                                                        d_int, d_status);
-        TRY(cudaGetLastError());
-    }
+    if (ret == RADIAN_OK)
+        ret = radian_normalise_batch_dev(d_sig, d_off, n_reads, outlier_z_score, outlier_is_int, d_out, d_int,
+                                         d_status, st);
     if (total) TRY(cudaMemcpyAsync((double *)out + offsets[0], d_out, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(out_is_int64, d_int, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(out_status, d_status, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
@@ -324,11 +438,8 @@ extern "C" int radian_windows_batch_host(const double *norm, const int64_t *offs
     if (total) TRY(cudaMemcpyAsync(d_in, norm + offsets[0], (size_t)total * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_off, rel.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_woff, wrel.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (ret == RADIAN_OK && n_win > 0) {
-        const dim3 grid(32, (unsigned)(n_reads < 4096 ? n_reads : 4096));
-        windows_kernel<<<grid, 256, 0, st>>>(d_in, d_off, d_woff, n_reads, window, step, d_out);
-        TRY(cudaGetLastError());
-    }
+    if (ret == RADIAN_OK && n_win > 0)
+        ret = radian_windows_batch_dev(d_in, d_off, d_woff, n_reads, window, step, d_out, st);
     if (n_win > 0)
         TRY(cudaMemcpyAsync(out + window_offsets[0] * window, d_out, (size_t)n_win * window * 8,
                             cudaMemcpyDeviceToHost, st));

@@ -18,6 +18,9 @@
 // the first largest block is the top-level match.  From 200 symbols on the autojunk rule drops
 // "popular" symbols from b2j and the top-level match need not be the largest block any more: those
 // pairs run the complete get_matching_blocks recursion in global scratch.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <vector>
 
 #include "internal.h"
@@ -295,8 +298,12 @@ extern "C" int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *
                 scratch_ints += pair_scratch_ints(frag_offsets[f] - frag_offsets[f - 1], lb);
             }
         }
+    static const bool trace = getenv("RADIAN_TRACE") != nullptr;
     cudaStream_t st = nullptr;
     RADIAN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaEvent_t evt[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (trace)
+        for (auto &x : evt) RADIAN_CUDA(cudaEventCreate(&x));
     uint8_t *d_sym = nullptr, *d_first = nullptr, *d_seq = nullptr;
     int64_t *d_foff = nullptr, *d_rfr = nullptr, *d_soff = nullptr, *d_start = nullptr, *d_len = nullptr, *d_col = nullptr;
     int32_t *d_fread = nullptr, *d_disp = nullptr, *d_status = nullptr, *d_counts = nullptr;
@@ -325,10 +332,12 @@ extern "C" int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *
     TRY(cudaMemcpyAsync(d_soff, scratch_off.data(), (size_t)n_frags * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_fread, frag_read.data(), (size_t)n_frags * 4, cudaMemcpyHostToDevice, st));
     if (ret == RADIAN_OK) {
+        if (trace) cudaEventRecord(evt[0], st);
         pair_kernel<<<(unsigned)((n_frags + 127) / 128), 128, 0, st>>>(d_sym, d_foff, d_first, n_frags, d_soff,
                                                                          d_scratch, d_disp);
         place_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, st>>>(d_foff, d_rfr, n_reads, d_disp, d_start,
                                                                           d_len, d_status);
+        if (trace) cudaEventRecord(evt[1], st);
         TRY(cudaGetLastError());
     }
     TRY(cudaMemcpyAsync(out_len, d_len, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, st));
@@ -356,9 +365,11 @@ extern "C" int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *
         TRY(cudaMemsetAsync(d_votes, 0, (size_t)n_cols * 8, st));
         TRY(cudaMemcpyAsync(d_col, col.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
         if (ret == RADIAN_OK) {
+            if (trace) cudaEventRecord(evt[2], st);
             vote_kernel<<<(unsigned)n_frags, 64, 0, st>>>(d_sym, d_foff, d_fread, n_frags, d_start, d_len, d_col,
                                                           d_votes);
             argmax_kernel<<<(unsigned)((n_cols + 255) / 256), 256, 0, st>>>(d_votes, n_cols, d_seq, d_counts);
+            if (trace) cudaEventRecord(evt[3], st);
             TRY(cudaGetLastError());
         }
         std::vector<uint8_t> h_seq((size_t)n_cols);
@@ -374,6 +385,15 @@ extern "C" int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *
             }
     }
 #undef TRY
+    if (trace && ret == RADIAN_OK && n_cols > 0) {
+        float ms_pair = 0, ms_vote = 0;
+        cudaEventElapsedTime(&ms_pair, evt[0], evt[1]);
+        cudaEventElapsedTime(&ms_vote, evt[2], evt[3]);
+        fprintf(stderr, "[radian] stitch: %d reads, %lld fragments, %lld symbols, %lld columns | pair+place %.3f ms, "
+                "vote+argmax %.3f ms\n", n_reads, (long long)n_frags, (long long)n_sym, (long long)n_cols, ms_pair, ms_vote);
+    }
+    if (trace)
+        for (auto &x : evt) cudaEventDestroy(x);
     void *frees[] = {d_sym, d_first, d_foff, d_rfr, d_soff, d_start, d_fread, d_disp, d_len, d_col, d_status,
                      d_scratch, d_votes, d_seq, d_counts};
     for (void *p : frees)
