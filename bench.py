@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--cpu-reads", type=int, default=512, help="reads in the CPU baseline sample (also parity-checked)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-pageable", action="store_true", help="end-to-end leg from pageable host memory")
     ap.add_argument("--check-reads", type=int, default=4, help="reads re-decoded by the oracle after timing")
     return ap.parse_args()
 
@@ -283,7 +284,9 @@ def main():
     if not a.no_e2e:
         ne = min(a.e2e_reads, a.reads)
         fe = int(fo[ne].item())
-        h_post = torch.empty((fe, 5), dtype=post.dtype).pin_memory()
+        h_post = torch.empty((fe, 5), dtype=post.dtype)
+        if not a.e2e_pageable:
+            h_post = h_post.pin_memory()
         h_post.copy_(post[:fe])
         post_np = h_post.numpy()
         fo_np = fo[:ne + 1].cpu().numpy()

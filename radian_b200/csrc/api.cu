@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <mutex>
 #include <thread>
@@ -311,6 +312,143 @@ static void *pinned_scratch(size_t bytes)
     return p;
 }
 
+// ---- staged upload -----------------------------------------------------------------------------
+// Pageable host memory reaches the device at ~10 GB/s through cudaMemcpyAsync (the driver stages
+// it on the calling thread), and page-locked memory at 80 % of the link when every read is its own
+// transfer.  Here host threads gather the reads, in queue order, into a ring of page-locked slots
+// and the calling thread sends every filled slot with one large copy: the source may be any
+// memory, and the copy engine only sees 32 MB transfers.
+constexpr int kStageSlots = 4;
+constexpr size_t kStageBytes = (size_t)32 << 20;
+
+struct StageRing {
+    char *slot[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    int *flags = nullptr;  // page-locked flag values
+    size_t bytes = 0, n_flags = 0;
+};
+
+static StageRing *stage_ring(size_t slot_bytes, size_t n_flags)
+{
+    static thread_local StageRing ring;
+    if (slot_bytes > ring.bytes) {
+        for (int k = 0; k < kStageSlots; ++k) {
+            if (ring.slot[k]) cudaFreeHost(ring.slot[k]);
+            ring.slot[k] = nullptr;
+            if (cudaHostAlloc((void **)&ring.slot[k], slot_bytes, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                ring.bytes = 0;
+                return nullptr;
+            }
+            if (!ring.ev[k] && cudaEventCreateWithFlags(&ring.ev[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        ring.bytes = slot_bytes;
+    }
+    if (n_flags > ring.n_flags) {
+        if (ring.flags) cudaFreeHost(ring.flags);
+        ring.flags = nullptr;
+        if (cudaHostAlloc((void **)&ring.flags, (n_flags + 64) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            ring.n_flags = 0;
+            return nullptr;
+        }
+        ring.n_flags = n_flags + 64;
+    }
+    return &ring;
+}
+
+// reads in queue order k = 0..n-1: source frames src_frame[k], T[k] of them, device frames fo[k]
+static int staged_upload(const char *post, size_t row, const std::vector<int64_t> &src_frame,
+                         const std::vector<int64_t> &fo, char *d_post, int *d_ready, cudaStream_t cs[2],
+                         cudaEvent_t ev_last, int device)
+{
+    const int n = (int)src_frame.size();
+    size_t biggest = 0;
+    for (int k = 0; k < n; ++k) biggest = std::max(biggest, (size_t)(fo[k + 1] - fo[k]) * row);
+    const size_t slot_bytes = std::max(kStageBytes, biggest);
+    struct Seg {
+        int k0, k1;
+    };
+    std::vector<Seg> segs;
+    for (int k = 0; k < n;) {
+        int j = k;
+        size_t bytes = (size_t)(fo[k + 1] - fo[k]) * row;
+        while (j + 1 < n && bytes + (size_t)(fo[j + 2] - fo[j + 1]) * row <= slot_bytes) {
+            ++j;
+            bytes += (size_t)(fo[j + 1] - fo[j]) * row;
+        }
+        segs.push_back({k, j + 1});
+        k = j + 1;
+    }
+    const int nseg = (int)segs.size();
+    StageRing *ring = stage_ring(slot_bytes, (size_t)nseg);
+    if (!ring) {
+        set_error("radian_decode_batch_host: cannot page-lock the staging ring (%zu bytes per slot)", slot_bytes);
+        return RADIAN_E_CUDA;
+    }
+    std::vector<std::atomic<int>> filled((size_t)nseg), issued((size_t)nseg);
+    for (int i = 0; i < nseg; ++i) filled[i].store(0), issued[i].store(0);
+    std::atomic<int> next(0), failed(0);
+    unsigned nw = std::thread::hardware_concurrency();
+    nw = nw > 4 ? nw - 2 : 2;  // leave room for the submitting thread
+    nw = nw > 12 ? 12 : nw;
+    if ((int)nw > nseg) nw = (unsigned)nseg;
+    std::vector<std::thread> workers;
+    for (unsigned w = 0; w < nw; ++w)
+        workers.emplace_back([&]() {
+            cudaSetDevice(device);
+            for (;;) {
+                const int sgm = next.fetch_add(1);
+                if (sgm >= nseg || failed.load()) break;
+                const int slot = sgm % kStageSlots;
+                if (sgm >= kStageSlots) {  // the slot's previous transfer must have left it
+                    while (!issued[sgm - kStageSlots].load(std::memory_order_acquire) && !failed.load()) std::this_thread::yield();
+                    if (cudaEventSynchronize(ring->ev[slot]) != cudaSuccess) failed.store(1);
+                }
+                char *dst = ring->slot[slot];
+                for (int k = segs[sgm].k0; k < segs[sgm].k1; ++k) {
+                    const size_t bytes = (size_t)(fo[k + 1] - fo[k]) * row;
+                    memcpy(dst, post + (size_t)src_frame[k] * row, bytes);
+                    dst += bytes;
+                }
+                filled[sgm].store(1, std::memory_order_release);
+            }
+        });
+    int ret = RADIAN_OK;
+    cudaError_t e = cudaSuccess;
+    for (int sgm = 0; sgm < nseg && ret == RADIAN_OK; ++sgm) {
+        while (!filled[sgm].load(std::memory_order_acquire) && !failed.load()) std::this_thread::yield();
+        if (failed.load()) {
+            set_error("radian_decode_batch_host: staging worker failed");
+            ret = RADIAN_E_CUDA;
+            break;
+        }
+        const int slot = sgm % kStageSlots, which = sgm & 1;
+        const size_t bytes = (size_t)(fo[segs[sgm].k1] - fo[segs[sgm].k0]) * row;
+        ring->flags[sgm] = segs[sgm].k1;
+        if (bytes && (e = cudaMemcpyAsync(d_post + (size_t)fo[segs[sgm].k0] * row, ring->slot[slot], bytes,
+                                          cudaMemcpyHostToDevice, cs[which])) != cudaSuccess)
+            ret = cuda_fail(e, "staged cudaMemcpyAsync");
+        if (ret == RADIAN_OK && (e = cudaMemcpyAsync(d_ready + which, &ring->flags[sgm], 4, cudaMemcpyHostToDevice,
+                                                     cs[which])) != cudaSuccess)
+            ret = cuda_fail(e, "staged flag copy");
+        if (ret == RADIAN_OK && (e = cudaEventRecord(ring->ev[slot], cs[which])) != cudaSuccess)
+            ret = cuda_fail(e, "cudaEventRecord");
+        issued[sgm].store(1, std::memory_order_release);
+        if (ret == RADIAN_OK && sgm + 1 == nseg) {
+            // the other stream's counter stops short of n: let it catch up once everything landed
+            if ((e = cudaEventRecord(ev_last, cs[which])) != cudaSuccess ||
+                (e = cudaStreamWaitEvent(cs[which ^ 1], ev_last, 0)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(d_ready + (which ^ 1), &ring->flags[sgm], 4, cudaMemcpyHostToDevice,
+                                     cs[which ^ 1])) != cudaSuccess)
+                ret = cuda_fail(e, "final flag copy");
+        }
+    }
+    if (ret != RADIAN_OK) failed.store(1);
+    for (auto &t : workers) t.join();
+    return ret;
+}
+
 // One streamed pass over the reads listed in `sel` (indices into the caller's batch); results are
 // written to the caller's arrays at those indices.  arena_nodes = 0 uses the default arena size.
 //
@@ -450,8 +588,24 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     // Segments (the transfers up to and including a publishing one) alternate between two copy
     // streams, so that the fixed gap between stream-ordered copies of one stream is covered by
     // the other stream's transfer; stream s publishes into d_ready[s].
+    // pageable sources (and RADIAN_HOST_STAGE=1) go through the staging ring
+    bool staged = getenv("RADIAN_HOST_STAGE") != nullptr && getenv("RADIAN_HOST_STAGE")[0] != '0';
+    if (!staged && !(getenv("RADIAN_HOST_STAGE") != nullptr) && frames > 0) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, post) != cudaSuccess) {
+            cudaGetLastError();
+            staged = true;
+        } else {
+            staged = pa.type == cudaMemoryTypeUnregistered;
+        }
+    }
+    if (staged && ret == RADIAN_OK) {
+        std::vector<int64_t> src_frame((size_t)n);
+        for (int k = 0; k < n; ++k) src_frame[k] = frame_offsets[sel[q[k]]];
+        ret = staged_upload((const char *)post, row, src_frame, fo, (char *)d_post, d_ready, cs, ev_last, device);
+    }
     int which = 0;
-    for (size_t i = 0; i < plan.size() && ret == RADIAN_OK; ++i) {
+    for (size_t i = 0; i < plan.size() && ret == RADIAN_OK && !staged; ++i) {
         const Xfer &x = plan[i];
         if (x.n_frames > 0)
             TRY(cudaMemcpyAsync((char *)d_post + (size_t)x.dst_frame * row,
