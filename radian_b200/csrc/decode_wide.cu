@@ -21,10 +21,10 @@ constexpr int kWideWarps = 2;  // warps (reads) per CTA
 template <int BPL, bool LM, typename PT>
 struct __align__(16) WideSmem {
     static constexpr int NB = 32 * BPL;
-    static constexpr int REC = LM ? 12 : 6;  // doubles per frame: P0..P4, gate, q0..q3, S, pad
+    static constexpr int REC = LM ? 18 : 10;  // doubles per frame, extended record of decode_common.cuh
     double rec[32 * REC];
     double row[LM ? NB * 4 : 4];      // RNA table row of every beam's extend-context (cp.async target)
-    double ex[NB * 4];                // extension scores of every beam
+    double ex[NB * 2];                // {pr_total, pr_blank} of every beam before the frame
     unsigned long long key[5 * NB];   // candidate scores: [0,NB) copies by beam id, then extensions
     unsigned long long sh[NB];        // staged: labeling hash of every beam
     uint32_t k32[5 * NB];             // high words of the candidate scores (incremental ranking)
@@ -41,9 +41,11 @@ struct __align__(16) WideSmem {
     uint16_t byrank[NB];              // beam id by rank
     uint16_t srank[NB];               // staged: rank of every beam
     uint8_t sgext[NB];                // staged: gate bit of every beam's extend-context
+    uint8_t slast[NB];                // staged: last symbol of every beam
 };
 
 constexpr unsigned long long kHashEmpty = 0x243F6A8885A308D3ull;
+constexpr int kNoRmaxW = (int)0x80000000;
 
 template <int BPL, bool LM, typename PT, bool COUNT>
 __global__ void __launch_bounds__(kWideWarps * 32)
@@ -72,6 +74,8 @@ decode_wide_kernel(const DecodeArgs a)
     uint32_t ctx[BPL], km[BPL];
     int len[BPL], node[BPL], rank[BPL], plane[BPL], last[BPL], succ[BPL];
     bool alive[BPL], gext[BPL], gcopy[BPL];
+    int prep[BPL];  // 1 if the live parent (plane) ends in the same symbol as this beam
+    int rmax[BPL];  // max high word of the unmerged entries of this beam's table row, or kNoRmaxW
 
     while (true) {
         // ------------------------------------------------------------ fetch a read
@@ -112,6 +116,8 @@ decode_wide_kernel(const DecodeArgs a)
             succ[s] = s * 32 + lane;
             km[s] = alive[s] ? 0x80808080u : 0u;
             gext[s] = gcopy[s] = false;
+            prep[s] = 0;
+            rmax[s] = kNoRmaxW;
         }
         int first = 0, last_b = 0;  // beam ids of the best and the worst ranked beam
         int top = 1, old_top = 1, na = 1, status = 0;  // node 0 = the empty labeling
@@ -126,7 +132,7 @@ decode_wide_kernel(const DecodeArgs a)
             if ((t & 31) == 0) {
                 cp_async_wait_all();
                 __syncwarp();
-                if (t + lane < T) make_record<LM>(&sm.raw[lane * 5], a.s_thr, &sm.rec[lane * REC]);
+                if (t + lane < T) make_record<LM, true>(&sm.raw[lane * 5], a.s_thr, &sm.rec[lane * REC]);
                 __syncwarp();
                 if (t + 32 + lane < T) prefetch_row(&sm.raw[lane * 5], rp, t + 32 + lane);
             }
@@ -184,90 +190,150 @@ decode_wide_kernel(const DecodeArgs a)
                 }
             }
 
-            // -------------------------------------------------------- one frame
-            const double *rec = &sm.rec[(t & 31) * REC];
-            const double P4 = rec[4];
-            const double2 P01 = *reinterpret_cast<const double2 *>(rec);
-            const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
-            bool fgate = false;
-            double2 q01 = make_double2(0, 0), q23 = make_double2(0, 0);
-            double S = 0.0;
-            if (LM) {
-                fgate = rec[5] != 0.0;
-                q01 = *reinterpret_cast<const double2 *>(rec + 6);
-                q23 = *reinterpret_cast<const double2 *>(rec + 8);
-                S = rec[10];
+            // RESCALE by an exact power of two when the best beam has fallen below 2^-256 (checked
+            // every frame: a float32-derived probability is >= 2^-149)
+            {
+                int hi = 0;
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) {
+                    const int x = __shfl_sync(kFull, __double2hiint(ptot[s]), first & 31);
+                    if ((first >> 5) == s) hi = x;
+                }
+                const int exb = hi >> 20;
+                if (exb != 0 && exb < 1023 - 256) {
+                    const double sc = __hiloint2double((2046 - exb) << 20, 0);
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) {
+                        ptot[s] *= sc;
+                        pnb[s] *= sc;
+                        pb[s] *= sc;
+                    }
+                    kacc += exb - 1023;
+                }
             }
-            double nptot[BPL], npnb[BPL], npb[BPL];
-            unsigned long long ke[BPL][4];
+
+            // -------------------------------------------------------- one frame
+            // (the structure of decode.cu's frame: copy, child-side merge, integer quiet test; the
+            // extension scores are only computed when some extension may reach the beam)
+            const double *rec = &sm.rec[(t & 31) * REC];
+            const int *reci = reinterpret_cast<const int *>(rec);
+            const double P4 = rec[4];
+            bool fgate = false;
+            int hS = 0;
+            if (LM) {
+                const int2 gs = *reinterpret_cast<const int2 *>(reci + 32);
+                fgate = gs.x != 0;
+                hS = gs.y;
+            }
+            double nptot[BPL], npnb[BPL], npb[BPL], dl[BPL];
 #pragma unroll
             for (int s = 0; s < BPL; ++s) {
                 const int b = s * 32 + lane;
-                const bool av = alive[s];
-                const bool has_last = av && len[s] > 0;
-                const bool lm_copy = LM && av && len[s] >= L + 1;  // decode.py:157
-                const bool lm_ext = LM && av && len[s] >= L;       // decode.py:180
                 if (COUNT && LM) {
+                    const bool lm_copy = alive[s] && len[s] >= L + 1;  // decode.py:157
+                    const bool lm_ext = alive[s] && len[s] >= L;       // decode.py:180
                     n_lookup += __popc(__ballot_sync(kFull, lm_copy)) + __popc(__ballot_sync(kFull, lm_ext));
                     n_combine += __popc(__ballot_sync(kFull, lm_copy && gcopy[s] && fgate)) +
                                  __popc(__ballot_sync(kFull, lm_ext && gext[s] && fgate));
                 }
-                // COPY (decode.py:150-175)
-                double dl = has_last ? rec[last[s]] : 0.0;
-                if (LM && lm_copy && gcopy[s] && fgate)
-                    dl = __dmul_rn(__dmul_rn(__dadd_rn(rcopy[s], rec[6 + last[s]]), 0.5), S);  // decode.py:58-61
-                npnb[s] = has_last ? __dmul_rn(pnb[s], dl) : 0.0;
+                // COPY (decode.py:150-175); the empty labeling and dead beams have pnb == 0
+                dl[s] = rec[last[s]];
+                if (LM && gcopy[s] && fgate) dl[s] = __dmul_rn(__dadd_rn(rcopy[s], rec[6 + last[s]]), rec[11]);
+                npnb[s] = __dmul_rn(pnb[s], dl[s]);
                 npb[s] = __dmul_rn(ptot[s], P4);
                 nptot[s] = __dadd_rn(npb[s], npnb[s]);
-                // EXTEND (decode.py:177-201)
-                double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
-                if (LM && lm_ext && gext[s] && fgate) {
-                    cp_async_wait_all();  // the row gathered when this beam was created
-                    const double2 r01 = *reinterpret_cast<const double2 *>(&sm.row[b * 4]);
-                    const double2 r23 = *reinterpret_cast<const double2 *>(&sm.row[b * 4 + 2]);
-                    d0 = __dmul_rn(__dmul_rn(__dadd_rn(r01.x, q01.x), 0.5), S);
-                    d1 = __dmul_rn(__dmul_rn(__dadd_rn(r01.y, q01.y), 0.5), S);
-                    d2 = __dmul_rn(__dmul_rn(__dadd_rn(r23.x, q23.x), 0.5), S);
-                    d3 = __dmul_rn(__dmul_rn(__dadd_rn(r23.y, q23.y), 0.5), S);
-                }
-                // a repeated symbol continues only paths that ended in a blank (decode.py:192-195)
-                const int lrep = has_last ? last[s] : -1;
-                const double e0 = __dmul_rn(lrep == 0 ? pb[s] : ptot[s], d0);
-                const double e1 = __dmul_rn(lrep == 1 ? pb[s] : ptot[s], d1);
-                const double e2 = __dmul_rn(lrep == 2 ? pb[s] : ptot[s], d2);
-                const double e3 = __dmul_rn(lrep == 3 ? pb[s] : ptot[s], d3);
-                *reinterpret_cast<double2 *>(&sm.ex[b * 4]) = make_double2(e0, e1);
-                *reinterpret_cast<double2 *>(&sm.ex[b * 4 + 2]) = make_double2(e2, e3);
-                ke[s][0] = (unsigned long long)__double_as_longlong(e0);
-                ke[s][1] = (unsigned long long)__double_as_longlong(e1);
-                ke[s][2] = (unsigned long long)__double_as_longlong(e2);
-                ke[s][3] = (unsigned long long)__double_as_longlong(e3);
+                *reinterpret_cast<double2 *>(&sm.ex[b * 2]) = make_double2(ptot[s], pb[s]);
             }
             __syncwarp();
-            // MERGE copy(X) with extend(parent(X), last(X)): the same dict key in the reference
+            // MERGE copy(X) with extend(parent(X), last(X)): the parent's extension by last(X) is
+            // (pr_blank or pr_total of the parent) x this beam's own copy emission
             unsigned long long kcopy[BPL];
 #pragma unroll
             for (int s = 0; s < BPL; ++s) {
                 if (alive[s] && plane[s] >= 0) {
-                    const double v = sm.ex[plane[s] * 4 + last[s]];
+                    const double v = __dmul_rn(sm.ex[plane[s] * 2 + prep[s]], dl[s]);
                     npnb[s] = __dadd_rn(npnb[s], v);
                     nptot[s] = __dadd_rn(nptot[s], v);
                 }
                 kcopy[s] = (unsigned long long)__double_as_longlong(nptot[s]);
-                sm.key[s * 32 + lane] = alive[s] ? kcopy[s] : 0ull;
+                sm.key[s * 32 + lane] = kcopy[s];  // zero for a dead beam
             }
             __syncwarp();
 
-            // SELECT (decode.py:145, 35-39): does the order still hold, does any extension compete?
+            // SELECT (decode.py:145, 35-39): does the order still hold, can any extension compete?
             bool ok = true;
 #pragma unroll
             for (int s = 0; s < BPL; ++s)
                 if (alive[s] && succ[s] != s * 32 + lane) ok = ok && (kcopy[s] > sm.key[succ[s]]);
+            const unsigned long long kworst = sm.key[last_b];
+            {
+                // QUIET frame: order intact, beam full, and by the integer log bound of decode.cu no
+                // unmerged extension reaches the high word of the worst copy
+                const int hw = (int)(kworst >> 32);
+                bool quiet = ok && na >= bw && hw >= 0x00100000;
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) {
+                    const int b = s * 32 + lane;
+                    const bool gated = LM && gext[s] && fgate;
+                    if (LM && gated && rmax[s] == kNoRmaxW) {
+                        cp_async_wait_all();  // the row gathered when this beam was created
+                        const int4 ra = *reinterpret_cast<const int4 *>(&sm.row[b * 4]);
+                        const int4 rb = *reinterpret_cast<const int4 *>(&sm.row[b * 4 + 2]);
+                        rmax[s] = max(max(ra.y & (int)byte_sign_mask<0>(km[s]), ra.w & (int)byte_sign_mask<1>(km[s])),
+                                      max(rb.y & (int)byte_sign_mask<2>(km[s]), rb.w & (int)byte_sign_mask<3>(km[s])));
+                    }
+                    const int4 hx = *reinterpret_cast<const int4 *>(reci + ((LM && gated) ? 28 : (LM ? 24 : 12)));
+                    int z = max(max(hx.x & (int)byte_sign_mask<0>(km[s]), hx.y & (int)byte_sign_mask<1>(km[s])),
+                                max(hx.z & (int)byte_sign_mask<2>(km[s]), hx.w & (int)byte_sign_mask<3>(km[s])));
+                    if (LM && gated) z = max(z, rmax[s]) + hS;
+                    const int ub = __double2hiint(ptot[s]) + z + (272000 - 0x3ff00000);
+                    quiet = quiet && ub < hw;
+                }
+                if (__all_sync(kFull, quiet)) {
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) {
+                        ptot[s] = nptot[s];  // (a dead beam's new values are zero as well)
+                        pnb[s] = npnb[s];
+                        pb[s] = npb[s];
+                    }
+                    continue;
+                }
+            }
             const bool order_ok = __all_sync(kFull, ok);
+
+            // EXTEND (decode.py:177-201)
+            unsigned long long ke[BPL][4];
+            {
+                const double2 P01 = *reinterpret_cast<const double2 *>(rec);
+                const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) {
+                    const int b = s * 32 + lane;
+                    double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
+                    if (LM && gext[s] && fgate) {
+                        cp_async_wait_all();
+                        const double2 q01 = *reinterpret_cast<const double2 *>(rec + 6);
+                        const double2 q23 = *reinterpret_cast<const double2 *>(rec + 8);
+                        const double Sh = rec[11];
+                        const double2 r01 = *reinterpret_cast<const double2 *>(&sm.row[b * 4]);
+                        const double2 r23 = *reinterpret_cast<const double2 *>(&sm.row[b * 4 + 2]);
+                        d0 = __dmul_rn(__dadd_rn(r01.x, q01.x), Sh);
+                        d1 = __dmul_rn(__dadd_rn(r01.y, q01.y), Sh);
+                        d2 = __dmul_rn(__dadd_rn(r23.x, q23.x), Sh);
+                        d3 = __dmul_rn(__dadd_rn(r23.y, q23.y), Sh);
+                    }
+                    // a repeated symbol continues only paths that ended in a blank (decode.py:192-195);
+                    // for the empty labeling (last = 0 by convention) pb == ptot
+                    ke[s][0] = (unsigned long long)__double_as_longlong(__dmul_rn(last[s] == 0 ? pb[s] : ptot[s], d0));
+                    ke[s][1] = (unsigned long long)__double_as_longlong(__dmul_rn(last[s] == 1 ? pb[s] : ptot[s], d1));
+                    ke[s][2] = (unsigned long long)__double_as_longlong(__dmul_rn(last[s] == 2 ? pb[s] : ptot[s], d2));
+                    ke[s][3] = (unsigned long long)__double_as_longlong(__dmul_rn(last[s] == 3 ? pb[s] : ptot[s], d3));
+                }
+            }
             unsigned long long tau = 0ull;  // with room left in the beam every extension is a candidate
             if (na >= bw) {
                 if (order_ok) {
-                    tau = sm.key[last_b];
+                    tau = kworst;
                 } else {
                     unsigned long long mn = ~0ull;
 #pragma unroll
@@ -431,6 +497,7 @@ decode_wide_kernel(const DecodeArgs a)
                         sm.snode[b] = node[s];
                         sm.sh[b] = len[s] > 0 ? hash_step(hp[s], last[s]) : kHashEmpty;
                         sm.sgext[b] = (uint8_t)gext[s];
+                        sm.slast[b] = (uint8_t)last[s];
                     }
                     if (LM) cp_async_wait_all();  // every lane's rows have landed before a child reads them
                     __syncwarp();
@@ -486,6 +553,7 @@ decode_wide_kernel(const DecodeArgs a)
                             for (int s2 = 0; s2 < BPL; ++s2)
                                 if ((pbm >> 5) == s2) sv = survb[s2];
                             plane[s] = ((sv >> (pbm & 31)) & 1u) ? pbm : -1;
+                            prep[s] = (c == (int)sm.slast[pbm]) ? 1 : 0;
                             alive[s] = true;
                             arena[node[s]] = ((uint32_t)sm.snode[pbm] << 2) | (uint32_t)c;
                             sm.newbeam[ford[s]] = (uint16_t)b;
@@ -517,6 +585,7 @@ decode_wide_kernel(const DecodeArgs a)
                             const int b = s * 32 + lane;
                             sm.sh[b] = hash_step(hp[s], last[s]);
                             sm.slen[b] = len[s];
+                            sm.slast[b] = (uint8_t)last[s];
                         }
                     __syncwarp();
                     for (int k = 0; k < n_new; ++k) {
@@ -525,7 +594,10 @@ decode_wide_kernel(const DecodeArgs a)
                         const int zlen = sm.slen[zb];
 #pragma unroll
                         for (int s = 0; s < BPL; ++s)
-                            if (survive[s] && plane[s] < 0 && len[s] == zlen + 1 && hp[s] == zh) plane[s] = zb;
+                            if (survive[s] && plane[s] < 0 && len[s] == zlen + 1 && hp[s] == zh) {
+                                plane[s] = zb;
+                                prep[s] = ((int)sm.slast[zb] == last[s]) ? 1 : 0;
+                            }
                     }
                     // the beam set changed: refresh which extensions are merged into a live child
 #pragma unroll
@@ -537,7 +609,10 @@ decode_wide_kernel(const DecodeArgs a)
                             reinterpret_cast<uint8_t *>(sm.kill)[plane[s] * 4 + last[s]] = 0x80;
                     __syncwarp();
 #pragma unroll
-                    for (int s = 0; s < BPL; ++s) km[s] = alive[s] ? (0x80808080u & ~sm.kill[s * 32 + lane]) : 0u;
+                    for (int s = 0; s < BPL; ++s) {
+                        km[s] = alive[s] ? (0x80808080u & ~sm.kill[s * 32 + lane]) : 0u;
+                        rmax[s] = kNoRmaxW;  // the merge mask (or the beam) changed
+                    }
                 } else {
 #pragma unroll
                     for (int s = 0; s < BPL; ++s)
@@ -560,28 +635,6 @@ decode_wide_kernel(const DecodeArgs a)
                 first = (int)sm.byrank[0];
                 last_b = (int)sm.byrank[na - 1];
                 __syncwarp();
-            }
-
-            // RESCALE by the exponent of the best beam (an exact power of two), every 4th frame: a
-            // float32-derived probability is >= 2^-149, so at most 596 binades are lost in between
-            if ((t & 3) == 3) {
-                int hi = 0;
-#pragma unroll
-                for (int s = 0; s < BPL; ++s) {
-                    const int x = __shfl_sync(kFull, __double2hiint(ptot[s]), first & 31);
-                    if ((first >> 5) == s) hi = x;
-                }
-                const int ex = (hi >> 20) & 0x7ff;
-                if (ex != 0 && ex != 0x7ff) {
-                    const double sc = __hiloint2double((2046 - ex) << 20, 0);
-#pragma unroll
-                    for (int s = 0; s < BPL; ++s) {
-                        ptot[s] *= sc;
-                        pnb[s] *= sc;
-                        pb[s] *= sc;
-                    }
-                    kacc += ex - 1023;
-                }
             }
         }
         cp_async_wait_all();
