@@ -101,8 +101,12 @@ int radian_table_entropies(const radian_table_t *t, double *out_host);
  *  out_score     2 per read: natural-log pr_total of the best and of the second-best final
  *                beam (-inf when it has probability 0, NaN when there is no second beam).
  *  out_status    RADIAN_READ_* per read.
- *  out_counters  optional, 2 per read: number of lm[context] reads the reference would have
- *                done (decode.py:83) and number of combine_dists calls (decode.py:94).
+ *  out_counters  optional, 4 per read: number of lm[context] reads the reference would have
+ *                done (decode.py:83), number of combine_dists calls (decode.py:94), number of
+ *                frames whose selection ranked two candidates within 2^-40 of each other (the
+ *                reference decides those on the rounding noise of its log-domain sums; a read
+ *                whose sequence differs from the reference's has a non-zero count here and, for
+ *                a tie of the final beams, equal out_score entries), and a reserved zero.
  */
 /*
  *  arena_nodes   capacity of the per-read back-pointer arena; 0 picks a default from max_frames

@@ -528,7 +528,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     const size_t o_score = o_len + (size_t)n * 8;
     const size_t o_status = o_score + (size_t)n * 16;
     const size_t o_cnt = (o_status + (size_t)n * 4 + 15) & ~(size_t)15;
-    const size_t o_seq = o_cnt + (out_counters ? (size_t)n * 16 : 0);
+    const size_t o_seq = o_cnt + (out_counters ? (size_t)n * 32 : 0);
     char *hp = (char *)pinned_scratch(o_seq + (size_t)seq_bytes + 16);
     if (!hp) {
         set_error("radian_decode_batch_host: cannot page-lock %zu bytes of host scratch", o_seq + (size_t)seq_bytes);
@@ -570,7 +570,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     TRY(cudaMallocAsync(&d_ready, 256, st));
     TRY(cudaMallocAsync(&d_seq, (size_t)(seq_bytes ? seq_bytes : 1), st));
     TRY(cudaMallocAsync(&d_score, (size_t)n * 16, st));
-    if (out_counters) TRY(cudaMallocAsync(&d_cnt, (size_t)n * 16, st));
+    if (out_counters) TRY(cudaMallocAsync(&d_cnt, (size_t)n * 32, st));
     TRY(cudaMemcpyAsync(d_fo, fo.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_so, so.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemsetAsync(d_ready, 0, 256, st));
@@ -642,7 +642,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     TRY(cudaMemcpyAsync(h_len, d_len, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(h_score, d_score, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(h_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    if (out_counters) TRY(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    if (out_counters) TRY(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(cs[0]));
     TRY(cudaStreamSynchronize(cs[1]));
     stamp(3);
@@ -666,8 +666,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
         out_score[2 * r + 1] = h_score[2 * k + 1];
         out_status[r] = h_status[k];
         if (out_counters) {
-            out_counters[2 * r] = h_cnt[2 * k];
-            out_counters[2 * r + 1] = h_cnt[2 * k + 1];
+            for (int c = 0; c < 4; ++c) out_counters[4 * r + c] = h_cnt[4 * k + c];
         }
         const int64_t slot = so[k + 1] - so[k];
         const int64_t ncopy = h_len[k] < slot ? h_len[k] : slot;

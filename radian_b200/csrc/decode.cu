@@ -119,7 +119,7 @@ decode_kernel(const DecodeArgs a)
     int T = 0, t = 0, pend = -1;  // pend: queue ticket of a read that has not landed yet
     long long kacc = 0;
     const PT *rp = (const PT *)a.post;
-    unsigned long long n_lookup = 0, n_combine = 0;
+    unsigned long long n_lookup = 0, n_combine = 0, n_tie = 0;
     bool active = true;
 
     while (true) {
@@ -182,7 +182,7 @@ decode_kernel(const DecodeArgs a)
                     na = 1;
                     status = 0;
                     kacc = 0;
-                    n_lookup = n_combine = 0;
+                    n_lookup = n_combine = n_tie = 0;
                 }
             }
         }
@@ -564,6 +564,7 @@ decode_kernel(const DecodeArgs a)
                         sm.pos[li] = av ? (uint16_t)pos_copy : kPosInvalid;
                     }
                     __syncwarp();
+                    bool near = false;
                     if (run && !fast) {
                         for (int idx = li; idx < m; idx += G) {
                             const uint16_t p = sm.pos[idx];
@@ -574,6 +575,9 @@ decode_kernel(const DecodeArgs a)
                                     const uint16_t pj = sm.pos[j];
                                     const unsigned long long kj = sm.key[j];
                                     cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
+                                    // two candidates within 2^-40 of each other: a decision that the
+                                    // log-domain reference takes on its own rounding noise
+                                    if (COUNT) near = near || (j != idx && pj != kPosInvalid && k != 0ull && kj - k + 4096ull < 8192ull);
                                 }
                                 sm.rnk[idx] = (uint8_t)(cnt > 255 ? 255 : cnt);
                             }
@@ -581,6 +585,7 @@ decode_kernel(const DecodeArgs a)
                     }
                     __syncwarp();
                     if (run && !fast) new_rank = av ? (int)sm.rnk[li] : 255;
+                    if (COUNT) n_tie += (GBALLOT(near) != 0u);
                 } else {
                     __syncwarp();
                 }
@@ -747,8 +752,10 @@ decode_kernel(const DecodeArgs a)
                 if (succ_first == first_lane) a.out_score[2 * read + 1] = NAN;
                 a.out_status[read] = status;
                 if (a.out_counters) {
-                    a.out_counters[2 * read] = n_lookup;
-                    a.out_counters[2 * read + 1] = n_combine;
+                    a.out_counters[4 * read] = n_lookup;
+                    a.out_counters[4 * read + 1] = n_combine;
+                    a.out_counters[4 * read + 2] = n_tie;
+                    a.out_counters[4 * read + 3] = 0;
                 }
             }
             if (status == 0 && succ_first != first_lane && lane == succ_first)

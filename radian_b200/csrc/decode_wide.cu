@@ -122,7 +122,7 @@ decode_wide_kernel(const DecodeArgs a)
         int first = 0, last_b = 0;  // beam ids of the best and the worst ranked beam
         int top = 1, old_top = 1, na = 1, status = 0;  // node 0 = the empty labeling
         long long kacc = 0;
-        unsigned long long n_lookup = 0, n_combine = 0;
+        unsigned long long n_lookup = 0, n_combine = 0, n_tie = 0;
 
         __syncwarp();
         if (lane < T) prefetch_row(&sm.raw[lane * 5], rp, lane);
@@ -450,6 +450,7 @@ decode_wide_kernel(const DecodeArgs a)
                 }
                 // ---- exact ranks: (float64 bits desc, dict insertion position asc)
                 if (!inc) {
+                    bool near = false;  // two candidates within 2^-40 of each other (see decode.cu)
                     for (int ci = lane; ci < m; ci += 32) {
                         const uint16_t p = sm.pos[ci];
                         int cnt = 0xffff;
@@ -460,10 +461,12 @@ decode_wide_kernel(const DecodeArgs a)
                                 const uint16_t pj = sm.pos[j];
                                 const unsigned long long kj = sm.key[j];
                                 cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
+                                if (COUNT) near = near || (j != ci && pj != kPosInvalid && k != 0ull && kj - k + 4096ull < 8192ull);
                             }
                         }
                         sm.rnk[ci] = (uint16_t)cnt;
                     }
+                    if (COUNT) n_tie += __any_sync(kFull, near) ? 1 : 0;
                 }
                 __syncwarp();
                 bool survive[BPL];
@@ -669,8 +672,10 @@ decode_wide_kernel(const DecodeArgs a)
                     if (second == first) a.out_score[2 * read + 1] = NAN;
                     a.out_status[read] = st;
                     if (a.out_counters) {
-                        a.out_counters[2 * read] = n_lookup;
-                        a.out_counters[2 * read + 1] = n_combine;
+                        a.out_counters[4 * read] = n_lookup;
+                        a.out_counters[4 * read + 1] = n_combine;
+                        a.out_counters[4 * read + 2] = n_tie;
+                        a.out_counters[4 * read + 3] = 0;
                     }
                 }
                 if (second != first && b == second)

@@ -134,8 +134,9 @@ def _current_device() -> int:
 def beam_search_batch(mats, beam_width, lm=None, s_threshold=None, r_threshold=None, len_context=None,
                       bases="ACGT", device=None, return_details=False):
     """Decode a list of (T_i, 5) posterior matrices (all float32 or all float64) in one launch.
-    Returns the list of decoded strings, or (strings, scores[n,2], counters[n,2]) with
-    ``return_details``."""
+    Returns the list of decoded strings, or (strings, scores[n,2], counters[n,4]) with
+    ``return_details`` (counters: lm reads, combine_dists calls, near-tie frames, 0; see
+    include/radian_b200.h)."""
     if len(bases) != N_BASES:
         raise ValueError("this build decodes 4 bases + blank (chars == 5, decode.py:124-125)")
     if int(beam_width) < 1 or int(beam_width) > _native.MAX_BEAM_WIDTH:
@@ -144,7 +145,7 @@ def beam_search_batch(mats, beam_width, lm=None, s_threshold=None, r_threshold=N
     table = _resolve_table(lm, len_context, device)
     n = len(mats)
     if n == 0:
-        return ([], np.zeros((0, 2)), np.zeros((0, 2), np.uint64)) if return_details else []
+        return ([], np.zeros((0, 2)), np.zeros((0, 4), np.uint64)) if return_details else []
     dt = np.float64 if any(np.asarray(m).dtype == np.float64 for m in mats) else np.float32
     arrs = []
     for m in mats:
@@ -164,7 +165,7 @@ def beam_search_batch(mats, beam_width, lm=None, s_threshold=None, r_threshold=N
     ln = np.zeros(n, dtype=np.int64)
     score = np.zeros((n, 2), dtype=np.float64)
     status = np.zeros(n, dtype=np.int32)
-    cnt = np.zeros((n, 2), dtype=np.uint64) if return_details else None
+    cnt = np.zeros((n, 4), dtype=np.uint64) if return_details else None
     rc = lib.radian_decode_batch_host(
         _native.np_ptr(post), int(dt == np.float64), _native.np_ptr(fo), n, int(beam_width),
         table._h if table else None, int(len_context) if table else 0,
@@ -195,7 +196,7 @@ class DeviceDecodeResult:
     lengths: "object"      # int64 CUDA tensor (n)
     scores: "object"       # float64 CUDA tensor (n, 2)
     status: "object"       # int32 CUDA tensor (n)
-    counters: "object"     # uint64-as-int64 CUDA tensor (n, 2) or None
+    counters: "object"     # uint64-as-int64 CUDA tensor (n, 4) or None
 
     def strings(self, bases="ACGT"):
         seq = self.seq.cpu().numpy()
@@ -242,7 +243,7 @@ def decode_batch_device(post, frame_offsets, beam_width, table=None, s_threshold
             lengths=torch.empty(n, dtype=torch.int64, device=post.device),
             scores=torch.empty((n, 2), dtype=torch.float64, device=post.device),
             status=torch.empty(n, dtype=torch.int32, device=post.device),
-            counters=torch.zeros((n, 2), dtype=torch.int64, device=post.device) if counters else None)
+            counters=torch.zeros((n, 4), dtype=torch.int64, device=post.device) if counters else None)
     nbytes = lib.radian_decode_workspace_bytes(dev, int(beam_width), int(n), int(max_frames), int(arena_nodes))
     if nbytes == 0:
         raise _native.RadianError(f"no CUDA device / bad beam width: {_native.last_error()}")

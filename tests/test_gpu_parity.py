@@ -390,3 +390,23 @@ def test_cli_from_raw_fast5_vs_oracle(tmp_path, mode):
             seq = oracle.stitch(["".join("ACGT"[s] for s in oracle.beam_search(m, 6)[0]) for m in mats])[0]
         want += [f">{rid}", seq[::-1]]
     assert got[:len(want)] == want and len(want) == 10
+
+
+def test_near_tie_counter():
+    """out_counters[2]: frames whose selection ranked two candidates within 2^-40 of each other.
+    Posteriors drawn from a handful of values are full of them; realistic posteriors have almost
+    none (a beam search on those never hangs on rounding noise)."""
+    from radian_b200 import decode, synth
+
+    rng = np.random.default_rng(2)
+    lg = np.round(rng.normal(0, 1.5, (300, 5)))
+    tie = np.exp(lg)
+    tie = (tie / tie.sum(1, keepdims=True)).astype(np.float32)
+    post, off = synth.make_reads(np.array([40, 60, 25]), seed=9)
+    post = post.numpy()
+    off = off.numpy()
+    mats = [tie] + [post[off[i]:off[i + 1]] for i in range(3)]
+    for bw in (6, 64):
+        _, scores, cnt = decode.beam_search_batch(mats, bw, None, None, None, None, return_details=True)
+        assert cnt.shape == (4, 4) and int(cnt[0, 2]) > 20
+        assert int(cnt[1:, 2].sum()) <= 3
