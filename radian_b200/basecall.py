@@ -89,15 +89,15 @@ def basecall_batch(read_ids, chunk_lists, args, table):
                                  args.context_len)
     # chunk mode (basecall.py:110-123): every window decoded with the model off, then all reads'
     # fragments stitched in one call
-    from .sequence_assembly import stitch_batch
+    from .sequence_assembly import stitch_flat
 
     flat = [m for mats in chunk_lists for m in mats]
-    frags = beam_search_batch(flat, args.beam_width, None, None, None, None)
-    per_read, k = [], 0
-    for mats in chunk_lists:
-        per_read.append(frags[k:k + len(mats)])
-        k += len(mats)
-    return stitch_batch(per_read)
+    sym, frag_off = beam_search_batch(flat, args.beam_width, None, None, None, None, return_symbols=True)
+    ranges = np.zeros(len(chunk_lists) + 1, dtype=np.int64)
+    ranges[1:] = np.cumsum([len(mats) for mats in chunk_lists])
+    seq, off = stitch_flat(sym, frag_off, ranges)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    return [lut[seq[off[r]:off[r + 1]]].tobytes().decode("ascii") for r in range(len(chunk_lists))]
 
 
 def windows_from_fast5(path, args):

@@ -132,11 +132,12 @@ def _current_device() -> int:
 
 
 def beam_search_batch(mats, beam_width, lm=None, s_threshold=None, r_threshold=None, len_context=None,
-                      bases="ACGT", device=None, return_details=False):
+                      bases="ACGT", device=None, return_details=False, return_symbols=False):
     """Decode a list of (T_i, 5) posterior matrices (all float32 or all float64) in one launch.
     Returns the list of decoded strings, or (strings, scores[n,2], counters[n,4]) with
     ``return_details`` (counters: lm reads, combine_dists calls, near-tie frames, 0; see
-    include/radian_b200.h)."""
+    include/radian_b200.h), or with ``return_symbols`` the compact ``(symbols uint8, offsets int64[n+1])``
+    pair that ``sequence_assembly.stitch_flat`` takes."""
     if len(bases) != N_BASES:
         raise ValueError("this build decodes 4 bases + blank (chars == 5, decode.py:124-125)")
     if int(beam_width) < 1 or int(beam_width) > _native.MAX_BEAM_WIDTH:
@@ -145,6 +146,8 @@ def beam_search_batch(mats, beam_width, lm=None, s_threshold=None, r_threshold=N
     table = _resolve_table(lm, len_context, device)
     n = len(mats)
     if n == 0:
+        if return_symbols:
+            return np.zeros(0, np.uint8), np.zeros(1, np.int64)
         return ([], np.zeros((0, 2)), np.zeros((0, 4), np.uint64)) if return_details else []
     dt = np.float64 if any(np.asarray(m).dtype == np.float64 for m in mats) else np.float32
     arrs = []
@@ -173,6 +176,12 @@ def beam_search_batch(mats, beam_width, lm=None, s_threshold=None, r_threshold=N
         _native.np_ptr(seq), _native.np_ptr(so), _native.np_ptr(ln), _native.np_ptr(score),
         _native.np_ptr(status), _native.np_ptr(cnt), device)
     _native.check(rc)
+    if return_symbols:
+        # compact symbols 0..3 of all reads back to back + offsets: what stitch_flat takes
+        off = np.zeros(n + 1, dtype=np.int64)
+        off[1:] = np.cumsum(ln)
+        idx = np.repeat(so[:-1] - off[:-1], ln) + np.arange(int(off[-1]), dtype=np.int64)
+        return seq[idx], off
     lut = np.frombuffer(bases.encode("ascii"), dtype=np.uint8)
     out = [lut[seq[so[i]:so[i] + ln[i]]].tobytes().decode("ascii") for i in range(n)]
     return (out, score, cnt) if return_details else out

@@ -30,36 +30,57 @@ def _encode(fragment) -> np.ndarray:
     return sym
 
 
+def stitch_flat(sym, frag_offsets, read_frag_ranges, device=None, return_votes=False):
+    """Stitch on flat arrays: ``sym`` uint8 symbols 0..3 of all fragments back to back,
+    ``frag_offsets`` (n_frags+1) into it, ``read_frag_ranges`` (n_reads+1) fragment indices per read.
+    -> ``(consensus symbols uint8 back to back, offsets int64[n_reads+1])`` and, with
+    ``return_votes``, the ``(columns, 4)`` int32 vote counts at the same offsets."""
+    from .decode import _current_device
+
+    device = _current_device() if device is None else int(device)
+    sym = np.ascontiguousarray(sym, dtype=np.uint8)
+    foff = np.ascontiguousarray(frag_offsets, dtype=np.int64)
+    rfr = np.ascontiguousarray(read_frag_ranges, dtype=np.int64)
+    n = len(rfr) - 1
+    if n <= 0:
+        return (np.zeros(0, np.uint8), np.zeros(1, np.int64)) + ((np.zeros((0, 4), np.int32),) if return_votes else ())
+    # a slot as large as the sum of the read's fragment lengths always suffices
+    slots = np.zeros(n + 1, dtype=np.int64)
+    slots[1:] = np.cumsum(np.maximum(foff[rfr[1:]] - foff[rfr[:-1]], 1))
+    seq = np.zeros(int(slots[-1]), dtype=np.uint8)
+    ln = np.zeros(n, dtype=np.int64)
+    status = np.zeros(n, dtype=np.int32)
+    votes = np.zeros((int(slots[-1]), 4), dtype=np.int32) if return_votes else None
+    if sym.size == 0:
+        sym = np.zeros(1, dtype=np.uint8)
+    rc = lib.radian_stitch_batch_host(_native.np_ptr(sym), _native.np_ptr(foff), _native.np_ptr(rfr), n,
+                                      _native.np_ptr(seq), _native.np_ptr(slots), _native.np_ptr(ln),
+                                      _native.np_ptr(status), _native.np_ptr(votes), device)
+    _native.check(rc)
+    off = np.zeros(n + 1, dtype=np.int64)
+    off[1:] = np.cumsum(ln)
+    idx = np.repeat(slots[:-1] - off[:-1], ln) + np.arange(int(off[-1]), dtype=np.int64)
+    return (seq[idx], off) + ((votes[idx],) if return_votes else ())
+
+
 def stitch_batch(fragment_lists, device=None, return_votes=False, bases="ACGT"):
     """Consensus string of every read from its chunk-mode fragments (strings over ACGT, or uint8
     arrays of symbols 0..3 as the decoder returns them).  With ``return_votes`` also the
     ``(4, length)`` vote counts of every read, the array the reference's simple_assembly returns."""
-    from .decode import _current_device
-
-    device = _current_device() if device is None else int(device)
     n = len(fragment_lists)
     frags = [[_encode(f) for f in fl] for fl in fragment_lists]
     rfr = np.zeros(n + 1, dtype=np.int64)
-    rfr[1:] = np.cumsum([len(fl) for fl in frags])
+    rfr[1:] = np.cumsum([len(fl) for fl in frags]) if n else 0
     flat = [f for fl in frags for f in fl]
     foff = np.zeros(len(flat) + 1, dtype=np.int64)
     foff[1:] = np.cumsum([f.size for f in flat]) if flat else 0
-    sym = np.concatenate(flat) if flat and foff[-1] else np.zeros(1, dtype=np.uint8)
-    slots = np.zeros(n + 1, dtype=np.int64)
-    slots[1:] = np.cumsum([max(1, int(sum(f.size for f in fl))) for fl in frags])
-    seq = np.zeros(int(slots[-1]) if n else 1, dtype=np.uint8)
-    ln = np.zeros(max(n, 1), dtype=np.int64)
-    status = np.zeros(max(n, 1), dtype=np.int32)
-    votes = np.zeros((int(slots[-1]) if n else 1, 4), dtype=np.int32) if return_votes else None
-    if n:
-        rc = lib.radian_stitch_batch_host(_native.np_ptr(sym), _native.np_ptr(foff), _native.np_ptr(rfr), n,
-                                          _native.np_ptr(seq), _native.np_ptr(slots), _native.np_ptr(ln),
-                                          _native.np_ptr(status), _native.np_ptr(votes), device)
-        _native.check(rc)
+    sym = np.concatenate(flat) if flat and foff[-1] else np.zeros(0, dtype=np.uint8)
+    res = stitch_flat(sym, foff, rfr, device, return_votes)
+    seq, off = res[0], res[1]
     lut = np.frombuffer(bases.encode("ascii"), dtype=np.uint8)
-    out = [lut[seq[slots[r]:slots[r] + ln[r]]].tobytes().decode("ascii") for r in range(n)]
+    out = [lut[seq[off[r]:off[r + 1]]].tobytes().decode("ascii") for r in range(n)]
     if return_votes:
-        return out, [votes[slots[r]:slots[r] + ln[r]].T.astype(np.float64) for r in range(n)]
+        return out, [res[2][off[r]:off[r + 1]].T.astype(np.float64) for r in range(n)]
     return out
 
 
