@@ -192,6 +192,23 @@ int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *frag_offset
                              int32_t *out_votes, int device);
 
 /*
+ * The same on device pointers, asynchronous on `stream`.  Fragments are given by start and length
+ * into frag_sym, so the out_seq / seq_offsets / out_len of a chunk-mode radian_decode_batch_dev call
+ * can be passed as they are (frag_start = seq_offsets, frag_len = out_len).  out_offsets are the
+ * caller's slots (total_slots = out_offsets[n_reads]; a read whose consensus does not fit its slot
+ * gets RADIAN_READ_SEQ_OVERFLOW).  Pairs whose second fragment has 200 symbols or more run
+ * difflib's full recursion in a scratch pool of long_pair_scratch_ints 32-bit words inside the
+ * workspace (0 if no fragment is that long; a read that finds the pool empty gets
+ * RADIAN_READ_TRIE_OVERFLOW).  Statuses are per read; the call itself returns RADIAN_OK.
+ */
+size_t radian_stitch_workspace_bytes(int64_t n_frags, int64_t total_slots, int64_t long_pair_scratch_ints);
+int radian_stitch_batch_dev(const uint8_t *frag_sym, const int64_t *frag_start, const int64_t *frag_len,
+                            const int64_t *read_frag_ranges, int n_reads, int64_t n_frags, uint8_t *out_seq,
+                            const int64_t *out_offsets, int64_t total_slots, int64_t *out_len,
+                            int32_t *out_status, int32_t *out_votes, int64_t long_pair_scratch_ints,
+                            void *workspace, size_t workspace_bytes, radian_stream_t stream);
+
+/*
  * Signal preprocessing for a batch of reads: replaces preprocess.mad_normalise
  * (radian/preprocess.py:23-49, call site radian/basecall.py:78).
  *

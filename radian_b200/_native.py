@@ -20,7 +20,7 @@ EXPORTS = [
     "radian_table_create", "radian_table_destroy", "radian_table_context_len", "radian_table_entropies",
     "radian_decode_workspace_bytes", "radian_decode_batch_dev", "radian_decode_batch_host",
     "radian_assemble_plan", "radian_assemble_batch_dev", "radian_assemble_batch_host",
-    "radian_stitch_batch_host",
+    "radian_stitch_batch_host", "radian_stitch_batch_dev", "radian_stitch_workspace_bytes",
     "radian_normalise_batch_host", "radian_normalise_batch_dev", "radian_windows_plan",
     "radian_windows_batch_host", "radian_windows_batch_dev",
 ]
@@ -67,6 +67,12 @@ def _load():
     lib.radian_stitch_batch_host.restype = c_int
     lib.radian_stitch_batch_host.argtypes = [
         c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]
+    lib.radian_stitch_workspace_bytes.restype = c_size_t
+    lib.radian_stitch_workspace_bytes.argtypes = [c_int64, c_int64, c_int64]
+    lib.radian_stitch_batch_dev.restype = c_int
+    lib.radian_stitch_batch_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p,
+                                            c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                            c_size_t, c_void_p]
     lib.radian_normalise_batch_host.restype = c_int
     lib.radian_normalise_batch_host.argtypes = [c_void_p, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p,
                                                 c_void_p, c_int]

@@ -18,6 +18,7 @@
 // the first largest block is the top-level match.  From 200 symbols on the autojunk rule drops
 // "popular" symbols from b2j and the top-level match need not be the largest block any more: those
 // pairs run the complete get_matching_blocks recursion in global scratch.
+#include <limits.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -135,34 +136,49 @@ __host__ __device__ inline int64_t pair_scratch_ints(int64_t la, int64_t lb)
     return 3 * nmax + 4 * (2 * nmax + 2) + 2 * (lb + 2);
 }
 
-// disp[f] = block[0] - block[1] for fragment f against its predecessor (0 for a read's first)
-__global__ void pair_kernel(const uint8_t *__restrict__ sym, const int64_t *__restrict__ frag_off,
-                            const uint8_t *__restrict__ is_first, int64_t n_frags,
-                            const int64_t *__restrict__ scratch_off, int *__restrict__ scratch,
+// which read owns fragment f (one thread per read fills its range)
+__global__ void owner_kernel(const int64_t *__restrict__ read_frag, int n_reads, int32_t *__restrict__ frag_read)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    for (int64_t f = read_frag[r]; f < read_frag[r + 1]; ++f) frag_read[f] = r;
+}
+
+// disp[f] = block[0] - block[1] for fragment f against its predecessor (0 for a read's first).
+// Fragments are given by start and length, so the decoder's output slots can be used as they are.
+// Pairs with 200 symbols or more take their scratch from a pool (bump allocation); a pair that
+// finds it empty marks the read (disp = INT_MIN).
+__global__ void pair_kernel(const uint8_t *__restrict__ sym, const int64_t *__restrict__ frag_start,
+                            const int64_t *__restrict__ frag_len, const int64_t *__restrict__ read_frag,
+                            const int32_t *__restrict__ frag_read, int64_t n_frags, int *__restrict__ pool,
+                            unsigned long long *__restrict__ pool_used, int64_t pool_ints,
                             int32_t *__restrict__ disp)
 {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frags) return;
-    if (is_first[f]) {
+    if (f == read_frag[frag_read[f]]) {
         disp[f] = 0;
         return;
     }
-    const uint8_t *a = sym + frag_off[f - 1];
-    const uint8_t *b = sym + frag_off[f];
-    const int la = (int)(frag_off[f] - frag_off[f - 1]);
-    const int lb = (int)(frag_off[f + 1] - frag_off[f]);
+    const uint8_t *a = sym + frag_start[f - 1];
+    const uint8_t *b = sym + frag_start[f];
+    const int la = (int)frag_len[f - 1];
+    const int lb = (int)frag_len[f];
     if (lb < kStitchFast) {
         uint16_t row0[kStitchFast + 2], row1[kStitchFast + 2];  // a match is at most lb < 200 long
         const Blk x = longest_match<uint16_t>(a, b, 0, la, 0, lb, 0u, row0, row1);
         disp[f] = x.k ? x.i - x.j : la - lb;  // no common symbol: only the (la, lb, 0) sentinel
     } else {
-        disp[f] = disp_general(a, la, b, lb, scratch + scratch_off[f]);
+        const int64_t need = pair_scratch_ints(la, lb);
+        const unsigned long long at = atomicAdd(pool_used, (unsigned long long)need);
+        disp[f] = (int64_t)at + need <= pool_ints ? disp_general(a, la, b, lb, pool + at) : INT_MIN;
     }
 }
 
 // per read: running position, growth rule, IndexError, consensus length
-__global__ void place_kernel(const int64_t *__restrict__ frag_off, const int64_t *__restrict__ read_frag,
-                             int n_reads, const int32_t *__restrict__ disp, int64_t *__restrict__ start,
+__global__ void place_kernel(const int64_t *__restrict__ frag_len, const int64_t *__restrict__ read_frag,
+                             const int64_t *__restrict__ out_offsets, int n_reads,
+                             const int32_t *__restrict__ disp, int64_t *__restrict__ start,
                              int64_t *__restrict__ out_len, int32_t *__restrict__ status)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -172,10 +188,11 @@ __global__ void place_kernel(const int64_t *__restrict__ frag_off, const int64_t
     const int64_t f0 = read_frag[r], f1 = read_frag[r + 1];
     if (f1 - f0 > 65535) st = RADIAN_READ_SEQ_OVERFLOW;  // the packed vote counters are 16 bits wide
     for (int64_t f = f0; f < f1; ++f) {
-        const int64_t len = frag_off[f + 1] - frag_off[f];
+        const int64_t len = frag_len[f];
         int64_t s = 0;
         if (f > f0) {
             const int64_t d = disp[f];
+            if (d == INT_MIN && st == RADIAN_READ_OK) st = RADIAN_READ_TRIE_OVERFLOW;  // scratch pool exhausted
             if (d + pos + len > census) census += 1000;  // sequence_assembly.py:33-36, one step only
             s = pos + d;
             pos += d;
@@ -187,55 +204,144 @@ __global__ void place_kernel(const int64_t *__restrict__ frag_off, const int64_t
         if (len > skip && s0 + (len - skip) > census && st == RADIAN_READ_OK) st = RADIAN_READ_INDEX_ERROR;
     }
     if (length > census) length = census;
+    if (st == RADIAN_READ_OK && length > out_offsets[r + 1] - out_offsets[r]) st = RADIAN_READ_SEQ_OVERFLOW;
     out_len[r] = st == RADIAN_READ_OK ? length : 0;
     status[r] = st;
 }
 
 // votes: one 64-bit word per consensus column, 16 bits per base
-__global__ void vote_kernel(const uint8_t *__restrict__ sym, const int64_t *__restrict__ frag_off,
-                            const int32_t *__restrict__ frag_read, int64_t n_frags,
-                            const int64_t *__restrict__ start, const int64_t *__restrict__ out_len,
-                            const int64_t *__restrict__ col_off, unsigned long long *__restrict__ votes)
+__global__ void vote_kernel(const uint8_t *__restrict__ sym, const int64_t *__restrict__ frag_start,
+                            const int64_t *__restrict__ frag_len, const int32_t *__restrict__ frag_read,
+                            int64_t n_frags, const int64_t *__restrict__ start, const int64_t *__restrict__ out_len,
+                            const int64_t *__restrict__ out_offsets, unsigned long long *__restrict__ votes)
 {
     const int64_t f = blockIdx.x;
     if (f >= n_frags) return;
     const int r = frag_read[f];
     const int64_t length = out_len[r];
     const int64_t s = start[f];
-    const int64_t len = frag_off[f + 1] - frag_off[f];
-    const uint8_t *p = sym + frag_off[f];
-    unsigned long long *v = votes + col_off[r];
+    const int64_t len = frag_len[f];
+    const uint8_t *p = sym + frag_start[f];
+    unsigned long long *v = votes + out_offsets[r];
     for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
         const int64_t col = s + i;  // s < 0: the first -s symbols fall off
         if (col >= 0 && col < length) atomicAdd(&v[col], 1ull << (16 * p[i]));
     }
 }
 
-__global__ void argmax_kernel(const unsigned long long *__restrict__ votes, int64_t n_cols,
-                              uint8_t *__restrict__ seq, int32_t *__restrict__ counts)
+// one block per read: first maximum of every consensus column, optional vote counts
+__global__ void argmax_kernel(const unsigned long long *__restrict__ votes, const int64_t *__restrict__ out_offsets,
+                              const int64_t *__restrict__ out_len, int n_reads, uint8_t *__restrict__ seq,
+                              int32_t *__restrict__ counts)
 {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cols) return;
-    const unsigned long long w = votes[c];
-    int best = 0, bv = (int)(w & 0xffff);
+    for (int r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const int64_t o = out_offsets[r], n = out_len[r];
+        for (int64_t c = threadIdx.x; c < n; c += blockDim.x) {
+            const unsigned long long w = votes[o + c];
+            int best = 0, bv = (int)(w & 0xffff);
 #pragma unroll
-    for (int s = 1; s < 4; ++s) {
-        const int x = (int)((w >> (16 * s)) & 0xffff);
-        if (x > bv) {  // np.argmax: first maximum
-            bv = x;
-            best = s;
+            for (int s = 1; s < 4; ++s) {
+                const int x = (int)((w >> (16 * s)) & 0xffff);
+                if (x > bv) {  // np.argmax: first maximum
+                    bv = x;
+                    best = s;
+                }
+            }
+            seq[o + c] = (uint8_t)best;
+            if (counts) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) counts[(o + c) * 4 + s] = (int)((w >> (16 * s)) & 0xffff);
+            }
         }
     }
-    seq[c] = (uint8_t)best;
-    if (counts) {
-#pragma unroll
-        for (int s = 0; s < 4; ++s) counts[c * 4 + s] = (int)((w >> (16 * s)) & 0xffff);
+}
+
+struct StitchWs {
+    int32_t *frag_read, *disp;
+    int64_t *start;
+    unsigned long long *votes, *pool_used;
+    int *pool;
+    int64_t pool_ints;
+};
+
+static size_t stitch_ws_layout(int64_t n_frags, int64_t total_slots, int64_t pool_ints, void *base, StitchWs *ws)
+{
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = o;
+        o += (bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    const size_t o_used = take(8), o_votes = take((size_t)total_slots * 8), o_start = take((size_t)n_frags * 8),
+                 o_read = take((size_t)n_frags * 4), o_disp = take((size_t)n_frags * 4),
+                 o_pool = take((size_t)pool_ints * 4);
+    if (ws) {
+        char *b = (char *)base;
+        ws->pool_used = (unsigned long long *)(b + o_used);
+        ws->votes = (unsigned long long *)(b + o_votes);
+        ws->start = (int64_t *)(b + o_start);
+        ws->frag_read = (int32_t *)(b + o_read);
+        ws->disp = (int32_t *)(b + o_disp);
+        ws->pool = (int *)(b + o_pool);
+        ws->pool_ints = pool_ints;
     }
+    return o;
 }
 
 }  // namespace radian
 
 using namespace radian;
+
+extern "C" size_t radian_stitch_workspace_bytes(int64_t n_frags, int64_t total_slots, int64_t long_pair_scratch_ints)
+{
+    if (n_frags < 0 || total_slots < 0 || long_pair_scratch_ints < 0) return 0;
+    return stitch_ws_layout(n_frags, total_slots, long_pair_scratch_ints, nullptr, nullptr);
+}
+
+extern "C" int radian_stitch_batch_dev(const uint8_t *frag_sym, const int64_t *frag_start, const int64_t *frag_len,
+                                       const int64_t *read_frag_ranges, int n_reads, int64_t n_frags,
+                                       uint8_t *out_seq, const int64_t *out_offsets, int64_t total_slots,
+                                       int64_t *out_len, int32_t *out_status, int32_t *out_votes,
+                                       int64_t long_pair_scratch_ints, void *workspace, size_t workspace_bytes,
+                                       radian_stream_t stream)
+{
+    if (n_reads < 0 || n_frags < 0 || !read_frag_ranges || !out_offsets || !out_len || !out_status ||
+        (n_frags > 0 && (!frag_start || !frag_len))) {
+        set_error("radian_stitch_batch_dev: null argument");
+        return RADIAN_E_ARG;
+    }
+    if (n_reads == 0) return RADIAN_OK;
+    StitchWs ws;
+    const size_t need = stitch_ws_layout(n_frags, total_slots, long_pair_scratch_ints, workspace, &ws);
+    if (!workspace || workspace_bytes < need) {
+        set_error("radian_stitch_batch_dev: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+        return RADIAN_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    RADIAN_CUDA(cudaMemsetAsync(ws.pool_used, 0, 8, st));
+    if (total_slots > 0) RADIAN_CUDA(cudaMemsetAsync(ws.votes, 0, (size_t)total_slots * 8, st));
+    const unsigned rb = (unsigned)((n_reads + 127) / 128);
+    owner_kernel<<<rb, 128, 0, st>>>(read_frag_ranges, n_reads, ws.frag_read);
+    if (n_frags > 0)
+        pair_kernel<<<(unsigned)((n_frags + 127) / 128), 128, 0, st>>>(frag_sym, frag_start, frag_len, read_frag_ranges,
+                                                                         ws.frag_read, n_frags, ws.pool, ws.pool_used,
+                                                                         ws.pool_ints, ws.disp);
+    place_kernel<<<rb, 128, 0, st>>>(frag_len, read_frag_ranges, out_offsets, n_reads, ws.disp, ws.start, out_len,
+                                     out_status);
+    if (n_frags > 0 && total_slots > 0) {
+        vote_kernel<<<(unsigned)n_frags, 64, 0, st>>>(frag_sym, frag_start, frag_len, ws.frag_read, n_frags, ws.start,
+                                                      out_len, out_offsets, ws.votes);
+        int device = 0;
+        RADIAN_CUDA(cudaGetDevice(&device));
+        DeviceInfo di;
+        int rc = device_info(device, &di);
+        if (rc) return rc;
+        const int grid = n_reads < di.sm_count * 16 ? n_reads : di.sm_count * 16;
+        argmax_kernel<<<grid, 128, 0, st>>>(ws.votes, out_offsets, out_len, n_reads, out_seq, out_votes);
+    }
+    RADIAN_CUDA(cudaGetLastError());
+    return RADIAN_OK;
+}
 
 extern "C" int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *frag_offsets,
                                         const int64_t *read_frag_ranges, int n_reads, uint8_t *out_seq,
@@ -252,8 +358,8 @@ extern "C" int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *
         return RADIAN_E_CUDA;
     }
     const int64_t n_frags = read_frag_ranges[n_reads];
-    if (read_frag_ranges[0] != 0 || n_frags < 0) {
-        set_error("radian_stitch_batch_host: read_frag_ranges must start at 0");
+    if (read_frag_ranges[0] != 0 || n_frags < 0 || out_offsets[0] != 0) {
+        set_error("radian_stitch_batch_host: read_frag_ranges and out_offsets must start at 0");
         return RADIAN_E_ARG;
     }
     for (int r = 0; r < n_reads; ++r)
@@ -262,11 +368,15 @@ extern "C" int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *
             return RADIAN_E_ARG;
         }
     const int64_t n_sym = n_frags ? frag_offsets[n_frags] : 0;
+    int64_t pool_ints = 0;
+    std::vector<int64_t> flen((size_t)(n_frags ? n_frags : 1));
     for (int64_t f = 0; f < n_frags; ++f) {
         if (frag_offsets[f + 1] < frag_offsets[f]) {
             set_error("radian_stitch_batch_host: fragment offsets not monotone at fragment %lld", (long long)f);
             return RADIAN_E_ARG;
         }
+        flen[f] = frag_offsets[f + 1] - frag_offsets[f];
+        if (f > 0 && flen[f] >= kStitchFast) pool_ints += pair_scratch_ints(flen[f - 1], flen[f]);
     }
     for (int64_t i = 0; i < n_sym; ++i)
         if (frag_sym[i] > 3) {
@@ -283,119 +393,58 @@ extern "C" int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *
         int krc = keep_pool(device);
         if (krc) return krc;
     }
-    // host-side plan: which fragment starts a read, which read owns it, scratch of the long pairs
-    std::vector<uint8_t> is_first((size_t)n_frags, 0);
-    std::vector<int32_t> frag_read((size_t)n_frags, 0);
-    std::vector<int64_t> scratch_off((size_t)n_frags, 0);
-    int64_t scratch_ints = 0;
-    for (int r = 0; r < n_reads; ++r)
-        for (int64_t f = read_frag_ranges[r]; f < read_frag_ranges[r + 1]; ++f) {
-            is_first[f] = (f == read_frag_ranges[r]);
-            frag_read[f] = r;
-            const int64_t lb = frag_offsets[f + 1] - frag_offsets[f];
-            if (!is_first[f] && lb >= kStitchFast) {
-                scratch_off[f] = scratch_ints;
-                scratch_ints += pair_scratch_ints(frag_offsets[f] - frag_offsets[f - 1], lb);
-            }
-        }
     static const bool trace = getenv("RADIAN_TRACE") != nullptr;
+    const int64_t total_slots = out_offsets[n_reads];
+    const size_t ws_bytes = radian_stitch_workspace_bytes(n_frags, total_slots, pool_ints);
     cudaStream_t st = nullptr;
     RADIAN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    cudaEvent_t evt[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evt[2] = {nullptr, nullptr};
     if (trace)
         for (auto &x : evt) RADIAN_CUDA(cudaEventCreate(&x));
-    uint8_t *d_sym = nullptr, *d_first = nullptr, *d_seq = nullptr;
-    int64_t *d_foff = nullptr, *d_rfr = nullptr, *d_soff = nullptr, *d_start = nullptr, *d_len = nullptr, *d_col = nullptr;
-    int32_t *d_fread = nullptr, *d_disp = nullptr, *d_status = nullptr, *d_counts = nullptr;
-    int *d_scratch = nullptr;
-    unsigned long long *d_votes = nullptr;
+    uint8_t *d_sym = nullptr, *d_seq = nullptr;
+    int64_t *d_fstart = nullptr, *d_flen = nullptr, *d_rfr = nullptr, *d_ooff = nullptr, *d_len = nullptr;
+    int32_t *d_status = nullptr, *d_counts = nullptr;
+    void *d_ws = nullptr;
     int ret = RADIAN_OK;
     cudaError_t e;
 #define TRY(x)                                   \
     if (ret == RADIAN_OK && (e = (x)) != cudaSuccess) ret = cuda_fail(e, #x)
     TRY(cudaMallocAsync(&d_sym, (size_t)(n_sym ? n_sym : 1), st));
-    TRY(cudaMallocAsync(&d_first, (size_t)n_frags, st));
-    TRY(cudaMallocAsync(&d_foff, (size_t)(n_frags + 1) * 8, st));
+    TRY(cudaMallocAsync(&d_seq, (size_t)(total_slots ? total_slots : 1), st));
+    TRY(cudaMallocAsync(&d_fstart, (size_t)n_frags * 8, st));
+    TRY(cudaMallocAsync(&d_flen, (size_t)n_frags * 8, st));
     TRY(cudaMallocAsync(&d_rfr, (size_t)(n_reads + 1) * 8, st));
-    TRY(cudaMallocAsync(&d_soff, (size_t)n_frags * 8, st));
-    TRY(cudaMallocAsync(&d_start, (size_t)n_frags * 8, st));
-    TRY(cudaMallocAsync(&d_fread, (size_t)n_frags * 4, st));
-    TRY(cudaMallocAsync(&d_disp, (size_t)n_frags * 4, st));
+    TRY(cudaMallocAsync(&d_ooff, (size_t)(n_reads + 1) * 8, st));
     TRY(cudaMallocAsync(&d_len, (size_t)n_reads * 8, st));
-    TRY(cudaMallocAsync(&d_col, (size_t)(n_reads + 1) * 8, st));
     TRY(cudaMallocAsync(&d_status, (size_t)n_reads * 4, st));
-    TRY(cudaMallocAsync(&d_scratch, (size_t)(scratch_ints ? scratch_ints : 1) * 4, st));
+    TRY(cudaMallocAsync(&d_ws, ws_bytes, st));
+    if (out_votes) TRY(cudaMallocAsync(&d_counts, (size_t)(total_slots ? total_slots : 1) * 16, st));
     if (n_sym) TRY(cudaMemcpyAsync(d_sym, frag_sym, (size_t)n_sym, cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(d_first, is_first.data(), (size_t)n_frags, cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(d_foff, frag_offsets, (size_t)(n_frags + 1) * 8, cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(d_fstart, frag_offsets, (size_t)n_frags * 8, cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(d_flen, flen.data(), (size_t)n_frags * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_rfr, read_frag_ranges, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(d_soff, scratch_off.data(), (size_t)n_frags * 8, cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(d_fread, frag_read.data(), (size_t)n_frags * 4, cudaMemcpyHostToDevice, st));
-    if (ret == RADIAN_OK) {
-        if (trace) cudaEventRecord(evt[0], st);
-        pair_kernel<<<(unsigned)((n_frags + 127) / 128), 128, 0, st>>>(d_sym, d_foff, d_first, n_frags, d_soff,
-                                                                         d_scratch, d_disp);
-        place_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, st>>>(d_foff, d_rfr, n_reads, d_disp, d_start,
-                                                                          d_len, d_status);
-        if (trace) cudaEventRecord(evt[1], st);
-        TRY(cudaGetLastError());
-    }
+    TRY(cudaMemcpyAsync(d_ooff, out_offsets, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (trace && ret == RADIAN_OK) cudaEventRecord(evt[0], st);
+    if (ret == RADIAN_OK)
+        ret = radian_stitch_batch_dev(d_sym, d_fstart, d_flen, d_rfr, n_reads, n_frags, d_seq, d_ooff, total_slots,
+                                      d_len, d_status, d_counts, pool_ints, d_ws, ws_bytes, st);
+    if (trace && ret == RADIAN_OK) cudaEventRecord(evt[1], st);
     TRY(cudaMemcpyAsync(out_len, d_len, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(out_status, d_status, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
+    if (total_slots) TRY(cudaMemcpyAsync(out_seq, d_seq, (size_t)total_slots, cudaMemcpyDeviceToHost, st));
+    if (out_votes && total_slots)
+        TRY(cudaMemcpyAsync(out_votes, d_counts, (size_t)total_slots * 16, cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
-    // consensus columns of all reads back to back
-    std::vector<int64_t> col((size_t)n_reads + 1, 0);
-    bool slot_small = false;
-    if (ret == RADIAN_OK) {
-        for (int r = 0; r < n_reads; ++r) {
-            col[r + 1] = col[r] + out_len[r];
-            if (out_len[r] > out_offsets[r + 1] - out_offsets[r]) slot_small = true;
-        }
-        if (slot_small) {
-            set_error("radian_stitch_batch_host: an output slot is smaller than the consensus "
-                      "(the sum of a read's fragment lengths always suffices)");
-            ret = RADIAN_E_ARG;
-        }
-    }
-    const int64_t n_cols = col[n_reads];
-    if (ret == RADIAN_OK && n_cols > 0) {
-        TRY(cudaMallocAsync(&d_votes, (size_t)n_cols * 8, st));
-        TRY(cudaMallocAsync(&d_seq, (size_t)n_cols, st));
-        if (out_votes) TRY(cudaMallocAsync(&d_counts, (size_t)n_cols * 16, st));
-        TRY(cudaMemsetAsync(d_votes, 0, (size_t)n_cols * 8, st));
-        TRY(cudaMemcpyAsync(d_col, col.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-        if (ret == RADIAN_OK) {
-            if (trace) cudaEventRecord(evt[2], st);
-            vote_kernel<<<(unsigned)n_frags, 64, 0, st>>>(d_sym, d_foff, d_fread, n_frags, d_start, d_len, d_col,
-                                                          d_votes);
-            argmax_kernel<<<(unsigned)((n_cols + 255) / 256), 256, 0, st>>>(d_votes, n_cols, d_seq, d_counts);
-            if (trace) cudaEventRecord(evt[3], st);
-            TRY(cudaGetLastError());
-        }
-        std::vector<uint8_t> h_seq((size_t)n_cols);
-        std::vector<int32_t> h_counts(out_votes ? (size_t)n_cols * 4 : 0);
-        TRY(cudaMemcpyAsync(h_seq.data(), d_seq, (size_t)n_cols, cudaMemcpyDeviceToHost, st));
-        if (out_votes) TRY(cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)n_cols * 16, cudaMemcpyDeviceToHost, st));
-        TRY(cudaStreamSynchronize(st));
-        if (ret == RADIAN_OK)
-            for (int r = 0; r < n_reads; ++r) {
-                if (out_len[r] > 0) memcpy(out_seq + out_offsets[r], h_seq.data() + col[r], (size_t)out_len[r]);
-                if (out_votes && out_len[r] > 0)
-                    memcpy(out_votes + out_offsets[r] * 4, h_counts.data() + col[r] * 4, (size_t)out_len[r] * 16);
-            }
-    }
 #undef TRY
-    if (trace && ret == RADIAN_OK && n_cols > 0) {
-        float ms_pair = 0, ms_vote = 0;
-        cudaEventElapsedTime(&ms_pair, evt[0], evt[1]);
-        cudaEventElapsedTime(&ms_vote, evt[2], evt[3]);
-        fprintf(stderr, "[radian] stitch: %d reads, %lld fragments, %lld symbols, %lld columns | pair+place %.3f ms, "
-                "vote+argmax %.3f ms\n", n_reads, (long long)n_frags, (long long)n_sym, (long long)n_cols, ms_pair, ms_vote);
+    if (trace && ret == RADIAN_OK) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, evt[0], evt[1]);
+        fprintf(stderr, "[radian] stitch: %d reads, %lld fragments, %lld symbols | kernels %.3f ms\n", n_reads,
+                (long long)n_frags, (long long)n_sym, ms);
     }
     if (trace)
         for (auto &x : evt) cudaEventDestroy(x);
-    void *frees[] = {d_sym, d_first, d_foff, d_rfr, d_soff, d_start, d_fread, d_disp, d_len, d_col, d_status,
-                     d_scratch, d_votes, d_seq, d_counts};
+    void *frees[] = {d_sym, d_seq, d_fstart, d_flen, d_rfr, d_ooff, d_len, d_status, d_ws, d_counts};
     for (void *p : frees)
         if (p) cudaFreeAsync(p, st);
     cudaStreamSynchronize(st);
@@ -403,6 +452,11 @@ extern "C" int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *
     if (ret != RADIAN_OK) return ret;
     for (int r = 0; r < n_reads; ++r)
         if (out_status[r] != RADIAN_READ_OK) {
+            if (out_status[r] == RADIAN_READ_SEQ_OVERFLOW) {
+                set_error("radian_stitch_batch_host: read %d: output slot smaller than the consensus, or more than "
+                          "65535 fragments (the sum of a read's fragment lengths always suffices as a slot)", r);
+                return RADIAN_E_ARG;
+            }
             set_error("radian_stitch_batch_host: read %d failed with status %d%s", r, out_status[r],
                       out_status[r] == RADIAN_READ_INDEX_ERROR
                           ? " (a fragment does not fit the reference's vote buffer: IndexError in add_count, "

@@ -63,6 +63,37 @@ def stitch_flat(sym, frag_offsets, read_frag_ranges, device=None, return_votes=F
     return (seq[idx], off) + ((votes[idx],) if return_votes else ())
 
 
+def stitch_device(frag_sym, frag_start, frag_len, read_frag_ranges, long_pair_scratch_ints=0):
+    """Resident variant on torch CUDA tensors, asynchronous on the current torch stream:
+    ``frag_sym`` uint8, ``frag_start`` / ``frag_len`` int64 (n_frags) -- e.g. ``res.seq``,
+    ``res.seq_offsets[:-1]``, ``res.lengths`` of a chunk-mode ``decode_batch_device`` call --
+    ``read_frag_ranges`` int64 (n_reads+1).  -> (seq uint8, out_offsets int64[n_reads+1], lengths
+    int64, status int32); every read's slot is the sum of its fragment lengths."""
+    import ctypes
+
+    import torch
+
+    dev = frag_sym.device
+    n_reads = read_frag_ranges.numel() - 1
+    n_frags = frag_len.numel()
+    csum = torch.zeros(n_frags + 1, dtype=torch.int64, device=dev)
+    csum[1:] = torch.cumsum(frag_len, 0)
+    slots = csum[read_frag_ranges]
+    out_offsets = (slots - slots[0]).contiguous()
+    total = int(out_offsets[-1].item())
+    seq = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    lengths = torch.empty(n_reads, dtype=torch.int64, device=dev)
+    status = torch.empty(n_reads, dtype=torch.int32, device=dev)
+    nbytes = lib.radian_stitch_workspace_bytes(n_frags, total, int(long_pair_scratch_ints))
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _native.check(lib.radian_stitch_batch_dev(
+        frag_sym.data_ptr(), frag_start.data_ptr(), frag_len.data_ptr(), read_frag_ranges.data_ptr(), n_reads,
+        n_frags, seq.data_ptr(), out_offsets.data_ptr(), total, lengths.data_ptr(), status.data_ptr(), None,
+        int(long_pair_scratch_ints), ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream)))
+    return seq, out_offsets, lengths, status
+
+
 def stitch_batch(fragment_lists, device=None, return_votes=False, bases="ACGT"):
     """Consensus string of every read from its chunk-mode fragments (strings over ACGT, or uint8
     arrays of symbols 0..3 as the decoder returns them).  With ``return_votes`` also the

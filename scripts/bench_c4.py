@@ -114,9 +114,18 @@ for r in range(2):
     mats = [c[cro[k] - cro[rcr[r]]:cro[k + 1] - cro[rcr[r]]] for k in range(int(rcr[r]), int(rcr[r + 1]))]
     ofr = ["".join("ACGT"[s] for s in oracle.beam_search(m, BW)[0]) for m in mats]
     assert frags == ofr and cons[r] == oracle.stitch(ofr)[0], f"chunk mode differs from the oracle on read {r}"
+# the same with everything resident: decoder output -> stitch, no host in between
+d_rcr = torch.from_numpy(rcr).to(dev)
+fstart = so[:-1].contiguous()
+dseq, doff, dlen, dst = sequence_assembly.stitch_device(cres.seq, fstart, cres.lengths, d_rcr)
+ms_st = timed(lambda: sequence_assembly.stitch_device(cres.seq, fstart, cres.lengths, d_rcr))
+assert int(dst.abs().sum()) == 0
+hs, ho, hl = dseq.cpu().numpy(), doff.cpu().numpy(), dlen.cpu().numpy()
+assert ["".join("ACGT"[s] for s in hs[ho[r]:ho[r] + hl[r]]) for r in range(n_reads)] == cons
 cbases = sum(len(c) for c in cons)
 out["chunk_decode_then_stitch"] = {
     "decode_ms": ms_cdec, "decode_frames_per_s": int(cro[-1]) / (ms_cdec * 1e-3), "stitch_host_call_s": dt_st,
+    "stitch_resident_ms": ms_st, "bases_per_s_resident": cbases / ((ms_cdec + ms_st) * 1e-3),
     "bases": cbases, "bases_per_s_decode_only": cbases / (ms_cdec * 1e-3),
     "bases_per_s_with_stitch_call": cbases / (ms_cdec * 1e-3 + dt_st), "identical_to_oracle_reads": 2,
     "note": "8x the frames of global mode (every frame is decoded in 8 windows); the stitch call is "

@@ -410,3 +410,32 @@ def test_near_tie_counter():
         _, scores, cnt = decode.beam_search_batch(mats, bw, None, None, None, None, return_details=True)
         assert cnt.shape == (4, 4) and int(cnt[0, 2]) > 20
         assert int(cnt[1:, 2].sum()) <= 3
+
+
+def test_stitch_device_resident_matches_host():
+    """radian_stitch_batch_dev on the decoder's own output slots == the host entry point."""
+    import torch
+
+    from radian_b200 import decode, sequence_assembly, synth
+
+    post, off = synth.make_reads(np.array([70, 30, 45]), seed=33, device="cuda")
+    p = post.cpu().numpy()
+    o = off.cpu().numpy()
+    chunk_lists = [synth.split_windows(p[o[i]:o[i + 1]], 256, 32) for i in range(3)]
+    flat = [m for cl in chunk_lists for m in cl]
+    rfr = np.zeros(4, np.int64)
+    rfr[1:] = np.cumsum([len(cl) for cl in chunk_lists])
+    cro = np.zeros(len(flat) + 1, np.int64)
+    cro[1:] = np.cumsum([len(m) for m in flat])
+    chunks = torch.from_numpy(np.concatenate(flat)).cuda()
+    d_cro = torch.from_numpy(cro).cuda()
+    res = decode.decode_batch_device(chunks, d_cro, 6, None, max_frames=256)
+    seq, ooff, ln, st = sequence_assembly.stitch_device(res.seq, res.seq_offsets[:-1].contiguous(), res.lengths,
+                                                        torch.from_numpy(rfr).cuda())
+    torch.cuda.synchronize()
+    assert int(st.abs().sum()) == 0
+    hs, ho, hl = seq.cpu().numpy(), ooff.cpu().numpy(), ln.cpu().numpy()
+    got = ["".join("ACGT"[s] for s in hs[ho[r]:ho[r] + hl[r]]) for r in range(3)]
+    frags = decode.beam_search_batch(flat, 6, None, None, None, None)
+    want = sequence_assembly.stitch_batch([frags[rfr[r]:rfr[r + 1]] for r in range(3)])
+    assert got == want and all(len(g) > 20 for g in got)
