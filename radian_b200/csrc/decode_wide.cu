@@ -286,7 +286,7 @@ decode_wide_kernel(const DecodeArgs a)
                     int z = max(max(hx.x & (int)byte_sign_mask<0>(km[s]), hx.y & (int)byte_sign_mask<1>(km[s])),
                                 max(hx.z & (int)byte_sign_mask<2>(km[s]), hx.w & (int)byte_sign_mask<3>(km[s])));
                     if (LM && gated) z = max(z, rmax[s]) + hS;
-                    const int ub = __double2hiint(ptot[s]) + z + (272000 - 0x3ff00000);
+                    const int ub = __double2hiint(ptot[s]) + z + (((LM && gated) ? 272000 : 181000) - 0x3ff00000);
                     quiet = quiet && ub < hw;
                 }
                 if (__all_sync(kFull, quiet)) {
