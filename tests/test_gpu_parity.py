@@ -439,3 +439,22 @@ def test_stitch_device_resident_matches_host():
     frags = decode.beam_search_batch(flat, 6, None, None, None, None)
     want = sequence_assembly.stitch_batch([frags[rfr[r]:rfr[r + 1]] for r in range(3)])
     assert got == want and all(len(g) > 20 for g in got)
+
+
+def test_host_entry_point_is_reentrant():
+    """Several host threads decoding at once through the same table handle (one call each, own
+    streams and scratch) get the results of a single-threaded run."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from radian_b200 import decode, synth
+
+    tab = decode.RnaTable(synth.make_table(6, 3))
+    batches = []
+    for k in range(6):
+        post, off = synth.make_reads(synth.read_lengths(20, 50 + k, median=60, lo=5, hi=200), seed=70 + k)
+        p, o = post.numpy(), off.numpy()
+        batches.append([p[o[i]:o[i + 1]] for i in range(20)])
+    want = [decode.beam_search_batch(b, 16, tab, 0.5, 0.5, 6) for b in batches]
+    with ThreadPoolExecutor(6) as ex:
+        got = list(ex.map(lambda b: decode.beam_search_batch(b, 16, tab, 0.5, 0.5, 6), batches * 3))
+    assert got == want * 3
