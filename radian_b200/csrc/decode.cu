@@ -6,8 +6,8 @@
 // How it computes it is new:
 //   * one group of G lanes (8/16/32) owns a read; lane == beam, all per-beam state in registers;
 //     a warp carries 32/G reads; a persistent grid pulls reads from an atomic queue.
-//   * scores are kept in the LINEAR domain as float64, rescaled every frame by an exact power
-//     of two (exponent accumulated in an integer).  logaddexp becomes '+', '+ log p' becomes
+//   * scores are kept in the LINEAR domain as float64, rescaled by an exact power of two whenever
+//     the best beam falls below 2^-256 (exponent accumulated in an integer).  logaddexp becomes '+', '+ log p' becomes
 //     '* p', and combine_dists is already linear, so the frame loop has no transcendental at
 //     all; ordering by pr_total is unchanged because log is monotone.  One log per read at
 //     the end gives the reference's log score.
@@ -17,10 +17,16 @@
 //     lanes then consume the records by broadcast reads.
 //   * a labeling is identified by a 64-bit rolling hash + length (the reference's dict key is
 //     the tuple itself); the only collision the algorithm can produce is copy(X) with
-//     extend(parent(X), last(X)), found through a parent-lane pointer kept per beam.
+//     extend(parent(X), last(X)), found through a parent-lane pointer kept per beam; the child
+//     computes the merged term itself from the parent's two scores and its own copy emission.
+//   * most frames are QUIET: the rank order of the copies (kept as state) holds and no extension
+//     can reach the worst copy, which an integer bound on the high words of the float64 values
+//     proves without computing a single extension; such a frame is one vote and three score
+//     updates per beam.  Only otherwise are the extension scores formed and, if needed, ranked.
 //   * stable top-k: rank = #candidates with (score desc, dict insertion position asc) before
-//     it, counted exactly on the float64 bit patterns; candidates that cannot reach the
-//     beam (below the worst copy) are pruned first.
+//     it, counted on the high words when they are all distinct (proved by the rank sum), else
+//     exactly on the float64 bit patterns; candidates that cannot reach the beam (below the
+//     worst copy) are pruned first.
 //   * labelings live in a per-group back-pointer arena (parent<<2|symbol).  The live beams of a
 //     read are combinations of its few most ambiguous positions, so their common ancestor stays
 //     near the start of the read: nothing can be flushed early.  The arena is generational
