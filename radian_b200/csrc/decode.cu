@@ -384,7 +384,15 @@ decode_kernel(const DecodeArgs a)
                                max(rb.y & (int)byte_sign_mask<2>(km), rb.w & (int)byte_sign_mask<3>(km)));
                 }
                 // high words of q0..q3 (gated lanes) or of P0..P3
-                const int4 hx = *reinterpret_cast<const int4 *>(reci + ((LM && gated) ? 28 : (LM ? 24 : 12)));
+                // (both loaded, then selected: one load whose address waits for `gated` is 1 % slower.
+                // Other A/Bs on B200: pinning `lane` in a register to spare the per-frame re-read of
+                // SR_TID costs more in register pressure than it saves, -2 %; refreshing the rescale
+                // exponent where the scores are committed instead of at the frame start is a wash.)
+                int4 hx = *reinterpret_cast<const int4 *>(reci + (LM ? 24 : 12));
+                if (LM) {
+                    const int4 hq = *reinterpret_cast<const int4 *>(reci + 28);
+                    if (gated) hx = hq;
+                }
                 // slack: 2 * 0.0861 * 2^20 for p * P_c, one more 0.0861 for the max(r, q) * S bound
                 const int kSlack = (LM && gated) ? 272000 : 181000;
                 const int z0 = hx.x & (int)byte_sign_mask<0>(km);
