@@ -68,6 +68,12 @@ int keep_pool(int device)
     return 0;
 }
 
+std::mutex &host_mutex(int device)
+{
+    static std::mutex mu[64];
+    return mu[device >= 0 && device < 64 ? device : 0];
+}
+
 // gate bit of context i: entropy(lm[context]) < r_threshold (decode.py:93, strict)
 __global__ void gate_kernel(const double *__restrict__ entropy, size_t rows, double thr, uint32_t *__restrict__ gate)
 {
@@ -312,6 +318,7 @@ static void *pinned_scratch(size_t bytes)
     return p;
 }
 
+
 // ---- staged upload -----------------------------------------------------------------------------
 // Pageable host memory reaches the device at ~10 GB/s through cudaMemcpyAsync (the driver stages
 // it on the calling thread), and page-locked memory at 80 % of the link when every read is its own
@@ -357,19 +364,24 @@ static StageRing *stage_ring(size_t slot_bytes, size_t n_flags)
     return &ring;
 }
 
-// reads in queue order k = 0..n-1: source frames src_frame[k], T[k] of them, device frames fo[k]
-static int staged_upload(const char *post, size_t row, const std::vector<int64_t> &src_frame,
-                         const std::vector<int64_t> &fo, char *d_post, int *d_ready, cudaStream_t cs[2],
-                         cudaEvent_t ev_last, int device)
+struct StageSeg {
+    int k0, k1;
+};
+
+struct StagePlan {
+    std::vector<StageSeg> segs;
+    StageRing *ring = nullptr;
+};
+
+// Segments of the queue that fit a slot, and the ring itself.  Everything that allocates happens
+// here, BEFORE the kernel is launched: a page-locked allocation can wait for the device to go
+// idle, which a kernel waiting for its input never does.
+static int stage_plan(const std::vector<int64_t> &fo, size_t row, StagePlan *plan)
 {
-    const int n = (int)src_frame.size();
+    const int n = (int)fo.size() - 1;
     size_t biggest = 0;
     for (int k = 0; k < n; ++k) biggest = std::max(biggest, (size_t)(fo[k + 1] - fo[k]) * row);
     const size_t slot_bytes = std::max(kStageBytes, biggest);
-    struct Seg {
-        int k0, k1;
-    };
-    std::vector<Seg> segs;
     for (int k = 0; k < n;) {
         int j = k;
         size_t bytes = (size_t)(fo[k + 1] - fo[k]) * row;
@@ -377,15 +389,25 @@ static int staged_upload(const char *post, size_t row, const std::vector<int64_t
             ++j;
             bytes += (size_t)(fo[j + 1] - fo[j]) * row;
         }
-        segs.push_back({k, j + 1});
+        plan->segs.push_back({k, j + 1});
         k = j + 1;
     }
-    const int nseg = (int)segs.size();
-    StageRing *ring = stage_ring(slot_bytes, (size_t)nseg);
-    if (!ring) {
+    plan->ring = stage_ring(slot_bytes, plan->segs.size());
+    if (!plan->ring) {
         set_error("radian_decode_batch_host: cannot page-lock the staging ring (%zu bytes per slot)", slot_bytes);
         return RADIAN_E_CUDA;
     }
+    return RADIAN_OK;
+}
+
+// reads in queue order k = 0..n-1: source frames src_frame[k], device frames fo[k]..fo[k+1]
+static int staged_upload(const char *post, size_t row, const std::vector<int64_t> &src_frame,
+                         const std::vector<int64_t> &fo, const StagePlan &plan, char *d_post, int *d_ready,
+                         cudaStream_t cs[2], cudaEvent_t ev_last, int device)
+{
+    const std::vector<StageSeg> &segs = plan.segs;
+    StageRing *ring = plan.ring;
+    const int nseg = (int)segs.size();
     std::vector<std::atomic<int>> filled((size_t)nseg), issued((size_t)nseg);
     for (int i = 0; i < nseg; ++i) filled[i].store(0), issued[i].store(0);
     std::atomic<int> next(0), failed(0);
@@ -416,7 +438,13 @@ static int staged_upload(const char *post, size_t row, const std::vector<int64_t
         });
     int ret = RADIAN_OK;
     cudaError_t e = cudaSuccess;
+    const char *stall_env = getenv("RADIAN_TEST_STALL_MS");  // test hook: hold the copies back midway
     for (int sgm = 0; sgm < nseg && ret == RADIAN_OK; ++sgm) {
+        if (stall_env && sgm == nseg / 2) {
+            cudaStreamSynchronize(cs[0]);
+            cudaStreamSynchronize(cs[1]);
+            std::this_thread::sleep_for(std::chrono::milliseconds(atoi(stall_env)));
+        }
         while (!filled[sgm].load(std::memory_order_acquire) && !failed.load()) std::this_thread::yield();
         if (failed.load()) {
             set_error("radian_decode_batch_host: staging worker failed");
@@ -542,6 +570,22 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     uint8_t *h_seq = (uint8_t *)(hp + o_seq);
     for (size_t i = 0; i < plan.size(); ++i) h_flag[i] = plan[i].pub;
 
+    // pageable sources (and RADIAN_HOST_STAGE=1) go through the staging ring, which is set up now
+    bool staged = getenv("RADIAN_HOST_STAGE") != nullptr && getenv("RADIAN_HOST_STAGE")[0] != '0';
+    if (!staged && getenv("RADIAN_HOST_STAGE") == nullptr && frames > 0) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, post) != cudaSuccess) {
+            cudaGetLastError();
+            staged = true;
+        } else {
+            staged = pa.type == cudaMemoryTypeUnregistered;
+        }
+    }
+    StagePlan splan;
+    if (staged) {
+        const int prc = stage_plan(fo, row, &splan);
+        if (prc) return prc;
+    }
     cudaStream_t st = nullptr, cs[2] = {nullptr, nullptr};
     cudaEvent_t ev = nullptr, ev_last = nullptr;
     RADIAN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -551,7 +595,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     RADIAN_CUDA(cudaEventCreateWithFlags(&ev_last, cudaEventDisableTiming));
     void *d_post = nullptr, *d_ws = nullptr;
     int64_t *d_fo = nullptr, *d_so = nullptr, *d_len = nullptr;
-    int32_t *d_status = nullptr;
+    int32_t *d_status = nullptr, *d_order = nullptr;
     int *d_ready = nullptr;
     uint8_t *d_seq = nullptr;
     double *d_score = nullptr;
@@ -568,12 +612,14 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     TRY(cudaMallocAsync(&d_len, (size_t)n * 8, st));
     TRY(cudaMallocAsync(&d_status, (size_t)n * 4, st));
     TRY(cudaMallocAsync(&d_ready, 256, st));
+    TRY(cudaMallocAsync(&d_order, (size_t)n * 4, st));
     TRY(cudaMallocAsync(&d_seq, (size_t)(seq_bytes ? seq_bytes : 1), st));
     TRY(cudaMallocAsync(&d_score, (size_t)n * 16, st));
     if (out_counters) TRY(cudaMallocAsync(&d_cnt, (size_t)n * 32, st));
     TRY(cudaMemcpyAsync(d_fo, fo.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_so, so.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemsetAsync(d_ready, 0, 256, st));
+    TRY(cudaMemsetAsync(d_status, 0xff, (size_t)n * 4, st));  // -1 = not run (stalled-transfer guard)
     TRY(cudaEventRecord(ev, st));
     // the copies need the allocations and the cleared counters
     TRY(cudaStreamWaitEvent(cs[0], ev, 0));
@@ -588,25 +634,20 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     // Segments (the transfers up to and including a publishing one) alternate between two copy
     // streams, so that the fixed gap between stream-ordered copies of one stream is covered by
     // the other stream's transfer; stream s publishes into d_ready[s].
-    // pageable sources (and RADIAN_HOST_STAGE=1) go through the staging ring
-    bool staged = getenv("RADIAN_HOST_STAGE") != nullptr && getenv("RADIAN_HOST_STAGE")[0] != '0';
-    if (!staged && !(getenv("RADIAN_HOST_STAGE") != nullptr) && frames > 0) {
-        cudaPointerAttributes pa;
-        if (cudaPointerGetAttributes(&pa, post) != cudaSuccess) {
-            cudaGetLastError();
-            staged = true;
-        } else {
-            staged = pa.type == cudaMemoryTypeUnregistered;
-        }
-    }
     if (staged && ret == RADIAN_OK) {
         std::vector<int64_t> src_frame((size_t)n);
         for (int k = 0; k < n; ++k) src_frame[k] = frame_offsets[sel[q[k]]];
-        ret = staged_upload((const char *)post, row, src_frame, fo, (char *)d_post, d_ready, cs, ev_last, device);
+        ret = staged_upload((const char *)post, row, src_frame, fo, splan, (char *)d_post, d_ready, cs, ev_last, device);
     }
     int which = 0;
+    const char *stall_env = getenv("RADIAN_TEST_STALL_MS");  // test hook: hold the copies back midway
     for (size_t i = 0; i < plan.size() && ret == RADIAN_OK && !staged; ++i) {
         const Xfer &x = plan[i];
+        if (stall_env && i == plan.size() / 2) {
+            cudaStreamSynchronize(cs[0]);
+            cudaStreamSynchronize(cs[1]);
+            std::this_thread::sleep_for(std::chrono::milliseconds(atoi(stall_env)));
+        }
         if (x.n_frames > 0)
             TRY(cudaMemcpyAsync((char *)d_post + (size_t)x.dst_frame * row,
                                 (const char *)post + (size_t)x.src_frame * row, (size_t)x.n_frames * row,
@@ -638,6 +679,26 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
                                         d_status, d_cnt, arena_nodes, d_ws, ws_bytes, nullptr, st);
     }
     stamp(2);
+    if (launched) {
+        // Reads the kernel gave up on because the transfer stood still (status still -1): once the
+        // copies are through, a second launch decodes them from the resident data.
+        TRY(cudaMemcpyAsync(h_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        TRY(cudaStreamSynchronize(cs[0]));
+        TRY(cudaStreamSynchronize(cs[1]));
+        TRY(cudaStreamSynchronize(st));
+        std::vector<int32_t> redo;
+        for (int k = 0; k < n && ret == RADIAN_OK; ++k)
+            if (h_status[k] == -1) redo.push_back(k);
+        if (!redo.empty() && ret == RADIAN_OK) {
+            if (trace) fprintf(stderr, "[radian] host pass: transfer stalled, %zu reads decoded by a second launch\n", redo.size());
+            TRY(cudaMemcpyAsync(d_order, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
+            if (ret == RADIAN_OK)
+                ret = decode_batch_dev_impl(d_post, post_is_f64, d_fo, (int)redo.size(), d_order, max_frames,
+                                            beam_width, table, len_context, s_threshold, r_threshold, d_seq, d_so,
+                                            d_len, d_score, d_status, d_cnt, arena_nodes, d_ws, ws_bytes, nullptr, st);
+            TRY(cudaStreamSynchronize(st));  // redo must outlive the copy of the order array
+        }
+    }
     TRY(cudaMemcpyAsync(h_seq, d_seq, (size_t)seq_bytes, cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(h_len, d_len, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(h_score, d_score, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
@@ -649,7 +710,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     TRY(cudaStreamSynchronize(st));
     stamp(4);
 #undef TRY
-    void *frees[] = {d_post, d_ws, d_fo, d_so, d_len, d_status, d_ready, d_seq, d_score, d_cnt};
+    void *frees[] = {d_post, d_ws, d_fo, d_so, d_len, d_status, d_order, d_ready, d_seq, d_score, d_cnt};
     for (void *p : frees)
         if (p) cudaFreeAsync(p, st);
     cudaStreamSynchronize(st);
@@ -695,6 +756,7 @@ extern "C" int radian_decode_batch_host(const void *post, int post_is_f64, const
         set_error("radian_decode_batch_host: CUDA device %d not available (no CPU fallback exists)", device);
         return RADIAN_E_CUDA;
     }
+    std::lock_guard<std::mutex> host_lock(host_mutex(device));
     RADIAN_CUDA(cudaSetDevice(device));
     std::vector<int32_t> sel(n_reads);
     for (int i = 0; i < n_reads; ++i) {

@@ -279,6 +279,7 @@ extern "C" int radian_assemble_batch_host(const float *chunks, const int64_t *ch
         set_error("radian_assemble_batch_host: overlapping chunks need a float64 output (matrix_assembly.py:53)");
         return RADIAN_E_ARG;
     }
+    std::lock_guard<std::mutex> host_lock(host_mutex(device));
     RADIAN_CUDA(cudaSetDevice(device));
     {
         int krc = keep_pool(device);

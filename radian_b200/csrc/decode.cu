@@ -67,6 +67,8 @@ struct __align__(16) GroupSmem {
     uint8_t rnk[5 * G];               // rank of the candidate
     uint8_t newlist[G];               // candidate indices of the new beams, in list order
     uint8_t lanerank[G];              // previous rank of every lane
+    int wait_seen;                    // streamed batches: last value of the arrival counter seen while
+    unsigned wait_t0;                 // waiting, and when it was first seen (stalled-transfer guard)
 };
 
 // Control flow is warp-uniform everywhere: a warp carries 32/G reads, and every branch that
@@ -93,6 +95,7 @@ decode_kernel(const DecodeArgs a)
     GroupSmem<G, LM, PT> &sm = smem[gib];
     // shared-memory address of this lane's extension scores, pinned in a register (the compiler
     // would otherwise rebuild it from the lane and group indices every frame)
+    if (li == 0) sm.wait_seen = -2;
     unsigned ex_addr = (unsigned)__cvta_generic_to_shared(&sm.ex[li * 2]);
     asm volatile("" : "+r"(ex_addr));
     const int slot = blockIdx.x * (kWarpsPerBlock * GPW) + gib;
@@ -146,11 +149,28 @@ decode_kernel(const DecodeArgs a)
                     const unsigned long long v = *(const volatile unsigned long long *)a.ready;
                     const int r0 = (int)(unsigned)v, r1 = (int)(unsigned)(v >> 32);
                     landed = r0 < r1 ? r0 : r1;
+                    if (landed <= idx) {
+                        // Stalled-transfer guard: something on the host (another thread freeing
+                        // memory, say) can hold the copies back until this very kernel has ended.
+                        // If the counter stands still for half a second everybody stops waiting;
+                        // the reads not decoded keep their "not run" status and the host decodes
+                        // them with a second launch once the data is there.
+                        const unsigned now = timer_units();
+                        if (*(const volatile int *)(a.queue + 1) != 0) {
+                            landed = -1;
+                        } else if (landed != sm.wait_seen) {
+                            sm.wait_seen = landed;
+                            sm.wait_t0 = now;
+                        } else if (now - sm.wait_t0 > kStallUnits) {
+                            atomicExch(a.queue + 1, 1);
+                            landed = -1;
+                        }
+                    }
                 }
                 landed = __shfl_sync(kFull, landed, gshift);
             }
             if (want) {
-                if (idx >= a.n_reads) {
+                if (idx >= a.n_reads || landed < 0) {
                     active = false;
                     pend = -1;
                 } else if (landed <= idx) {

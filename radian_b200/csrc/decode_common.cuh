@@ -10,6 +10,15 @@ namespace radian {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint16_t kPosInvalid = 0xffff;
 constexpr int kNursery = 4096;  // arena nodes between two collections
+constexpr unsigned kStallUnits = 512;  // ~0.54 s in units of 2^20 ns: a streamed transfer that does not
+                                       // advance for this long is given up (see DecodeArgs::ready)
+
+__device__ __forceinline__ unsigned timer_units()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return (unsigned)(t >> 20);
+}
 
 // all-ones if bit 7 of byte `B` of x is set, else zero (prmt with the sign-replicate selector bit)
 template <int B>

@@ -83,10 +83,27 @@ decode_wide_kernel(const DecodeArgs a)
         if (lane == 0) {
             idx = atomicAdd(a.queue, 1);
             if (a.ready != nullptr && idx < a.n_reads) {
+                int seen = -2;
+                unsigned t0 = 0;
                 while (true) {
                     const unsigned long long v = *(const volatile unsigned long long *)a.ready;
                     const int r0 = (int)(unsigned)v, r1 = (int)(unsigned)(v >> 32);
-                    if ((r0 < r1 ? r0 : r1) > idx) break;
+                    const int landed = r0 < r1 ? r0 : r1;
+                    if (landed > idx) break;
+                    // stalled-transfer guard, see decode.cu
+                    const unsigned now = timer_units();
+                    if (*(const volatile int *)(a.queue + 1) != 0) {
+                        idx = 0x7fffffff;
+                        break;
+                    }
+                    if (landed != seen) {
+                        seen = landed;
+                        t0 = now;
+                    } else if (now - t0 > kStallUnits) {
+                        atomicExch(a.queue + 1, 1);
+                        idx = 0x7fffffff;
+                        break;
+                    }
                     __nanosleep(400);
                 }
                 __threadfence();

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "radian_b200.h"
 
 namespace radian {
@@ -22,6 +24,9 @@ struct DeviceInfo {
 };
 int device_info(int device, DeviceInfo *out);
 int keep_pool(int device);
+// One host entry point at a time per device: while a streamed decode kernel waits for its input,
+// no other thread of this library may allocate, free or launch on that device.
+std::mutex &host_mutex(int device);
 
 }  // namespace radian
 
@@ -59,7 +64,8 @@ struct DecodeArgs {
     unsigned long long *out_counters;
     uint32_t *arena;         // slots x (arena_cap + nursery) words: nodes, then forwarding scratch
     int arena_cap;
-    int *queue;              // work-queue head, zeroed before launch
+    int *queue;              // work-queue head, zeroed before launch; queue[1] = "transfer stalled, stop
+                             // waiting" flag of streamed batches
     const int *ready;        // optional, 2 ints (8-byte aligned): reads (in queue order) whose posteriors
                              // have landed in HBM, as published by each of the two copy streams of the
                              // _host entry point while the kernel runs; a read is usable once both

@@ -358,6 +358,7 @@ extern "C" int radian_normalise_batch_host(const int16_t *signal, const int64_t 
             return RADIAN_E_ARG;
         }
     const int64_t total = offsets[n_reads] - offsets[0];
+    std::lock_guard<std::mutex> host_lock(host_mutex(device));
     RADIAN_CUDA(cudaSetDevice(device));
     {
         int krc = keep_pool(device);
@@ -416,6 +417,7 @@ extern "C" int radian_windows_batch_host(const double *norm, const int64_t *offs
     }
     const int64_t total = offsets[n_reads] - offsets[0];
     const int64_t n_win = window_offsets[n_reads] - window_offsets[0];
+    std::lock_guard<std::mutex> host_lock(host_mutex(device));
     RADIAN_CUDA(cudaSetDevice(device));
     {
         int krc = keep_pool(device);

@@ -388,6 +388,7 @@ extern "C" int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *
         for (int r = 0; r < n_reads; ++r) out_len[r] = 0, out_status[r] = RADIAN_READ_OK;
         return RADIAN_OK;
     }
+    std::lock_guard<std::mutex> host_lock(host_mutex(device));
     RADIAN_CUDA(cudaSetDevice(device));
     {
         int krc = keep_pool(device);

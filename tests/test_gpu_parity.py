@@ -458,3 +458,21 @@ def test_host_entry_point_is_reentrant():
     with ThreadPoolExecutor(6) as ex:
         got = list(ex.map(lambda b: decode.beam_search_batch(b, 16, tab, 0.5, 0.5, 6), batches * 3))
     assert got == want * 3
+
+
+@pytest.mark.parametrize("bw", [16, 64])
+def test_stalled_transfer_is_survived(bw, monkeypatch):
+    """If the copies of a streamed call stand still (here: held back for 1.5 s by a test hook, in
+    real life e.g. by another thread's cudaFree waiting for the device), the kernel stops waiting
+    after half a second and the reads it did not get are decoded by a second launch: same
+    results, no hang."""
+    from radian_b200 import decode, synth
+
+    post, off = synth.make_reads(synth.read_lengths(40, 8, median=80, lo=5, hi=300), seed=44)
+    p, o = post.numpy(), off.numpy()
+    mats = [p[o[i]:o[i + 1]] for i in range(40)]
+    tab = decode.RnaTable(synth.make_table(5, 2))
+    want = decode.beam_search_batch(mats, bw, tab, 0.5, 0.5, 5, return_details=True)
+    monkeypatch.setenv("RADIAN_TEST_STALL_MS", "1500")
+    got = decode.beam_search_batch(mats, bw, tab, 0.5, 0.5, 5, return_details=True)
+    assert got[0] == want[0] and np.array_equal(got[1], want[1], equal_nan=True) and np.array_equal(got[2], want[2])
