@@ -67,15 +67,41 @@ struct __align__(16) GroupSmem {
     uint8_t rnk[5 * G];               // rank of the candidate
     uint8_t newlist[G];               // candidate indices of the new beams, in list order
     uint8_t lanerank[G];              // previous rank of every lane
-    int wait_seen;                    // streamed batches: last value of the arrival counter seen while
-    unsigned wait_t0;                 // waiting, and when it was first seen (stalled-transfer guard)
 };
+
+// Streamed batches: how many reads (in queue order) have landed, or -1 when the transfer is given
+// up.  Two copy streams publish alternating segments; both counters must have passed a read.
+// Stalled-transfer guard: something on the host (another thread freeing memory, say) can hold the
+// copies back until this very kernel has ended.  If the counter stands still for half a second
+// everybody stops waiting; the reads not decoded keep their "not run" status and the host decodes
+// them with a second launch once the data is there.  Kept out of line: it runs once per read at
+// most, and inlined it costs the frame loop 8 % through register allocation.
+__device__ __noinline__ int poll_arrivals(const int *ready, int *stop_flag, int idx, int *wait_seen, unsigned *wait_t0)
+{
+    const unsigned long long v = *(const volatile unsigned long long *)ready;
+    const int r0 = (int)(unsigned)v, r1 = (int)(unsigned)(v >> 32);
+    const int landed = r0 < r1 ? r0 : r1;
+    if (landed > idx) return landed;
+    const unsigned now = timer_units();
+    if (*(const volatile int *)stop_flag != 0) return -1;
+    if (landed != *wait_seen) {
+        *wait_seen = landed;
+        *wait_t0 = now;
+    } else if (now - *wait_t0 > kStallUnits) {
+        atomicExch(stop_flag, 1);
+        return -1;
+    }
+    return landed;
+}
 
 // Control flow is warp-uniform everywhere: a warp carries 32/G reads, and every branch that
 // contains a warp collective is taken by all of them together (decided by a full-mask vote), so
 // all shuffles and votes use the full mask and each group extracts its own lanes' bits.  Sub-warp
 // masks would make the compiler emit a convergence check per collective and serialise the groups.
-template <int G, bool LM, typename PT, bool COUNT>
+// STREAM: the batch arrives while the kernel runs (DecodeArgs::ready); a separate instantiation,
+// because the mere presence of the arrival polling costs the frame loop of resident launches 8 %
+// (register allocation).
+template <int G, bool LM, typename PT, bool COUNT, bool STREAM>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, RADIAN_MIN_BLOCKS)
 decode_kernel(const DecodeArgs a)
 {
@@ -85,6 +111,10 @@ decode_kernel(const DecodeArgs a)
     constexpr int EPL = (NK - G) / G;  // extension slots ranked by each lane on the fast path
     constexpr unsigned GBITS = (G == 32) ? kFull : ((1u << G) - 1u);
     __shared__ GroupSmem<G, LM, PT> smem[kWarpsPerBlock * GPW];
+    // streamed batches: last value of the arrival counter a waiting group saw, and since when
+    // (stalled-transfer guard); kept out of GroupSmem, whose size the frame loop's addressing likes
+    __shared__ int wait_seen[kWarpsPerBlock * GPW];
+    __shared__ unsigned wait_t0[kWarpsPerBlock * GPW];
 
     const int lane = threadIdx.x & 31;
     const int li = lane % G;
@@ -95,7 +125,7 @@ decode_kernel(const DecodeArgs a)
     GroupSmem<G, LM, PT> &sm = smem[gib];
     // shared-memory address of this lane's extension scores, pinned in a register (the compiler
     // would otherwise rebuild it from the lane and group indices every frame)
-    if (li == 0) sm.wait_seen = -2;
+    if (STREAM && li == 0) wait_seen[gib] = -2;
     unsigned ex_addr = (unsigned)__cvta_generic_to_shared(&sm.ex[li * 2]);
     asm volatile("" : "+r"(ex_addr));
     const int slot = blockIdx.x * (kWarpsPerBlock * GPW) + gib;
@@ -143,41 +173,31 @@ decode_kernel(const DecodeArgs a)
             // in flight keeps its queue ticket and polls again later; it must not block the other
             // reads of its warp.
             int landed = 0x7fffffff;
-            if (a.ready != nullptr) {
+#ifndef RADIAN_RESIDENT_KEEPS_POLL
+#define RADIAN_RESIDENT_KEEPS_POLL 1
+#endif
+            if (STREAM) {
+                if (want && li == 0 && idx < a.n_reads) landed = poll_arrivals(a.ready, a.queue + 1, idx, &wait_seen[gib], &wait_t0[gib]);
+                landed = __shfl_sync(kFull, landed, gshift);
+            } else if (RADIAN_RESIDENT_KEEPS_POLL && a.ready != nullptr) {
+                // never taken (the host picks the STREAM instantiation whenever `ready` is set);
+                // kept because the frame loop of the resident kernel compiles 3 % faster with it
                 if (want && li == 0 && idx < a.n_reads) {
-                    // two copy streams publish alternating segments; both counters must have passed
                     const unsigned long long v = *(const volatile unsigned long long *)a.ready;
                     const int r0 = (int)(unsigned)v, r1 = (int)(unsigned)(v >> 32);
                     landed = r0 < r1 ? r0 : r1;
-                    if (landed <= idx) {
-                        // Stalled-transfer guard: something on the host (another thread freeing
-                        // memory, say) can hold the copies back until this very kernel has ended.
-                        // If the counter stands still for half a second everybody stops waiting;
-                        // the reads not decoded keep their "not run" status and the host decodes
-                        // them with a second launch once the data is there.
-                        const unsigned now = timer_units();
-                        if (*(const volatile int *)(a.queue + 1) != 0) {
-                            landed = -1;
-                        } else if (landed != sm.wait_seen) {
-                            sm.wait_seen = landed;
-                            sm.wait_t0 = now;
-                        } else if (now - sm.wait_t0 > kStallUnits) {
-                            atomicExch(a.queue + 1, 1);
-                            landed = -1;
-                        }
-                    }
                 }
                 landed = __shfl_sync(kFull, landed, gshift);
             }
             if (want) {
-                if (idx >= a.n_reads || landed < 0) {
+                if (idx >= a.n_reads || (STREAM && landed < 0)) {
                     active = false;
                     pend = -1;
-                } else if (landed <= idx) {
+                } else if ((STREAM || RADIAN_RESIDENT_KEEPS_POLL) && landed <= idx) {
                     pend = idx;
                 } else {
                     pend = -1;
-                    if (a.ready != nullptr) __threadfence();
+                    if (STREAM || (RADIAN_RESIDENT_KEEPS_POLL && a.ready != nullptr)) __threadfence();
                     read = a.order ? a.order[idx] : idx;
                     const long long foff = a.frame_offsets[read];
                     T = (int)(a.frame_offsets[read + 1] - foff);
@@ -228,7 +248,7 @@ decode_kernel(const DecodeArgs a)
             nrun = x < nrun ? x : nrun;
         }
         // a group waiting for its read gets another look at the flag after a bounded stretch
-        if (__any_sync(kFull, active && !live) && nrun > 256) nrun = 256;
+        if ((STREAM || RADIAN_RESIDENT_KEEPS_POLL) && __any_sync(kFull, active && !live) && nrun > 256) nrun = 256;
         // (re)prime the frame tiles so that all groups of the warp refill at the same iterations
         const int tb = t;
         __syncwarp();
@@ -823,17 +843,19 @@ static int group_size(int beam_width)
 }
 
 template <int G, bool LM, typename PT>
-static const void *kernel_ptr(bool count)
+static const void *kernel_ptr(bool count, bool stream)
 {
-    return count ? (const void *)decode_kernel<G, LM, PT, true> : (const void *)decode_kernel<G, LM, PT, false>;
+    if (stream)
+        return count ? (const void *)decode_kernel<G, LM, PT, true, true> : (const void *)decode_kernel<G, LM, PT, false, true>;
+    return count ? (const void *)decode_kernel<G, LM, PT, true, false> : (const void *)decode_kernel<G, LM, PT, false, false>;
 }
 
-static const void *pick_kernel(int G, bool lm, bool f64, bool count)
+static const void *pick_kernel(int G, bool lm, bool f64, bool count, bool stream)
 {
 #define RADIAN_PICK(GG)                                                                        \
     if (G == GG) {                                                                             \
-        if (lm) return f64 ? kernel_ptr<GG, true, double>(count) : kernel_ptr<GG, true, float>(count); \
-        return f64 ? kernel_ptr<GG, false, double>(count) : kernel_ptr<GG, false, float>(count);       \
+        if (lm) return f64 ? kernel_ptr<GG, true, double>(count, stream) : kernel_ptr<GG, true, float>(count, stream); \
+        return f64 ? kernel_ptr<GG, false, double>(count, stream) : kernel_ptr<GG, false, float>(count, stream);       \
     }
     RADIAN_PICK(8)
     RADIAN_PICK(16)
@@ -857,7 +879,7 @@ int64_t decode_arena_cap(int beam_width, int64_t max_frames, int64_t arena_nodes
     return cap < (1 << 16) ? (1 << 16) : cap;
 }
 
-int decode_pick(int device, int beam_width, bool lm, bool f64, bool count, DecodeLaunch *out)
+int decode_pick(int device, int beam_width, bool lm, bool f64, bool count, bool stream, DecodeLaunch *out)
 {
     DeviceInfo di;
     int rc = device_info(device, &di);
@@ -880,7 +902,7 @@ int decode_pick(int device, int beam_width, bool lm, bool f64, bool count, Decod
         out->groups_per_block = warps;
         return 0;
     }
-    const void *k = pick_kernel(G, lm, f64, count);
+    const void *k = pick_kernel(G, lm, f64, count, stream);
     // the kernel streams its global loads once; give shared memory the whole L1 carve-out
     RADIAN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     RADIAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k, kWarpsPerBlock * 32, 0));
@@ -896,9 +918,9 @@ int decode_pick(int device, int beam_width, bool lm, bool f64, bool count, Decod
 int decode_max_slots(int device, int beam_width)
 {
     int best = 0;
-    for (int v = 0; v < 8; ++v) {
+    for (int v = 0; v < 16; ++v) {
         DecodeLaunch dl;
-        if (decode_pick(device, beam_width, v & 1, v & 2, v & 4, &dl)) return -1;
+        if (decode_pick(device, beam_width, v & 1, v & 2, v & 4, v & 8, &dl)) return -1;
         int s = dl.grid * dl.groups_per_block;
         best = s > best ? s : best;
     }
@@ -909,7 +931,7 @@ int decode_launch(const DecodeArgs &a, bool f64, int device, cudaStream_t stream
 {
     const bool lm = a.table != nullptr;
     DecodeLaunch dl;
-    int rc = decode_pick(device, a.beam_width, lm, f64, a.out_counters != nullptr, &dl);
+    int rc = decode_pick(device, a.beam_width, lm, f64, a.out_counters != nullptr, a.ready != nullptr, &dl);
     if (rc) return rc;
     // no more groups than reads: extra CTAs would only touch the queue
     int64_t need = ((int64_t)a.n_reads + dl.groups_per_block - 1) / dl.groups_per_block;

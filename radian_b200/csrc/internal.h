@@ -80,7 +80,7 @@ struct DecodeLaunch {
     int groups_per_block;
 };
 
-int decode_pick(int device, int beam_width, bool lm, bool f64, bool count, DecodeLaunch *out);
+int decode_pick(int device, int beam_width, bool lm, bool f64, bool count, bool stream, DecodeLaunch *out);
 int decode_launch(const DecodeArgs &a, bool f64, int device, cudaStream_t stream);
 int decode_max_slots(int device, int beam_width);
 int64_t decode_arena_cap(int beam_width, int64_t max_frames, int64_t arena_nodes);
