@@ -139,3 +139,46 @@ def test_fast5_reader_on_the_reference_file():
         assert np.array_equal(sig, c["signal"])
     with pytest.raises(fast5.Fast5Error):
         list(fast5.reads(os.path.join(golden_io.GOLDEN, "assembly.npz")))
+
+
+def test_windows_plan_matches_reference_counts():
+    """radian_windows_plan (host only): window counts and pad_end of preprocess.get_windows
+    (preprocess.py:9-20) as recorded from the reference, and its two ValueErrors."""
+    from radian_b200 import _native
+
+    lib = _native.lib
+    for c in golden_io.preprocess_cases():
+        n = len(c["signal"])
+        for W, S, nw, pad, _, _ in c["windows"]:
+            off = np.array([0, n], np.int64)
+            cnt = np.zeros(1, np.int64)
+            p = np.zeros(1, np.int32)
+            _native.check(lib.radian_windows_plan(_native.np_ptr(off), 1, int(W), int(S), _native.np_ptr(cnt),
+                                                  _native.np_ptr(p)))
+            assert (int(cnt[0]), int(p[0])) == (int(nw), int(pad))
+    off = np.array([0, 10], np.int64)
+    cnt = np.zeros(1, np.int64)
+    p = np.zeros(1, np.int32)
+    with pytest.raises(ValueError, match="Step size must be > 0"):
+        _native.check(lib.radian_windows_plan(_native.np_ptr(off), 1, 4, 0, _native.np_ptr(cnt), _native.np_ptr(p)))
+    with pytest.raises(ValueError, match="<= window size"):
+        _native.check(lib.radian_windows_plan(_native.np_ptr(off), 1, 4, 5, _native.np_ptr(cnt), _native.np_ptr(p)))
+
+
+def test_new_entry_points_fail_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from radian_b200 import _native, preprocess, sequence_assembly
+
+    with pytest.raises(_native.RadianError, match="no CPU fallback"):
+        preprocess.mad_normalise(np.arange(10, dtype=np.int16), 4)
+    with pytest.raises(_native.RadianError, match="no CPU fallback"):
+        preprocess.get_windows(np.zeros(10), 4, 2)
+    with pytest.raises(_native.RadianError, match="no CPU fallback"):
+        sequence_assembly.simple_assembly(["ACGT", "CGTA"])
+    with pytest.raises(TypeError):
+        preprocess.mad_normalise(np.arange(10, dtype=np.float32), 4)
+    with pytest.raises(KeyError):
+        sequence_assembly.simple_assembly(["ACGT", "ACNT"])
