@@ -422,3 +422,24 @@ def write_preprocess_golden(seed=17):
                         result_is_int=np.array(res_int), error=np.array(err), windows=np.array(win))
     print("preprocess.npz:", len(cases), "cases,", sum(e != 0 for e in err), "raising,", sum(res_int), "int64 results,",
           len(win), "window checks")
+
+
+def write_decode_wide(seed=404):
+    """Reference fixtures for the wide kernel (beam widths above 32): bench-style posteriors of
+    short reads, model on and off, float32 and float64.  Run on its own:
+        python -c "from oracle import make_golden as m; m.write_decode_wide()" """
+    rng = np.random.default_rng(seed)
+    cases = []
+    for bw in (33, 48, 64, 65, 100, 128):
+        for L in (0, 3, 5):
+            nb = int(rng.integers(2, 6))
+            post, _ = synth.make_reads(np.array([nb]), seed=int(rng.integers(1 << 30)))
+            mat = post.numpy()
+            if rng.random() < 0.5:
+                mat = mat.astype(np.float64)
+            cases.append((mat, bw, L, int(rng.integers(0, 1 << 30)) if L else 0, 0.5 if L else None,
+                          0.5 if L else None))
+    with Pool(os.cpu_count()) as pool:
+        res = pool.map(run_case, cases, chunksize=1)
+    np.savez_compressed(os.path.join(GOLDEN, "decode_wide.npz"), **pack_cases(cases, res))
+    print("decode_wide.npz:", len(cases), "cases, ref cpu %.1fs" % sum(r[4] for r in res))

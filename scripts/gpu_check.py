@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import golden_io  # noqa: E402
 from radian_b200 import decode  # noqa: E402
 
-files = ["decode_kat.npz", "decode_random.npz", "decode_synth.npz", "decode_long.npz"]
+files = ["decode_kat.npz", "decode_random.npz", "decode_synth.npz", "decode_long.npz", "decode_wide.npz"]
 cases = [c for f in files for c in golden_io.decode_cases(f)]
 bad = 0
 tabs = {}

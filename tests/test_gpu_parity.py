@@ -11,7 +11,7 @@ import golden_io
 pytestmark = pytest.mark.gpu
 
 SCORE_RTOL = 1e-9
-FILES = ["decode_kat.npz", "decode_random.npz", "decode_synth.npz", "decode_long.npz"]
+FILES = ["decode_kat.npz", "decode_random.npz", "decode_synth.npz", "decode_long.npz", "decode_wide.npz"]
 CASES = [c for f in FILES for c in golden_io.decode_cases(f)]
 
 
