@@ -109,15 +109,30 @@ def _resolve_table(lm, len_context, device):
         raise TypeError("string indices must be integers, not 'tuple'")
     key = (id(lm), int(len_context), int(device))
     with _table_lock:
-        t = _table_cache.get(key)
-        if t is None:
-            t = RnaTable.from_dict(lm, len_context, device)
-            _table_cache[key] = t
-            try:
-                weakref.finalize(lm, _table_cache.pop, key, None)
-            except TypeError:
-                pass  # plain dicts cannot be weak-referenced: the entry lives as long as the process
+        hit = _table_cache.get(key)
+        # id() of a dead dict can be reused by a new one: a hit also has to look like the same table
+        mark = _fingerprint(lm, int(len_context))
+        if hit is not None and hit[1] == mark:
+            return hit[0]
+        t = RnaTable.from_dict(lm, len_context, device)
+        _table_cache[key] = (t, mark)
+        try:
+            weakref.finalize(lm, _table_cache.pop, key, None)
+        except TypeError:
+            pass  # plain dicts cannot be weak-referenced: the entry lives until the id is reused
         return t
+
+
+def _fingerprint(lm, L):
+    """Size plus the rows of a few fixed contexts: cheap, and enough to tell two model dicts apart."""
+    n = 4 ** L
+    picks = sorted({0, n - 1, n // 2, n // 3, (n * 2) // 3, n // 7, (n * 5) // 7, 1 % n})
+    rows = []
+    for i in picks:
+        ctx = tuple((i >> (2 * (L - 1 - j))) & 3 for j in range(L))
+        row = lm.get(ctx) if hasattr(lm, "get") else None
+        rows.append(None if row is None else tuple(float(x) for x in row))
+    return (len(lm), tuple(rows))
 
 
 def _current_device() -> int:
@@ -206,6 +221,7 @@ class DeviceDecodeResult:
     scores: "object"       # float64 CUDA tensor (n, 2)
     status: "object"       # int32 CUDA tensor (n)
     counters: "object"     # uint64-as-int64 CUDA tensor (n, 4) or None
+    table: "object" = None  # keeps the RnaTable alive while the launch that uses it is in flight
 
     def strings(self, bases="ACGT"):
         seq = self.seq.cpu().numpy()
@@ -267,4 +283,5 @@ def decode_batch_device(post, frame_offsets, beam_width, table=None, s_threshold
         out.counters.data_ptr() if out.counters is not None else None, int(arena_nodes),
         ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream))
     _native.check(rc)
+    out.table = table
     return out
