@@ -70,6 +70,9 @@ typedef void *radian_stream_t; /* cudaStream_t */
 const char *radian_last_error(void);
 const char *radian_version(void);
 int radian_device_count(void);
+/* The _host entry points keep their device buffers in the device's stream-ordered memory pool
+ * between calls; this synchronises the device and returns them to the driver. */
+int radian_trim_memory(int device);
 
 /*
  * Dense RNA k-mer table.  probs: host array of 4^L rows x 4 float64 linear probabilities,

@@ -16,7 +16,7 @@ MAX_BEAM_WIDTH = 128
 MAX_CONTEXT = 13
 
 EXPORTS = [
-    "radian_last_error", "radian_version", "radian_device_count",
+    "radian_last_error", "radian_version", "radian_device_count", "radian_trim_memory",
     "radian_table_create", "radian_table_destroy", "radian_table_context_len", "radian_table_entropies",
     "radian_decode_workspace_bytes", "radian_decode_batch_dev", "radian_decode_batch_host",
     "radian_assemble_plan", "radian_assemble_batch_dev", "radian_assemble_batch_host",
@@ -38,6 +38,8 @@ def _load():
     lib.radian_last_error.restype = c_char_p
     lib.radian_version.restype = c_char_p
     lib.radian_device_count.restype = c_int
+    lib.radian_trim_memory.restype = c_int
+    lib.radian_trim_memory.argtypes = [c_int]
     lib.radian_table_create.restype = c_int
     lib.radian_table_create.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p)]
     lib.radian_table_destroy.restype = c_int

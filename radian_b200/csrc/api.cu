@@ -107,6 +107,23 @@ using namespace radian;
 extern "C" const char *radian_last_error(void) { return g_err; }
 extern "C" const char *radian_version(void) { return "radian_b200 0.1 (sm_100a)"; }
 
+// The _host entry points keep their device buffers in the stream-ordered pool between calls
+// (keep_pool); this hands them back to the driver.
+extern "C" int radian_trim_memory(int device)
+{
+    if (radian_device_count() <= device || device < 0) {
+        set_error("radian_trim_memory: CUDA device %d not available", device);
+        return RADIAN_E_CUDA;
+    }
+    std::lock_guard<std::mutex> host_lock(host_mutex(device));
+    RADIAN_CUDA(cudaSetDevice(device));
+    RADIAN_CUDA(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    RADIAN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    RADIAN_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return RADIAN_OK;
+}
+
 extern "C" int radian_device_count(void)
 {
     int n = 0;

@@ -146,6 +146,11 @@ def _current_device() -> int:
     return 0
 
 
+def trim_memory(device=None):
+    """Return the device buffers the host entry points keep between calls to the driver."""
+    _native.check(lib.radian_trim_memory(_current_device() if device is None else int(device)))
+
+
 def beam_search_batch(mats, beam_width, lm=None, s_threshold=None, r_threshold=None, len_context=None,
                       bases="ACGT", device=None, return_details=False, return_symbols=False):
     """Decode a list of (T_i, 5) posterior matrices (all float32 or all float64) in one launch.

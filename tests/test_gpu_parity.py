@@ -458,6 +458,8 @@ def test_host_entry_point_is_reentrant():
     with ThreadPoolExecutor(6) as ex:
         got = list(ex.map(lambda b: decode.beam_search_batch(b, 16, tab, 0.5, 0.5, 6), batches * 3))
     assert got == want * 3
+    decode.trim_memory()  # hands the pooled device buffers back; the next call allocates afresh
+    assert decode.beam_search_batch(batches[0], 16, tab, 0.5, 0.5, 6) == want[0]
 
 
 @pytest.mark.parametrize("bw", [16, 64])
