@@ -61,6 +61,11 @@ extern "C" {
 #define RADIAN_READ_MAD_ZERO 5       /* preprocessing: ValueError("MAD is zero, issue with signal."),
                                        preprocess.py:47-48 */
 
+#define RADIAN_READ_RANGE 6          /* decode: two kept beams further apart than the float64 exponent range
+                                       lets the kernel's rescaled linear-domain scores express (the
+                                       reference's log-domain scores, decode.py:172-175, have no such
+                                       limit); never happens for posteriors above ~1e-150 */
+
 #define RADIAN_MAX_BEAM_WIDTH 128
 #define RADIAN_MAX_CONTEXT 13
 

@@ -443,3 +443,54 @@ def write_decode_wide(seed=404):
         res = pool.map(run_case, cases, chunksize=1)
     np.savez_compressed(os.path.join(GOLDEN, "decode_wide.npz"), **pack_cases(cases, res))
     print("decode_wide.npz:", len(cases), "cases, ref cpu %.1fs" % sum(r[4] for r in res))
+
+
+def write_decode_headline(seed=1212):
+    """Reference fixtures on BASELINE.json's own configurations (they all use the 12-symbol
+    context of the headline metric, which the older fixtures stop short of):
+      C3  RNA-LM global decode, bw 16, L 12, thresholds 0.5/0.5, float32 posteriors as the bench
+          feeds them, plus two float64 (assembled-matrix style) reads;
+      C4  chunk-len 1024 / step-size 128, bw 16: (i) every window matrix decoded with the model off
+          (basecall.py:110-120) and (ii) the reference's own assemble_matrices output decoded with
+          the model on (basecall.py:99-109);
+      C5  corners of the sweep that the reference can do in minutes: bw 6 and 64, L 6 and 12.
+    Run on its own (8 processes, a few CPU-minutes; the L=12 table is 512 MB per process):
+        python -c "from oracle import make_golden as m; m.write_decode_headline()" """
+    _, ma, _ = ref_loader.load()
+    rng = np.random.default_rng(seed)
+    cases = []
+    # C3
+    nb = np.array([30, 55, 80, 100])
+    post, off = synth.make_reads(nb, seed=int(rng.integers(1 << 30)))
+    post, off = post.numpy(), off.numpy()
+    for i in range(len(nb)):
+        cases.append((post[off[i]:off[i + 1]].copy(), 16, 12, 5, 0.5, 0.5))
+    for i in (0, 2):
+        m64 = post[off[i]:off[i + 1]].astype(np.float64)
+        cases.append((m64 / np.abs(m64).sum(1, keepdims=True), 16, 12, 5, 0.5, 0.5))
+    # C4: one read of ~70 bases -> windows of 1024 frames every 128
+    p4, _ = synth.make_reads(np.array([70]), seed=int(rng.integers(1 << 30)))
+    mats = synth.split_windows(p4.numpy(), 1024, 128)
+    for m in mats:
+        if len(m):
+            cases.append((np.ascontiguousarray(m), 16, 0, 0, None, None))
+    glob = np.asarray(ma.assemble_matrices([m for m in mats], 128))
+    assert glob.dtype == np.float64
+    cases.append((glob, 16, 12, 5, 0.5, 0.5))
+    # C5 corners
+    p5, o5 = synth.make_reads(np.array([500, 500, 100, 100]), seed=int(rng.integers(1 << 30)))
+    p5, o5 = p5.numpy(), o5.numpy()
+    cases.append((p5[o5[0]:o5[1]].copy(), 6, 6, 5, 0.5, 0.5))
+    cases.append((p5[o5[1]:o5[2]].copy(), 6, 12, 5, 0.5, 0.5))
+    cases.append((p5[o5[2]:o5[3]].copy(), 64, 6, 5, 0.5, 0.5))
+    cases.append((p5[o5[3]:o5[4]].copy(), 64, 12, 5, 0.5, 0.5))
+    t0 = time.time()
+    # longest first so that the pool stays balanced
+    order = sorted(range(len(cases)), key=lambda i: -cases[i][0].shape[0] * cases[i][1])
+    with Pool(min(8, os.cpu_count())) as pool:
+        res_o = pool.map(run_case, [cases[i] for i in order], chunksize=1)
+    res = [None] * len(cases)
+    for i, r in zip(order, res_o):
+        res[i] = r
+    np.savez_compressed(os.path.join(GOLDEN, "decode_headline.npz"), **pack_cases(cases, res))
+    print("decode_headline.npz:", len(cases), "cases, %.1fs wall, ref cpu %.1fs" % (time.time() - t0, sum(r[4] for r in res)))

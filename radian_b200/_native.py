@@ -12,6 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_
 from . import build as _build
 
 OK, E_ARG, E_CUDA, E_CONTEXT, E_READ, E_GAP = 0, -1, -2, -3, -4, -5
+READ_RANGE = 6  # RADIAN_READ_RANGE
 MAX_BEAM_WIDTH = 128
 MAX_CONTEXT = 13
 

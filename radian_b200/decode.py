@@ -169,7 +169,10 @@ def beam_search_batch(mats, beam_width, lm=None, s_threshold=None, r_threshold=N
         if return_symbols:
             return np.zeros(0, np.uint8), np.zeros(1, np.int64)
         return ([], np.zeros((0, 2)), np.zeros((0, 4), np.uint64)) if return_details else []
-    dt = np.float64 if any(np.asarray(m).dtype == np.float64 for m in mats) else np.float32
+    # The reference decodes every matrix in its own dtype (float32 window / single-chunk matrices,
+    # float64 assembled ones: matrix_assembly.py:36-53), and the float32 path differs in the S, p/S
+    # and entropy arithmetic (decode.py:54-55, 67-76 under numpy promotion): a mixed batch is
+    # therefore split by dtype, one launch each, and scattered back in the caller's order.
     arrs = []
     for m in mats:
         m = np.asarray(m)
@@ -178,7 +181,37 @@ def beam_search_batch(mats, beam_width, lm=None, s_threshold=None, r_threshold=N
                 m = m.reshape(0, N_BASES + 1)
             else:
                 raise ValueError(f"posterior matrix must be (T, 5), got {m.shape}")
-        arrs.append(np.ascontiguousarray(m, dtype=dt))
+        if m.dtype != np.float64:
+            m = m.astype(np.float32, copy=False)
+        arrs.append(np.ascontiguousarray(m))
+    is64 = np.array([a.dtype == np.float64 for a in arrs])
+    seqs = [None] * n
+    score = np.zeros((n, 2), dtype=np.float64)
+    cnt = np.zeros((n, 4), dtype=np.uint64) if return_details else None
+    for want64 in (False, True):
+        idx = np.flatnonzero(is64 == want64)
+        if len(idx) == 0:
+            continue
+        sub, sc, c = _decode_host([arrs[i] for i in idx], np.float64 if want64 else np.float32, beam_width, table,
+                                  s_threshold, r_threshold, len_context, device, return_details)
+        for k, i in enumerate(idx):
+            seqs[i] = sub[k]
+        score[idx] = sc
+        if cnt is not None:
+            cnt[idx] = c
+    if return_symbols:
+        # compact symbols 0..3 of all reads back to back + offsets: what stitch_flat takes
+        off = np.zeros(n + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(q) for q in seqs])
+        return (np.concatenate(seqs) if n else np.zeros(0, np.uint8)), off
+    lut = np.frombuffer(bases.encode("ascii"), dtype=np.uint8)
+    out = [lut[q].tobytes().decode("ascii") for q in seqs]
+    return (out, score, cnt) if return_details else out
+
+
+def _decode_host(arrs, dt, beam_width, table, s_threshold, r_threshold, len_context, device, want_counters):
+    """One radian_decode_batch_host call on same-dtype matrices -> (symbol arrays, scores, counters)."""
+    n = len(arrs)
     fo = np.zeros(n + 1, dtype=np.int64)
     fo[1:] = np.cumsum([a.shape[0] for a in arrs])
     post = np.concatenate(arrs) if fo[-1] else np.zeros((0, 5), dt)
@@ -188,23 +221,20 @@ def beam_search_batch(mats, beam_width, lm=None, s_threshold=None, r_threshold=N
     ln = np.zeros(n, dtype=np.int64)
     score = np.zeros((n, 2), dtype=np.float64)
     status = np.zeros(n, dtype=np.int32)
-    cnt = np.zeros((n, 4), dtype=np.uint64) if return_details else None
+    cnt = np.zeros((n, 4), dtype=np.uint64) if want_counters else None
     rc = lib.radian_decode_batch_host(
         _native.np_ptr(post), int(dt == np.float64), _native.np_ptr(fo), n, int(beam_width),
         table._h if table else None, int(len_context) if table else 0,
         float(s_threshold) if table else 0.0, float(r_threshold) if table else 0.0,
         _native.np_ptr(seq), _native.np_ptr(so), _native.np_ptr(ln), _native.np_ptr(score),
         _native.np_ptr(status), _native.np_ptr(cnt), device)
+    if rc == _native.E_READ and (status == _native.READ_RANGE).any():
+        bad = int(np.flatnonzero(status == _native.READ_RANGE)[0])
+        raise FloatingPointError(
+            f"read {bad}: beam scores spread over more than the float64 exponent range "
+            "(the reference's log-domain scores have no such limit, decode.py:172-175); see INTEGRATION.md")
     _native.check(rc)
-    if return_symbols:
-        # compact symbols 0..3 of all reads back to back + offsets: what stitch_flat takes
-        off = np.zeros(n + 1, dtype=np.int64)
-        off[1:] = np.cumsum(ln)
-        idx = np.repeat(so[:-1] - off[:-1], ln) + np.arange(int(off[-1]), dtype=np.int64)
-        return seq[idx], off
-    lut = np.frombuffer(bases.encode("ascii"), dtype=np.uint8)
-    out = [lut[seq[so[i]:so[i] + ln[i]]].tobytes().decode("ascii") for i in range(n)]
-    return (out, score, cnt) if return_details else out
+    return [seq[so[i]:so[i] + ln[i]] for i in range(n)], score, cnt
 
 
 def beam_search(mat, bases, beam_width, lm, s_threshold, r_threshold, len_context, entr_cache):

@@ -5,7 +5,8 @@ import pytest
 import golden_io
 from oracle import oracle
 
-FILES = ["decode_kat.npz", "decode_random.npz", "decode_synth.npz", "decode_long.npz", "decode_wide.npz"]
+FILES = ["decode_kat.npz", "decode_random.npz", "decode_synth.npz", "decode_long.npz", "decode_wide.npz",
+         "decode_headline.npz"]
 CASES = [c for f in FILES for c in golden_io.decode_cases(f)]
 
 
