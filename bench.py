@@ -254,6 +254,10 @@ def main():
         raise SystemExit(f"bench.py: {int((status != 0).sum())} reads failed, status codes {np.unique(status)}")
     n_lookup = int(res.counters[:, 0].sum().item())
     n_combine = int(res.counters[:, 1].sum().item())
+    if os.environ.get("RADIAN_STAGE_STATS"):  # library built with -DRADIAN_STAGE_STATS
+        c3 = res.counters[:, 3]
+        print(json.dumps({"stage2_frames": int((c3 >> 32).sum().item()), "slow_frames": int((c3 & 0xffffffff).sum().item()),
+                          "frames": int(post.shape[0])}), file=sys.stderr)
     bases = int(res.lengths.sum().item())
     out = decode.decode_batch_device(post, fo, a.beam_width, table, 0.5, 0.5, max_frames=max_frames, order=order,
                                      seq_offsets=seq_offsets)

@@ -66,6 +66,10 @@ extern "C" {
                                        reference's log-domain scores, decode.py:172-175, have no such
                                        limit); never happens for posteriors above ~1e-150 */
 
+#define RADIAN_READ_KEY_ERROR 7      /* decode: a kept beam reached a context that the model does not hold
+                                       (KeyError at lm[context], decode.py:83); out_len holds the index of
+                                       that context.  Only tables made by radian_table_create_sparse. */
+
 #define RADIAN_MAX_BEAM_WIDTH 128
 #define RADIAN_MAX_CONTEXT 13
 
@@ -75,8 +79,8 @@ typedef void *radian_stream_t; /* cudaStream_t */
 const char *radian_last_error(void);
 const char *radian_version(void);
 int radian_device_count(void);
-/* The _host entry points keep their device buffers in the device's stream-ordered memory pool
- * between calls; this synchronises the device and returns them to the driver. */
+/* The _host entry points keep their device buffers between calls in a stream-ordered memory pool
+ * that belongs to this library (never the device's default pool); this returns them to the driver. */
 int radian_trim_memory(int device);
 
 /*
@@ -87,6 +91,11 @@ int radian_trim_memory(int device);
  * operation order, and uploaded with the rows; the table stays resident in HBM.
  */
 int radian_table_create(const double *probs, int L, int device, radian_table_t **out);
+/* The same for a model that does not hold every context (the reference's dict may be sparse: it fails
+ * with KeyError only when the search reaches a missing context, decode.py:83).  present: 4^L bytes,
+ * 0 = context absent (its row in probs is ignored); NULL = all present. */
+int radian_table_create_sparse(const double *probs, const uint8_t *present, int L, int device,
+                               radian_table_t **out);
 int radian_table_destroy(radian_table_t *t);
 int radian_table_context_len(const radian_table_t *t);
 /* copies the 4^L float64 row entropies back to the host (tests) */
@@ -117,6 +126,10 @@ int radian_table_entropies(const radian_table_t *t, double *out_host);
  *                a tie of the final beams, equal out_score entries), and a reserved zero.
  */
 /*
+ *  max_frames    frames of the longest read; total_frames: frames of all reads (= frame_offsets[n_reads],
+ *                which lives in device memory), or 0 if the caller does not know it.  Both only shape
+ *                the launch: a batch that does not fill the GPU several times over runs with fewer
+ *                resident warps per SM, which finishes its longest read sooner.
  *  arena_nodes   capacity of the per-read back-pointer arena; 0 picks a default from max_frames
  *                (exact worst case for small problems, else beam lanes x max_frames/16).  A read
  *                that needs more gets RADIAN_READ_TRIE_OVERFLOW; lanes x (T+1) always suffices.
@@ -126,7 +139,8 @@ size_t radian_decode_workspace_bytes(int device, int beam_width, int n_reads, in
                                      int64_t arena_nodes);
 
 int radian_decode_batch_dev(const void *post, int post_is_f64, const int64_t *frame_offsets,
-                            int n_reads, const int32_t *order, int64_t max_frames, int beam_width,
+                            int n_reads, const int32_t *order, int64_t max_frames,
+                            int64_t total_frames, int beam_width,
                             const radian_table_t *table, int len_context, double s_threshold,
                             double r_threshold, uint8_t *out_seq, const int64_t *seq_offsets,
                             int64_t *out_len, double *out_score, int32_t *out_status,

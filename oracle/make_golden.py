@@ -494,3 +494,39 @@ def write_decode_headline(seed=1212):
         res[i] = r
     np.savez_compressed(os.path.join(GOLDEN, "decode_headline.npz"), **pack_cases(cases, res))
     print("decode_headline.npz:", len(cases), "cases, %.1fs wall, ref cpu %.1fs" % (time.time() - t0, sum(r[4] for r in res)))
+
+
+def write_decode_sparse(seed=77):
+    """Reference behaviour with a model that lacks contexts (a plain dict without some keys): the
+    search raises KeyError at lm[context] (decode.py:83) as soon as a kept labeling reaches a missing
+    context, and is unaffected otherwise.  -> tests/golden/decode_sparse.npz
+        python -c "from oracle import make_golden as m; m.write_decode_sparse()" """
+    dec, _, _ = ref_loader.load()
+    rng = np.random.default_rng(seed)
+    mats, meta, seqs, masks = [], [], [], []
+    for i in range(40):
+        T = int(rng.integers(3, 120))
+        L = int(rng.integers(1, 4))
+        bw = int(rng.choice([1, 3, 6, 16, 40]))
+        tseed = int(rng.integers(1 << 20))
+        frac = float(rng.choice([0.02, 0.1, 0.3, 0.9]))
+        mat = random_posteriors(rng, T, True, 0.0, np.float32 if i % 2 else np.float64)
+        if i % 5 == 0:  # strongly peaked on two symbols: few contexts are ever reached
+            mat[:, 2:4] *= 1e-6
+        tab = synth.make_table(L, tseed)
+        present = rng.random(4 ** L) >= frac
+        lm = {}
+        for idx in np.flatnonzero(present):
+            lm[tuple((int(idx) >> (2 * (L - 1 - j))) & 3 for j in range(L))] = [float(x) for x in tab[idx]]
+        try:
+            seq = dec.beam_search(mat, "ACGT", bw, lm, 0.5, 0.5, L, {})
+            err = 0
+        except KeyError:
+            seq, err = "", 1
+        mats.append(mat.astype(np.float64))
+        meta.append([T, L, bw, tseed, err, len(seq), int(mat.dtype == np.float64)])
+        seqs.append(seq_to_u8(seq))
+        masks.append(present)
+    np.savez_compressed(os.path.join(GOLDEN, "decode_sparse.npz"), post=np.concatenate(mats), meta=np.array(meta, dtype=np.int64),
+                        seq=np.concatenate(seqs), present=np.concatenate(masks))
+    print("decode_sparse.npz:", len(meta), "cases,", sum(m[4] for m in meta), "raising KeyError")

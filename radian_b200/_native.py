@@ -13,12 +13,13 @@ from . import build as _build
 
 OK, E_ARG, E_CUDA, E_CONTEXT, E_READ, E_GAP = 0, -1, -2, -3, -4, -5
 READ_RANGE = 6  # RADIAN_READ_RANGE
+READ_KEY_ERROR = 7  # RADIAN_READ_KEY_ERROR
 MAX_BEAM_WIDTH = 128
 MAX_CONTEXT = 13
 
 EXPORTS = [
     "radian_last_error", "radian_version", "radian_device_count", "radian_trim_memory",
-    "radian_table_create", "radian_table_destroy", "radian_table_context_len", "radian_table_entropies",
+    "radian_table_create", "radian_table_create_sparse", "radian_table_destroy", "radian_table_context_len", "radian_table_entropies",
     "radian_decode_workspace_bytes", "radian_decode_batch_dev", "radian_decode_batch_host",
     "radian_assemble_plan", "radian_assemble_batch_dev", "radian_assemble_batch_host",
     "radian_stitch_batch_host", "radian_stitch_batch_dev", "radian_stitch_workspace_bytes",
@@ -43,6 +44,8 @@ def _load():
     lib.radian_trim_memory.argtypes = [c_int]
     lib.radian_table_create.restype = c_int
     lib.radian_table_create.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p)]
+    lib.radian_table_create_sparse.restype = c_int
+    lib.radian_table_create_sparse.argtypes = [c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]
     lib.radian_table_destroy.restype = c_int
     lib.radian_table_destroy.argtypes = [c_void_p]
     lib.radian_table_context_len.restype = c_int
@@ -53,7 +56,7 @@ def _load():
     lib.radian_decode_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int64, c_int64]
     lib.radian_decode_batch_dev.restype = c_int
     lib.radian_decode_batch_dev.argtypes = [
-        c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_double, c_double,
+        c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_double, c_double,
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]
     lib.radian_decode_batch_host.restype = c_int
     lib.radian_decode_batch_host.argtypes = [

@@ -46,25 +46,41 @@ int device_info(int device, DeviceInfo *out)
     if (!have[device]) {
         RADIAN_CUDA(cudaDeviceGetAttribute(&cache[device].sm_count, cudaDevAttrMultiProcessorCount, device));
         RADIAN_CUDA(cudaDeviceGetAttribute(&cache[device].max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        RADIAN_CUDA(cudaDeviceGetAttribute(&cache[device].smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
         have[device] = true;
     }
     *out = cache[device];
     return 0;
 }
 
-// The _host entry points allocate with cudaMallocAsync; keep freed blocks in the device pool so
-// that repeated calls do not pay for fresh allocations every time.
-int keep_pool(int device)
+// The _host entry points allocate stream-ordered from a pool of their own (one per device), which
+// keeps freed blocks between calls so that repeated calls do not pay for fresh allocations.  The
+// device's default pool -- shared with every other cudaMallocAsync user of the process -- is never
+// touched: neither its release threshold nor its contents (radian_trim_memory trims only this pool).
+static cudaMemPool_t g_pool[64] = {nullptr};
+
+int keep_pool(int device, cudaMemPool_t *pool)
 {
     static std::mutex mu;
-    static bool done[64] = {false};
     std::lock_guard<std::mutex> lk(mu);
-    if (device < 0 || device >= 64 || done[device]) return 0;
-    cudaMemPool_t pool;
-    RADIAN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long thr = ~0ull;
-    RADIAN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    done[device] = true;
+    if (device < 0 || device >= 64) {
+        set_error("bad device index %d", device);
+        return RADIAN_E_ARG;
+    }
+    if (!g_pool[device]) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t p = nullptr;
+        RADIAN_CUDA(cudaMemPoolCreate(&p, &props));
+        unsigned long long thr = ~0ull;  // keep freed blocks until radian_trim_memory
+        RADIAN_CUDA(cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &thr));
+        g_pool[device] = p;
+    }
+    *pool = g_pool[device];
     return 0;
 }
 
@@ -75,28 +91,66 @@ std::mutex &host_mutex(int device)
 }
 
 // gate bit of context i: entropy(lm[context]) < r_threshold (decode.py:93, strict)
-__global__ void gate_kernel(const double *__restrict__ entropy, size_t rows, double thr, uint32_t *__restrict__ gate)
+// (a context that is absent from the model never opens the gate; a read that reaches it fails)
+__global__ void gate_kernel(const double *__restrict__ entropy, const uint32_t *__restrict__ miss, size_t rows, double thr,
+                            uint32_t *__restrict__ gate)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((rows + 31) & ~(size_t)31); i += stride) {
         const bool g = i < rows && entropy[i] < thr;
-        const unsigned b = __ballot_sync(0xffffffffu, g);
-        if ((threadIdx.x & 31) == 0) gate[i >> 5] = b;
+        unsigned b = __ballot_sync(0xffffffffu, g);
+        if ((threadIdx.x & 31) == 0) {
+            if (miss) b &= ~miss[i >> 5];
+            gate[i >> 5] = b;
+        }
     }
 }
 
-int table_prepare_gate(radian_table *t, double r_threshold, cudaStream_t stream)
+constexpr size_t kMaxGateMasks = 8;
+
+int table_get_gate(const radian_table *t, double r_threshold, cudaStream_t stream, const uint32_t **d_bits)
 {
-    if (t->gate_valid && t->gate_threshold == r_threshold) return 0;
-    int dev = 0;
-    RADIAN_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(t->mu);
+    for (GateMask &g : t->gates)
+        if (g.threshold == r_threshold) {
+            g.last_use = ++t->tick;
+            RADIAN_CUDA(cudaStreamWaitEvent(stream, g.ready, 0));
+            *d_bits = g.d_bits;
+            return 0;
+        }
+    if (t->gates.size() >= kMaxGateMasks) {
+        // drop the mask that was used longest ago; a launch on some other stream may still be reading
+        // it, so the device is drained first (a ninth distinct threshold on one table is rare)
+        size_t lru = 0;
+        for (size_t i = 1; i < t->gates.size(); ++i)
+            if (t->gates[i].last_use < t->gates[lru].last_use) lru = i;
+        RADIAN_CUDA(cudaDeviceSynchronize());
+        cudaFree(t->gates[lru].d_bits);
+        cudaEventDestroy(t->gates[lru].ready);
+        t->gates.erase(t->gates.begin() + (long)lru);
+    }
     DeviceInfo di;
-    int rc = device_info(dev, &di);
+    int rc = device_info(t->device, &di);
     if (rc) return rc;
-    gate_kernel<<<di.sm_count * 8, 256, 0, stream>>>(t->d_entropy, t->rows, r_threshold, t->d_gate);
-    RADIAN_CUDA(cudaGetLastError());
-    t->gate_threshold = r_threshold;
-    t->gate_valid = 1;
+    GateMask g;
+    g.threshold = r_threshold;
+    g.last_use = ++t->tick;
+    g.d_bits = nullptr;
+    g.ready = nullptr;
+    RADIAN_CUDA(cudaMalloc(&g.d_bits, ((t->rows + 31) / 32) * sizeof(uint32_t)));
+    cudaError_t e = cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        gate_kernel<<<di.sm_count * 8, 256, 0, stream>>>(t->d_entropy, t->d_miss, t->rows, r_threshold, g.d_bits);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(g.ready, stream);
+    if (e != cudaSuccess) {
+        cudaFree(g.d_bits);
+        if (g.ready) cudaEventDestroy(g.ready);
+        return cuda_fail(e, "table_get_gate");
+    }
+    t->gates.push_back(g);
+    *d_bits = g.d_bits;
     return 0;
 }
 
@@ -117,10 +171,9 @@ extern "C" int radian_trim_memory(int device)
     }
     std::lock_guard<std::mutex> host_lock(host_mutex(device));
     RADIAN_CUDA(cudaSetDevice(device));
-    RADIAN_CUDA(cudaDeviceSynchronize());
-    cudaMemPool_t pool;
-    RADIAN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    RADIAN_CUDA(cudaMemPoolTrimTo(pool, 0));
+    // (the streams of finished _host calls are synchronised before they return; nothing of this
+    // library is in flight on the pool while the host mutex is held)
+    if (g_pool[device]) RADIAN_CUDA(cudaMemPoolTrimTo(g_pool[device], 0));
     return RADIAN_OK;
 }
 
@@ -145,6 +198,12 @@ static inline double row_entropy_host(const double *r)
 
 extern "C" int radian_table_create(const double *probs, int L, int device, radian_table_t **out)
 {
+    return radian_table_create_sparse(probs, nullptr, L, device, out);
+}
+
+extern "C" int radian_table_create_sparse(const double *probs, const uint8_t *present, int L, int device,
+                                          radian_table_t **out)
+{
     if (!probs || !out || L < 1 || L > RADIAN_MAX_CONTEXT) {
         set_error("radian_table_create: need probs, out and 1 <= L <= %d (got L=%d)", RADIAN_MAX_CONTEXT, L);
         return RADIAN_E_ARG;
@@ -161,26 +220,70 @@ extern "C" int radian_table_create(const double *probs, int L, int device, radia
     if (nt > 32) nt = 32;
     if (rows < (1u << 16)) nt = 1;
     std::vector<std::thread> th;
+    std::vector<double> vmax(nt, 0.0);
+    std::vector<int> vbad(nt, 0);
     for (unsigned k = 0; k < nt; ++k)
         th.emplace_back([&, k]() {
             const size_t lo = rows * k / nt, hi = rows * (k + 1) / nt;
-            for (size_t i = lo; i < hi; ++i) ent[i] = row_entropy_host(probs + i * 4);
+            double m = 0.0;
+            int bad = 0;
+            for (size_t i = lo; i < hi; ++i) {
+                if (present && !present[i]) {
+                    ent[i] = INFINITY;  // never below a threshold
+                    continue;
+                }
+                ent[i] = row_entropy_host(probs + i * 4);
+                for (int c = 0; c < 4; ++c) {
+                    const double x = probs[i * 4 + c];
+                    bad |= !(x >= 0.0 && x <= 4.0);  // also catches NaN
+                    m = x > m ? x : m;
+                }
+            }
+            vmax[k] = m;
+            vbad[k] = bad;
         });
     for (auto &x : th) x.join();
+    double tmax = 0.0;
+    for (unsigned k = 0; k < nt; ++k) {
+        tmax = vmax[k] > tmax ? vmax[k] : tmax;
+        if (vbad[k]) {
+            set_error("radian_table_create: table entries must be probabilities (finite, 0 <= p <= 4)");
+            return RADIAN_E_ARG;
+        }
+    }
 
     radian_table *t = new radian_table();
-    memset(t, 0, sizeof(*t));
     t->L = L;
     t->device = device;
     t->rows = rows;
+    {
+        // high word of the largest entry: what the decode kernel assumes of a row that is still on
+        // its way from HBM (decode.cu, quiet-frame bound)
+        uint64_t bits;
+        memcpy(&bits, &tmax, 8);
+        t->rcap = (int)(bits >> 32);
+    }
     cudaError_t e;
     if ((e = cudaMalloc(&t->d_rows, rows * 4 * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&t->d_entropy, rows * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&t->d_gate, ((rows + 31) / 32) * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemcpy(t->d_rows, probs, rows * 4 * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(t->d_entropy, ent.data(), rows * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
         radian_table_destroy(t);
         return cuda_fail(e, "radian_table_create");
+    }
+    if (present) {
+        std::vector<uint32_t> miss((rows + 31) / 32, 0u);
+        bool any = false;
+        for (size_t i = 0; i < rows; ++i)
+            if (!present[i]) {
+                miss[i >> 5] |= 1u << (i & 31);
+                any = true;
+            }
+        if (any && ((e = cudaMalloc(&t->d_miss, miss.size() * 4)) != cudaSuccess ||
+                    (e = cudaMemcpy(t->d_miss, miss.data(), miss.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)) {
+            radian_table_destroy(t);
+            return cuda_fail(e, "radian_table_create_sparse");
+        }
     }
     *out = t;
     return RADIAN_OK;
@@ -192,7 +295,11 @@ extern "C" int radian_table_destroy(radian_table_t *t)
     cudaSetDevice(t->device);
     if (t->d_rows) cudaFree(t->d_rows);
     if (t->d_entropy) cudaFree(t->d_entropy);
-    if (t->d_gate) cudaFree(t->d_gate);
+    if (t->d_miss) cudaFree(t->d_miss);
+    for (GateMask &g : t->gates) {
+        cudaFree(g.d_bits);
+        cudaEventDestroy(g.ready);
+    }
     delete t;
     return RADIAN_OK;
 }
@@ -246,7 +353,7 @@ static int check_decode_args(const void *post, const int64_t *fo, int n_reads, i
 }
 
 static int decode_batch_dev_impl(const void *post, int post_is_f64, const int64_t *frame_offsets, int n_reads,
-                                 const int32_t *order, int64_t max_frames, int beam_width,
+                                 const int32_t *order, int64_t max_frames, int64_t total_frames, int beam_width,
                                  const radian_table_t *table, int len_context, double s_threshold,
                                  double r_threshold, uint8_t *out_seq, const int64_t *seq_offsets, int64_t *out_len,
                                  double *out_score, int32_t *out_status, uint64_t *out_counters, int64_t arena_nodes,
@@ -272,8 +379,9 @@ static int decode_batch_dev_impl(const void *post, int post_is_f64, const int64_
         set_error("radian_decode_batch_dev: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
         return RADIAN_E_ARG;
     }
+    const uint32_t *d_gate = nullptr;
     if (table) {
-        rc = table_prepare_gate(const_cast<radian_table_t *>(table), r_threshold, st);
+        rc = table_get_gate(table, r_threshold, st, &d_gate);
         if (rc) return rc;
     }
     RADIAN_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
@@ -284,9 +392,13 @@ static int decode_batch_dev_impl(const void *post, int post_is_f64, const int64_
     a.order = order;
     a.n_reads = n_reads;
     a.beam_width = beam_width;
+    a.max_frames = max_frames;
+    a.total_frames = total_frames;
     a.table = table ? table->d_rows : nullptr;
-    a.gate = table ? table->d_gate : nullptr;
+    a.gate = d_gate;
+    a.miss = table ? table->d_miss : nullptr;
     a.L = table ? table->L : 0;
+    a.rcap = table ? table->rcap : 0;
     a.s_thr = s_threshold;
     a.out_seq = out_seq;
     a.seq_offsets = seq_offsets;
@@ -302,14 +414,14 @@ static int decode_batch_dev_impl(const void *post, int post_is_f64, const int64_
 }
 
 extern "C" int radian_decode_batch_dev(const void *post, int post_is_f64, const int64_t *frame_offsets, int n_reads,
-                                       const int32_t *order, int64_t max_frames, int beam_width,
+                                       const int32_t *order, int64_t max_frames, int64_t total_frames, int beam_width,
                                        const radian_table_t *table, int len_context, double s_threshold,
                                        double r_threshold, uint8_t *out_seq, const int64_t *seq_offsets,
                                        int64_t *out_len, double *out_score, int32_t *out_status,
                                        uint64_t *out_counters, int64_t arena_nodes, void *workspace,
                                        size_t workspace_bytes, radian_stream_t stream)
 {
-    return decode_batch_dev_impl(post, post_is_f64, frame_offsets, n_reads, order, max_frames, beam_width, table,
+    return decode_batch_dev_impl(post, post_is_f64, frame_offsets, n_reads, order, max_frames, total_frames, beam_width, table,
                                  len_context, s_threshold, r_threshold, out_seq, seq_offsets, out_len, out_score,
                                  out_status, out_counters, arena_nodes, workspace, workspace_bytes, nullptr,
                                  (cudaStream_t)stream);
@@ -542,8 +654,9 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     }
     const int64_t frames = fo[n], seq_bytes = so[n];
     const size_t ws_bytes = radian_decode_workspace_bytes(device, beam_width, n, max_frames, arena_nodes);
+    cudaMemPool_t pool_ = nullptr;  // this library's own stream-ordered pool on the device
     {
-        int krc = keep_pool(device);
+        int krc = keep_pool(device, &pool_);
         if (krc) return krc;
     }
     // copy plan: runs of queue-adjacent reads that are also adjacent in the caller's buffer go in
@@ -622,17 +735,17 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     cudaError_t e;
 #define TRY(x)                                   \
     if (ret == RADIAN_OK && (e = (x)) != cudaSuccess) ret = cuda_fail(e, #x)
-    TRY(cudaMallocAsync(&d_post, (size_t)(frames ? frames : 1) * row, st));
-    TRY(cudaMallocAsync(&d_ws, ws_bytes, st));
-    TRY(cudaMallocAsync(&d_fo, (size_t)(n + 1) * 8, st));
-    TRY(cudaMallocAsync(&d_so, (size_t)(n + 1) * 8, st));
-    TRY(cudaMallocAsync(&d_len, (size_t)n * 8, st));
-    TRY(cudaMallocAsync(&d_status, (size_t)n * 4, st));
-    TRY(cudaMallocAsync(&d_ready, 256, st));
-    TRY(cudaMallocAsync(&d_order, (size_t)n * 4, st));
-    TRY(cudaMallocAsync(&d_seq, (size_t)(seq_bytes ? seq_bytes : 1), st));
-    TRY(cudaMallocAsync(&d_score, (size_t)n * 16, st));
-    if (out_counters) TRY(cudaMallocAsync(&d_cnt, (size_t)n * 32, st));
+    TRY(cudaMallocFromPoolAsync(&d_post, (size_t)(frames ? frames : 1) * row, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_ws, ws_bytes, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_fo, (size_t)(n + 1) * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_so, (size_t)(n + 1) * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_len, (size_t)n * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_status, (size_t)n * 4, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_ready, 256, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_order, (size_t)n * 4, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_seq, (size_t)(seq_bytes ? seq_bytes : 1), pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_score, (size_t)n * 16, pool_, st));
+    if (out_counters) TRY(cudaMallocFromPoolAsync(&d_cnt, (size_t)n * 32, pool_, st));
     TRY(cudaMemcpyAsync(d_fo, fo.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_so, so.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemsetAsync(d_ready, 0, 256, st));
@@ -642,7 +755,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     TRY(cudaStreamWaitEvent(cs[0], ev, 0));
     TRY(cudaStreamWaitEvent(cs[1], ev, 0));
     if (ret == RADIAN_OK && !copy_first) {
-        ret = decode_batch_dev_impl(d_post, post_is_f64, d_fo, n, nullptr, max_frames, beam_width, table,
+        ret = decode_batch_dev_impl(d_post, post_is_f64, d_fo, n, nullptr, max_frames, frames, beam_width, table,
                                     len_context, s_threshold, r_threshold, d_seq, d_so, d_len, d_score, d_status,
                                     d_cnt, arena_nodes, d_ws, ws_bytes, d_ready, st);
         launched = (ret == RADIAN_OK);
@@ -691,7 +804,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
             TRY(cudaStreamWaitEvent(st, ev_last, 0));
         }
         if (ret == RADIAN_OK)
-            ret = decode_batch_dev_impl(d_post, post_is_f64, d_fo, n, nullptr, max_frames, beam_width, table,
+            ret = decode_batch_dev_impl(d_post, post_is_f64, d_fo, n, nullptr, max_frames, frames, beam_width, table,
                                         len_context, s_threshold, r_threshold, d_seq, d_so, d_len, d_score,
                                         d_status, d_cnt, arena_nodes, d_ws, ws_bytes, nullptr, st);
     }
@@ -710,7 +823,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
             if (trace) fprintf(stderr, "[radian] host pass: transfer stalled, %zu reads decoded by a second launch\n", redo.size());
             TRY(cudaMemcpyAsync(d_order, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
             if (ret == RADIAN_OK)
-                ret = decode_batch_dev_impl(d_post, post_is_f64, d_fo, (int)redo.size(), d_order, max_frames,
+                ret = decode_batch_dev_impl(d_post, post_is_f64, d_fo, (int)redo.size(), d_order, max_frames, 0,
                                             beam_width, table, len_context, s_threshold, r_threshold, d_seq, d_so,
                                             d_len, d_score, d_status, d_cnt, arena_nodes, d_ws, ws_bytes, nullptr, st);
             TRY(cudaStreamSynchronize(st));  // redo must outlive the copy of the order array

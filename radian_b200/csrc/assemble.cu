@@ -281,8 +281,9 @@ extern "C" int radian_assemble_batch_host(const float *chunks, const int64_t *ch
     }
     std::lock_guard<std::mutex> host_lock(host_mutex(device));
     RADIAN_CUDA(cudaSetDevice(device));
+    cudaMemPool_t pool_ = nullptr;  // this library's own stream-ordered pool on the device
     {
-        int krc = keep_pool(device);
+        int krc = keep_pool(device, &pool_);
         if (krc) return krc;
     }
     const int64_t n_chunks = read_chunk_ranges[n_reads];
@@ -298,11 +299,11 @@ extern "C" int radian_assemble_batch_host(const float *chunks, const int64_t *ch
     cudaError_t e;
 #define TRY(x)                                   \
     if (ret == RADIAN_OK && (e = (x)) != cudaSuccess) ret = cuda_fail(e, #x)
-    TRY(cudaMallocAsync(&d_chunks, (size_t)(in_rows ? in_rows : 1) * 20, st));
-    TRY(cudaMallocAsync(&d_cro, (size_t)(n_chunks + 1) * 8, st));
-    TRY(cudaMallocAsync(&d_rcr, (size_t)(n_reads + 1) * 8, st));
-    TRY(cudaMallocAsync(&d_oro, (size_t)(n_reads + 1) * 8, st));
-    TRY(cudaMallocAsync(&d_out, out_bytes ? out_bytes : 1, st));
+    TRY(cudaMallocFromPoolAsync(&d_chunks, (size_t)(in_rows ? in_rows : 1) * 20, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_cro, (size_t)(n_chunks + 1) * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_rcr, (size_t)(n_reads + 1) * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_oro, (size_t)(n_reads + 1) * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_out, out_bytes ? out_bytes : 1, pool_, st));
     TRY(cudaMemcpyAsync(d_chunks, chunks, (size_t)in_rows * 20, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_cro, chunk_row_offsets, (size_t)(n_chunks + 1) * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_rcr, read_chunk_ranges, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));

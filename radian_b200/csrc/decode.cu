@@ -34,12 +34,13 @@
 //     live beam are slid down onto the old generation (never revisited) and the rest is dropped.
 //     Every lineage promotes each of its symbols once, so the old generation is bounded by
 //     beam_width x decoded length.  The best labeling is read back by one walk at the end.
+#include <stdlib.h>
+
 #include "decode_common.cuh"
 
 namespace radian {
 
 constexpr int kWarpsPerBlock = 4;
-constexpr int kNoRmax = (int)0x80000000;
 // resident CTAs per SM asked from ptxas (A/B on B200, profiles/r1_minblocks_ab.txt): 6 CTAs =
 // 24 warps at <= 80 registers once the tile prefetch and the RNA rows moved to shared memory
 // (A/B on B200, scripts/ab_variants.sh: trading the pb/ptot selects of the extension scores for one
@@ -50,23 +51,30 @@ constexpr int kNoRmax = (int)0x80000000;
 
 template <int G, bool LM, typename PT>
 struct __align__(16) GroupSmem {
-    // doubles per frame (decode_common.cuh, EXT layout): P0..P4, gate, q0..q3, S, S/2, then the
-    // integer words of the quiet-frame test; 144 / 80 bytes per frame keep the record stores
-    // of neighbouring lanes on different banks
-    static constexpr int REC = LM ? 18 : 10;
-    static constexpr int NK = (2 * G > 32) ? 2 * G : 32;  // candidate slots of the fast ranking path
+    // doubles per frame (decode_common.cuh, compact layout): P0..P4, gate, p/S, 1, S/2, then the
+    // integer words of the quiet-frame test
+    static constexpr int REC = LM ? 14 : 6;  // compact records (decode_common.cuh)
     double rec[G * REC];
     double row[LM ? G * 4 : 4];       // RNA table row of every lane's extend-context (cp.async target)
     PT raw[G * 5];                    // next tile of posterior rows, landed by cp.async
     double ex[G * 2];                 // {pr_total, pr_blank} of every lane before the frame (copy/extend merge)
+    double zero[2];                   // 0.0: what a beam without a live parent reads as its parent's score
+                                      // (two of them: the arrays below are read with 16-byte loads)
     unsigned long long key[5 * G];    // candidate list: [0,G) copies by lane, [G,..) extensions
-    uint32_t k32[NK];                 // high words of the candidate scores (0 = empty slot)
+    uint32_t k32[G];                  // high words of the copies (ranking of the copies among themselves)
     uint32_t kill[G];                 // byte c of word l: extension (l,c) merged into a copy
     uint16_t pos[5 * G];              // dict insertion position of the candidate
     uint8_t src[5 * G];               // lane*4+c of an extension candidate
     uint8_t rnk[5 * G];               // rank of the candidate
     uint8_t newlist[G];               // candidate indices of the new beams, in list order
-    uint8_t lanerank[G];              // previous rank of every lane
+    // Per-beam state that only the frames that change the beam set touch (and the start and end of a
+    // read): kept here instead of in registers, which the quiet loop then has for itself.
+    unsigned long long c_h[G];        // hash of the labeling
+    unsigned long long c_hp[G];       // hash of the parent labeling
+    uint32_t c_ctx[G];                // last symbols, 2 bits each
+    int c_len[G];                     // labeling length
+    int c_node[G];                    // arena node of the last symbol
+    int c_rank[G];                    // rank among the kept beams
 };
 
 // Streamed batches: how many reads (in queue order) have landed, or -1 when the transfer is given
@@ -94,6 +102,76 @@ __device__ __noinline__ int poll_arrivals(const int *ready, int *stop_flag, int 
     return landed;
 }
 
+// max over the symbols c whose extension is a candidate of its own (bit 7 of byte c of km) of the high
+// word of the table value r_c; row = the four float64 of a beam's extend-context
+__device__ __forceinline__ int row_bound(const double *row, uint32_t km)
+{
+    const int4 ra = *reinterpret_cast<const int4 *>(row);      // r0 lo,hi r1 lo,hi
+    const int4 rb = *reinterpret_cast<const int4 *>(row + 2);  // r2, r3
+    return max(max(ra.y & (int)byte_sign_mask<0>(km), ra.w & (int)byte_sign_mask<1>(km)),
+               max(rb.y & (int)byte_sign_mask<2>(km), rb.w & (int)byte_sign_mask<3>(km)));
+}
+
+// -DRADIAN_STAGE_STATS: the COUNT instantiations report, in the reserved fourth counter of a read,
+// (frames that needed the second stage of the quiet test << 32) | frames that took the long way
+#ifdef RADIAN_STAGE_STATS
+#define RADIAN_STAT(x) if (COUNT) { x }
+#else
+#define RADIAN_STAT(x)
+#endif
+
+// The quiet loop (see the comment where it is used).  IDLE: some group of the warp has no read to
+// run (its lanes hold zeros and must not block the vote); a separate copy of the loop, so that the
+// common one does not carry the flag.  Everything a lane needs besides its three scores comes from
+// REFRESH(): q_rb0 + q_ox / q_oy = where this lane's copy emission is in a record, q_paddr = the
+// score of the parent whose extension merges into this beam (or a zero), q_succ / q_inc = the order
+// check.
+#define RADIAN_QUIET_LOOP(IDLE)                                                                              \
+    _Pragma("unroll 1") for (; it < nend; ++it)                                                             \
+    {                                                                                                        \
+        const unsigned rb = q_rb0 + (unsigned)it * (unsigned)(REC * 8);                                      \
+        const double P4 = lds_f64(rb + 32);                                                                  \
+        double dl_ = lds_f64(rb + q_ox);                                                                     \
+        int z;                                                                                               \
+        bool fgate_ = false;                                                                                 \
+        if (LM) {                                                                                            \
+            /* COPY emission (decode.py:150-175, 58-61): (r + p/S) * (S/2) with the gate open and a gated   \
+               copy-context, P[last] otherwise; both as (rcopy * gate + x) * y, see decode_common.cuh */    \
+            const double y_ = lds_f64(rb + q_oy);                                                            \
+            const double g_ = lds_f64(rb + 40);                                                              \
+            const int4 gi = lds_i4(rb + 96);                                                                 \
+            dl_ = __dmul_rn(__dadd_rn(__dmul_rn(rcopy, g_), dl_), y_);                                       \
+            z = gext ? max(gi.w, rmax) + gi.y : gi.z;                                                        \
+            fgate_ = gi.x != 0;                                                                              \
+        } else {                                                                                             \
+            z = lds_i32(rb + 40);                                                                            \
+        }                                                                                                    \
+        double npnb = __dmul_rn(pnb, dl_); /* the empty labeling and dead lanes have pnb == 0 */             \
+        const double npb = __dmul_rn(ptot, P4);                                                              \
+        double nptot = __dadd_rn(npb, npnb);                                                                 \
+        /* MERGE with the parent's extension by my last symbol (see the slow frame) */                       \
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ex_addr), "d"(ptot), "d"(pb) : "memory");      \
+        __syncwarp();                                                                                        \
+        {                                                                                                    \
+            const double v = __dmul_rn(lds_f64_volatile(q_paddr), dl_);                                      \
+            npnb = __dadd_rn(npnb, v);                                                                       \
+            nptot = __dadd_rn(nptot, v);                                                                     \
+        }                                                                                                    \
+        const uint32_t kc32 = (uint32_t)__double2hiint(nptot);                                               \
+        const uint32_t ksucc = __shfl_sync(kFull, kc32, q_succ);                                             \
+        const uint32_t kworst = __shfl_sync(kFull, kc32, last_lane);                                         \
+        const bool quiet = (IDLE && q_idle) || (kc32 >= ksucc + q_inc && kworst >= 0x00100000u &&            \
+                                                __double2hiint(ptot) + z < (int)kworst);                     \
+        if (!__all_sync(kFull, quiet)) break;                                                                \
+        if (COUNT && LM) {                                                                                   \
+            n_lookup += (unsigned)c_lookup;                                                                  \
+            if (fgate_) n_combine += (unsigned)c_combine;                                                    \
+        }                                                                                                    \
+        ptot = nptot; /* (a dead lane's new values are zero as well) */                                      \
+        pnb = npnb;                                                                                          \
+        pb = npb;                                                                                            \
+    }
+
 // Control flow is warp-uniform everywhere: a warp carries 32/G reads, and every branch that
 // contains a warp collective is taken by all of them together (decided by a full-mask vote), so
 // all shuffles and votes use the full mask and each group extracts its own lanes' bits.  Sub-warp
@@ -107,9 +185,8 @@ decode_kernel(const DecodeArgs a)
 {
     constexpr int GPW = 32 / G;  // groups (reads) per warp
     constexpr int REC = GroupSmem<G, LM, PT>::REC;
-    constexpr int NK = GroupSmem<G, LM, PT>::NK;
-    constexpr int EPL = (NK - G) / G;  // extension slots ranked by each lane on the fast path
     constexpr unsigned GBITS = (G == 32) ? kFull : ((1u << G) - 1u);
+    constexpr bool F64 = sizeof(PT) == 8;
     __shared__ GroupSmem<G, LM, PT> smem[kWarpsPerBlock * GPW];
     // streamed batches: last value of the arrival counter a waiting group saw, and since when
     // (stalled-transfer guard); kept out of GroupSmem, whose size the frame loop's addressing likes
@@ -141,15 +218,14 @@ decode_kernel(const DecodeArgs a)
 
     // ---- per-beam (lane) state; a dead lane keeps all three probabilities at zero
     double ptot = 0.0, pnb = 0.0, pb = 0.0;
-    unsigned long long h = 0, hp = 0;
-    uint32_t ctx = 0;
-    int len = 0, node = 0, rank = 0, plane = -1, last = 0;
+    int plane = -1, last = 0;  // (hash, context, length, arena node and rank live in sm.c_*)
     int prep = 0;        // 1 if the live parent (plane) ends in the same symbol as this beam
-    int rmax = kNoRmax;  // max high word of the unmerged entries of this beam's table row, or kNoRmax
+    int rmax = 0;  // max high word of the unmerged entries of this beam's table row (row_bound), or a.rcap
     bool alive = false;
     double rcopy = 0;  // table value of this beam's last symbol in its copy-context; the row of the
                        // extend-context lives in sm.row[li*4..]
     bool gext = false, gcopy = false;
+    bool rmax_prov = false;  // rmax is the table-wide bound: this beam's row was in flight when it was set
     int succ = 0;        // absolute lane of the beam ranked right after this one (own lane: none)
     uint32_t km = 0;     // byte c = 0x80: this lane holds a beam and its extension by c is a candidate
                          // of its own (not merged into a live child's copy); 0 for a dead lane
@@ -158,8 +234,62 @@ decode_kernel(const DecodeArgs a)
     int T = 0, t = 0, pend = -1;  // pend: queue ticket of a read that has not landed yet
     long long kacc = 0;
     const PT *rp = (const PT *)a.post;
-    unsigned long long n_lookup = 0, n_combine = 0, n_tie = 0;
+    unsigned long long n_lookup = 0, n_combine = 0, n_tie = 0, n_stage2 = 0;
     bool active = true;
+    // ---- what the quiet loop reads besides the scores; derived from the state above by REFRESH()
+    // whenever the beam set, the order or the read changes
+    bool q_idle = true;
+    const unsigned q_rb0 = (unsigned)__cvta_generic_to_shared(&sm.rec[0]);
+    const unsigned q_zero = (unsigned)__cvta_generic_to_shared(&sm.zero[0]);
+    unsigned q_paddr = q_zero, q_ox = 0, q_oy = 80, q_inc = 0;
+    int q_succ = lane;
+    int c_lookup = 0, c_combine = 0;  // COUNT: lm[context] reads / combine_dists calls of a gated frame
+    if (li == 0) sm.zero[0] = sm.zero[1] = 0.0;
+#define REFRESH()                                                                                          \
+    do {                                                                                                   \
+        const bool run_ = active && read >= 0 && status == 0;                                              \
+        const bool full_ = na >= bw;                                                                       \
+        q_idle = !run_;                                                                                    \
+        q_paddr = (run_ && alive && plane >= 0) ? (unsigned)__cvta_generic_to_shared(&sm.ex[plane * 2 + prep]) : q_zero; \
+        /* copy emission: rec[6 + last] and rec[11] for a gated copy-context, rec[last] and rec[10] otherwise */ \
+        q_ox = (unsigned)(((LM && gcopy) ? 6 + last : last) * 8);                                          \
+        q_oy = (LM && gcopy) ? 88u : 80u;                                                                  \
+        /* order check kc32 >= k(succ) + inc: strict for a beam with a successor, void for the last one    \
+           (succ == lane); a beam with room left is never quiet: every extension is a candidate */        \
+        q_succ = full_ ? succ : lane;                                                                      \
+        q_inc = (full_ && succ == lane) ? 0u : 1u;                                                         \
+        if (COUNT && LM) {                                                                                 \
+            const int len_ = sm.c_len[li];                                                                \
+            const bool lc_ = run_ && alive && len_ >= L + 1, le_ = run_ && alive && len_ >= L;               \
+            c_lookup = __popc(GBALLOT(lc_)) + __popc(GBALLOT(le_));                                        \
+            c_combine = __popc(GBALLOT(lc_ && gcopy)) + __popc(GBALLOT(le_ && gext));                      \
+        }                                                                                                  \
+    } while (0)
+    // the read cannot be finished: its status is reported, its remaining frames are skipped and it
+    // leaves no beam behind (an idle group must look "in order, nothing competing")
+#define GIVE_UP(code)           \
+    do {                        \
+        status = (code);        \
+        run = false;            \
+        alive = false;          \
+        km = 0u;                \
+        succ = lane;            \
+        ptot = pnb = pb = 0.0;  \
+    } while (0)
+    // best beam outside [2^300, 2^900): everything times an exact power of two, back to 2^600
+#define RESCALE_CHECK()                                                                                    \
+    do {                                                                                                   \
+        const int exb_ = (__shfl_sync(kFull, __double2hiint(ptot), first_lane) >> 20) & 0x7ff;             \
+        if (run && (unsigned)(exb_ - (1023 + 300)) >= 600u) {                                              \
+            const int k1_ = exb_ == 0 ? 1000 : 1023 - exb_; /* a subnormal best first comes up by 2^1000 */ \
+            const double s1_ = __hiloint2double((1023 + k1_) << 20, 0);                                    \
+            const double s2_ = __hiloint2double((1023 + 600) << 20, 0);                                    \
+            ptot = __dmul_rn(__dmul_rn(ptot, s1_), s2_);                                                   \
+            pnb = __dmul_rn(__dmul_rn(pnb, s1_), s2_);                                                     \
+            pb = __dmul_rn(__dmul_rn(pb, s1_), s2_);                                                       \
+            kacc -= k1_ + 600;                                                                             \
+        }                                                                                                  \
+    } while (0)
 
     while (true) {
         // ------------------------------------------------------------ fetch a read
@@ -208,15 +338,16 @@ decode_kernel(const DecodeArgs a)
                     ptot = alive ? 1.0 : 0.0;
                     pb = ptot;
                     pnb = 0.0;
-                    h = 0x243F6A8885A308D3ull;
-                    hp = 0;
-                    ctx = 0;
-                    len = 0;
-                    node = 0;
-                    rank = 0;
+                    sm.c_h[li] = 0x243F6A8885A308D3ull;
+                    sm.c_hp[li] = 0;
+                    sm.c_ctx[li] = 0;
+                    sm.c_len[li] = 0;
+                    sm.c_node[li] = 0;
+                    sm.c_rank[li] = 0;
                     plane = -1;
                     prep = 0;
-                    rmax = kNoRmax;
+                    rmax = 0;
+                    rmax_prov = false;
                     last = 0;
                     gext = gcopy = false;
                     succ = lane;
@@ -228,7 +359,7 @@ decode_kernel(const DecodeArgs a)
                     na = 1;
                     status = 0;
                     kacc = 0;
-                    n_lookup = n_combine = n_tie = 0;
+                    n_lookup = n_combine = n_tie = n_stage2 = 0;
                 }
             }
         }
@@ -254,23 +385,39 @@ decode_kernel(const DecodeArgs a)
         __syncwarp();
         if (live && tb + li < T) prefetch_row(&sm.raw[li * 5], rp, tb + li);
 
-        for (int it = 0; it < nrun; ++it) {
+        // (values the quiet loop reads per lane; they change only when the beam set does: REFRESH)
+        REFRESH();
+
+        for (int it0 = 0; it0 < nrun; it0 += G) {
             bool run = live && status == 0;  // group-uniform
+            const int nend = (nrun - it0) < G ? (nrun - it0) : G;  // frames of this tile the warp runs
             // -------------------------------------------------------- tile refill
-            if ((it % G) == 0) {
+            {
                 cp_async_wait_all();
                 __syncwarp();
-                if (run && tb + it + li < T) make_record<LM, true>(&sm.raw[li * 5], a.s_thr, &sm.rec[li * REC]);
+                int kf = 0;
+                if (run && tb + it0 + li < T) kf = make_record<LM, true, F64, true>(&sm.raw[li * 5], a.s_thr, &sm.rec[li * REC]);
                 __syncwarp();
-                if (run && tb + it + G + li < T) prefetch_row(&sm.raw[li * 5], rp, tb + it + G + li);
+                if (run && tb + it0 + G + li < T) prefetch_row(&sm.raw[li * 5], rp, tb + it0 + G + li);
+                if (F64) {
+                    // exponents taken out of tiny rows (make_record): added up for the frames that are
+                    // going to be consumed; stored score = true score x 2^-kacc
+                    kf = li < nend ? kf : 0;
+                    if (__any_sync(kFull, kf != 0)) {
+#pragma unroll
+                        for (int o = G / 2; o > 0; o >>= 1) kf += __shfl_xor_sync(kFull, kf, o);
+                        kacc -= kf;
+                    }
+                }
             }
 
             // -------------------------------------------------------- nursery collection
             // checked once per tile: a frame adds at most G nodes per read, a tile at most G*G
-            if ((it % G) == 0 && __any_sync(kFull, run && (top + G * G > old_top + kNursery || top + G * G > cap))) {
+            if (__any_sync(kFull, run && (top + G * G > old_top + kNursery || top + G * G > cap))) {
                 // every running group of the warp collects (early collection is harmless)
                 // 1. mark nursery nodes reachable from a live beam (stop at the old generation or
                 //    at a node somebody marked in an earlier step)
+                const int node = sm.c_node[li];
                 int cur = node;
                 bool walking = run && alive && cur >= old_top;
                 while (__any_sync(kFull, walking)) {
@@ -318,473 +465,481 @@ decode_kernel(const DecodeArgs a)
                     cnt += __popc(bal);
                     __syncwarp();
                 }
-                if (run && alive && node >= old_top) node = (int)fwd[node - old_top];
+                if (run && alive && node >= old_top) sm.c_node[li] = (int)fwd[node - old_top];
                 __syncwarp();
                 if (run) {
                     old_top = cnt;
                     top = cnt;
-                    if (top + G * G > cap) {
-                        status = RADIAN_READ_TRIE_OVERFLOW;  // reported; remaining frames are skipped
-                        run = false;
-                        alive = false;
-                        km = 0u;
-                        succ = lane;
-                        ptot = pnb = pb = 0.0;
-                    }
+                    if (top + G * G > cap) GIVE_UP(RADIAN_READ_TRIE_OVERFLOW);
                 }
+                REFRESH();
             }
-            const bool av = alive && run;  // this lane holds a beam that takes part in this frame
 
             // RESCALE by an exact power of two when the best beam (the largest value of the group)
-            // has fallen below 2^-256.  Checked every frame: a float32-derived probability is
-            // >= 2^-149, so nothing gets near the float64 limit in between.  Idle groups hold zeros.
-            {
-                const int exb = __shfl_sync(kFull, __double2hiint(ptot), first_lane) >> 20;
-                if (exb != 0 && exb < 1023 - 256) {
-                    const double sc = __hiloint2double((2046 - exb) << 20, 0);
-                    ptot *= sc;
-                    pnb *= sc;
-                    pb *= sc;
-                    kacc += exb - 1023;
-                }
-            }
+            // has left [2^300, 2^900): back to 2^600.  Checked once per tile here and again before
+            // every frame that is not quiet; in between, the quiet test itself refuses a frame in
+            // which a kept beam is not a normal number, so nothing is ever lost to underflow.
+            RESCALE_CHECK();
 
-            // -------------------------------------------------------- one frame
-            const double *rec = &sm.rec[(it % G) * REC];
-            const int *reci = reinterpret_cast<const int *>(rec);
-            const double P4 = rec[4];
-            bool fgate = false;
-            int hS = 0;
-            if (LM) {
-                const int2 gs = *reinterpret_cast<const int2 *>(reci + 32);
-                fgate = gs.x != 0;
-                hS = gs.y;
-            }
-            // (a dead lane computes on stale flags; all its scores are zero and stay zero)
-            if (COUNT && LM) {
-                const bool lm_copy = av && len >= L + 1;  // decode.py:157
-                const bool lm_ext = av && len >= L;       // decode.py:180
-                n_lookup += __popc(GBALLOT(lm_copy)) + __popc(GBALLOT(lm_ext));
-                n_combine += __popc(GBALLOT(lm_copy && gcopy && fgate)) + __popc(GBALLOT(lm_ext && gext && fgate));
-            }
-
-            // COPY (decode.py:150-175)
-            // the empty labeling and dead lanes have pnb == 0, so their copy needs no special case
-            double dl_ = rec[last];
-            // (gcopy implies len >= L+1 and gext implies len >= L: both are set when the beam is created)
-            if (LM && gcopy && fgate) dl_ = __dmul_rn(__dadd_rn(rcopy, rec[6 + last]), rec[11]);  // decode.py:58-61
-            double npnb = __dmul_rn(pnb, dl_);
-            const double npb = __dmul_rn(ptot, P4);
-            double nptot = __dadd_rn(npb, npnb);
-
-            // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference.  The
-            // parent's extension by last(X) is (pr_blank or pr_total of the parent) x the emission
-            // of last(X) in the parent's extend-context, and that emission is this beam's own
-            // copy emission dl_ (same context, same gate, same table value), so only the parent's
-            // two scores travel through shared memory.  Which pairs merge only changes when the
-            // beam set changes: the pairing (plane, prep, km) is state.
-            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ex_addr), "d"(ptot), "d"(pb) : "memory");
-            __syncwarp();
-            if (av && plane >= 0) {
-                const double v = __dmul_rn(sm.ex[plane * 2 + prep], dl_);
-                npnb = __dadd_rn(npnb, v);
-                nptot = __dadd_rn(nptot, v);
-            }
-
-            // SELECT the best beam_width candidates (decode.py:145, 35-39).
-            // Most frames change nothing but the scores: the rank order is kept as state (succ =
-            // lane of the next-ranked beam) and re-validated with one compare per beam; an
-            // extension matters only if it is not below the worst copy of a full beam.
-            const unsigned long long kcopy = (unsigned long long)__double_as_longlong(nptot);
-            const uint32_t kc32 = (uint32_t)(kcopy >> 32);  // zero on a dead lane: its scores are zero
-            const uint32_t ksucc = __shfl_sync(kFull, kc32, succ);
-            const uint32_t kworst = __shfl_sync(kFull, kc32, last_lane);
-            const bool prune = (na >= bw);
-            bool ranks_changed = false;
-            {
-                // QUIET frame (the common case, one vote): in every group of the warp the order of
-                // the copies holds strictly, the beam is full and no extension, merged ones
-                // excepted, can reach the worst copy.  The extensions are not computed for this:
-                // with h(x) = high word of the float64 x, (h(x) >> 20) - 1023 + mantissa fraction
-                // is a lower bound of log2 x that is short by at most 0.0861, so
+            int it = 0;
+            while (true) {
+                // ==================================================== QUIET frames
+                // The common case: in every group of the warp the order of the copies holds strictly,
+                // the beam is full and no extension, merged ones excepted, can reach the worst copy.
+                // The extensions are not computed for this: with h(x) = high word of the float64 x,
+                // (h(x) >> 20) - 1023 + mantissa fraction is a lower bound of log2 x that is short by at
+                // most 0.0861, so
                 //   h(p) + h(d) - bias + slack < h(worst)  implies  p*d < worst
-                // for slack >= 2 * 0.0861 * 2^20.  The emission d of an extension is P_c, or with
-                // the model ((r_c + q_c)/2) * S <= max(r_c, q_c) * S (one more 0.0861).
-                // (A/B on B200: 5 or 6 resident CTAs per SM make no difference any more, 9.09e9 vs
-                // 9.06e9 frames/s; 4 lose 10 %.)
-                // With the model the table part of the bound, max over the unmerged symbols of
-                // h(r_c), is a per-beam constant (rmax): it is rebuilt lazily from the row in shared
-                // memory after the beam was created or its merge mask changed.
-                const bool gated = LM && gext && fgate;
-                if (LM && gated && rmax == kNoRmax) {
-                    cp_async_wait_all();  // the row gathered when this beam was created
-                    const int4 ra = *reinterpret_cast<const int4 *>(&sm.row[li * 4]);      // r0 lo,hi r1 lo,hi
-                    const int4 rb = *reinterpret_cast<const int4 *>(&sm.row[li * 4 + 2]);  // r2, r3
-                    rmax = max(max(ra.y & (int)byte_sign_mask<0>(km), ra.w & (int)byte_sign_mask<1>(km)),
-                               max(rb.y & (int)byte_sign_mask<2>(km), rb.w & (int)byte_sign_mask<3>(km)));
+                // for slack >= 2 * 0.0861 * 2^20.  The emission d of an extension is P_c, or with the
+                // model ((r_c + q_c)/2) * S <= max(r_c, q_c) * S (one more 0.0861).  P_c and q_c are
+                // bounded by the largest of the four symbols (one word per frame, prepared with the
+                // record; measured on the bench workload, taking the largest over the unmerged
+                // symbols only would keep 0.1 % more frames quiet); the table part of the bound, max
+                // over the unmerged symbols of h(r_c), is a per-beam constant (rmax).
+                // Such a frame is one vote and three score updates per beam; the loop carries
+                // nothing but the three scores.
+                if (__any_sync(kFull, q_idle)) {
+                    RADIAN_QUIET_LOOP(true)
+                } else {
+                    RADIAN_QUIET_LOOP(false)
                 }
-                // high words of q0..q3 (gated lanes) or of P0..P3
-                // (both loaded, then selected: one load whose address waits for `gated` is 1 % slower.
-                // Other A/Bs on B200: pinning `lane` in a register to spare the per-frame re-read of
-                // SR_TID costs more in register pressure than it saves, -2 %; refreshing the rescale
-                // exponent where the scores are committed instead of at the frame start is a wash.)
-                int4 hx = *reinterpret_cast<const int4 *>(reci + (LM ? 24 : 12));
-                if (LM) {
-                    const int4 hq = *reinterpret_cast<const int4 *>(reci + 28);
-                    if (gated) hx = hq;
-                }
-                // slack: 2 * 0.0861 * 2^20 for p * P_c, one more 0.0861 for the max(r, q) * S bound
-                const int kSlack = (LM && gated) ? 272000 : 181000;
-                const int z0 = hx.x & (int)byte_sign_mask<0>(km);
-                const int z1 = hx.y & (int)byte_sign_mask<1>(km);
-                const int z2 = hx.z & (int)byte_sign_mask<2>(km);
-                const int z3 = hx.w & (int)byte_sign_mask<3>(km);
-                int zmax = max(max(z0, z1), max(z2, z3));
-                if (LM && gated) zmax = max(zmax, rmax) + hS;
-                const int ub = __double2hiint(ptot) + zmax + (kSlack - 0x3ff00000);
-                const bool quiet = !run || ((kc32 > ksucc || succ == lane) && prune && kworst >= 0x00100000u &&
-                                            ub < (int)kworst);
-                if (__all_sync(kFull, quiet)) {
-                    ptot = nptot;  // (a dead lane's new values are zero as well)
-                    pnb = npnb;
-                    pb = npb;
-                    continue;
-                }
-            }
+                if (it >= nend) break;
 
-            // EXTEND (decode.py:177-201), only when some extension may matter
-            const double2 P01 = *reinterpret_cast<const double2 *>(rec);
-            const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
-            double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
-            if (LM && gext && fgate) {
-                const double2 q01 = *reinterpret_cast<const double2 *>(rec + 6);
-                const double2 q23 = *reinterpret_cast<const double2 *>(rec + 8);
-                const double Sh = rec[11];
-                const double2 r01 = *reinterpret_cast<const double2 *>(&sm.row[li * 4]);
-                const double2 r23 = *reinterpret_cast<const double2 *>(&sm.row[li * 4 + 2]);
-                d0 = __dmul_rn(__dadd_rn(r01.x, q01.x), Sh);
-                d1 = __dmul_rn(__dadd_rn(r01.y, q01.y), Sh);
-                d2 = __dmul_rn(__dadd_rn(r23.x, q23.x), Sh);
-                d3 = __dmul_rn(__dadd_rn(r23.y, q23.y), Sh);
-            }
-            // a repeated symbol continues only paths that ended in a blank (decode.py:192-195); for
-            // the empty labeling (last = 0 by convention) pb == ptot, so the rule is harmless there
-            const double e0 = __dmul_rn(last == 0 ? pb : ptot, d0);
-            const double e1 = __dmul_rn(last == 1 ? pb : ptot, d1);
-            const double e2 = __dmul_rn(last == 2 ? pb : ptot, d2);
-            const double e3 = __dmul_rn(last == 3 ? pb : ptot, d3);
-            const bool order_ok = GBALLOT(kc32 > ksucc || succ == lane) == GBITS;
-            // worst copy of the group: the last lane of the order when the order still holds.
-            // With room left in the beam every extension is a candidate (threshold 1: keys are
-            // or-ed with 1 so that a zero-probability extension of a live beam still counts).
-            uint32_t tau = (prune && kworst > 1u) ? kworst : 1u;
-            // extension keys, zeroed where the extension is merged into a child or the lane is dead
-            const uint32_t x0 = ((uint32_t)__double2hiint(e0) | 1u) & byte_sign_mask<0>(km);
-            const uint32_t x1 = ((uint32_t)__double2hiint(e1) | 1u) & byte_sign_mask<1>(km);
-            const uint32_t x2 = ((uint32_t)__double2hiint(e2) | 1u) & byte_sign_mask<2>(km);
-            const uint32_t x3 = ((uint32_t)__double2hiint(e3) | 1u) & byte_sign_mask<3>(km);
-            const uint32_t xmax = max(max(x0, x1), max(x2, x3));
-            bool full;
-
-            if (__any_sync(kFull, !order_ok)) {
-                // some group's copies changed order: its worst copy is the minimum over the lanes
-                uint32_t tmin = av ? kc32 : 0xffffffffu;
-#pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) {
-                    const uint32_t x = __shfl_xor_sync(kFull, tmin, o);
-                    tmin = x < tmin ? x : tmin;
-                }
-                if (!order_ok) tau = (prune && tmin > 1u) ? tmin : 1u;
-                full = GBALLOT(run && xmax >= tau) != 0u;  // my group needs a full ranking
-                // groups without a competing extension rank their copies on the high words alone
-                sm.k32[li] = kc32;
-                __syncwarp();
-                int cc = 0;
-                const uint4 *kv = reinterpret_cast<const uint4 *>(sm.k32);
-#pragma unroll
-                for (int j = 0; j < G / 4; ++j) {
-                    const uint4 k4 = kv[j];
-                    cc += (k4.x > kc32) + (k4.y > kc32) + (k4.z > kc32) + (k4.w > kc32);
-                }
-                int ssum = av ? cc : 0;
-#pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(kFull, ssum, o);
-                if (!full && !order_ok) {
-                    if (ssum == na * (na - 1) / 2) {
-                        if (av) rank = cc;
-                        ranks_changed = true;
-                    } else {
-                        full = true;  // two copies share a high word: exact ranking below
+                // ==================================================== one frame the long way
+                // Everything is formed again from the scores before the frame (the quiet loop
+                // committed nothing for it).
+                const bool av = alive && run;  // this lane holds a beam that takes part in this frame
+                int rank = sm.c_rank[li];
+                RADIAN_STAT(n_stage2 += 1;)
+                if (LM && __any_sync(kFull, av && rmax_prov)) {
+                    // table bounds that were provisional (the row had not landed when the beam was
+                    // created): take the real ones now
+                    cp_async_wait_all();
+                    if (av && rmax_prov) {
+                        rmax = row_bound(&sm.row[li * 4], km);
+                        rmax_prov = false;
                     }
                 }
-                __syncwarp();
-            } else {
-                full = GBALLOT(run && xmax >= tau) != 0u;
-            }
-
-            if (!__any_sync(kFull, full)) {
-                // (a dead lane's new values are zero as well)
-                ptot = nptot;
-                pnb = npnb;
-                pb = npb;
-            } else {
-                // all groups of the warp go through the ranking; one that did not ask for it has no
-                // extension candidates and gets its current order back
-                ranks_changed = ranks_changed || run;
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) sm.k32[G + e * G + li] = 0u;
-                __syncwarp();
-                int n_ext = 0;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const double ec = c == 0 ? e0 : c == 1 ? e1 : c == 2 ? e2 : e3;
-                    const bool comp = full && (c == 0 ? x0 : c == 1 ? x1 : c == 2 ? x2 : x3) >= tau;
-                    const unsigned bal = GBALLOT(comp);
-                    if (comp) {
-                        const int idx = G + n_ext + __popc(bal & belowg);
-                        const unsigned long long kc = (unsigned long long)__double_as_longlong(ec);
-                        sm.key[idx] = kc;
-                        sm.pos[idx] = (uint16_t)(5 * rank + 1 + c);
-                        sm.src[idx] = (uint8_t)(li * 4 + c);
-                        if (idx < NK) sm.k32[idx] = (uint32_t)(kc >> 32);
-                    }
-                    n_ext += __popc(bal);
+                RESCALE_CHECK();
+                const double *rec = &sm.rec[it * REC];
+                const int *reci = reinterpret_cast<const int *>(rec);
+                const double P4 = rec[4];
+                bool fgate = false;
+                if (LM) fgate = reci[24] != 0;
+                // (a dead lane computes on stale flags; all its scores are zero and stay zero)
+                if (COUNT && LM) {
+                    const int len_c = sm.c_len[li];
+                    const bool lm_copy = av && len_c >= L + 1;  // decode.py:157
+                    const bool lm_ext = av && len_c >= L;       // decode.py:180
+                    n_lookup += __popc(GBALLOT(lm_copy)) + __popc(GBALLOT(lm_ext));
+                    n_combine += __popc(GBALLOT(lm_copy && gcopy && fgate)) + __popc(GBALLOT(lm_ext && gext && fgate));
                 }
-                sm.k32[li] = kc32;
-                sm.lanerank[li] = (uint8_t)rank;
+
+                // COPY (decode.py:150-175)
+                // the empty labeling and dead lanes have pnb == 0, so their copy needs no special case
+                double dl_ = rec[last];
+                // (gcopy implies len >= L+1 and gext implies len >= L: both are set when the beam is created)
+                if (LM && gcopy && fgate) dl_ = __dmul_rn(__dadd_rn(rcopy, rec[6 + last]), rec[11]);  // decode.py:58-61
+                double npnb = __dmul_rn(pnb, dl_);
+                const double npb = __dmul_rn(ptot, P4);
+                double nptot = __dadd_rn(npb, npnb);
+                // a kept beam whose new score is not a normal number although its factors are not zero:
+                // the spread of the beam exceeds what the rescaled float64 scores can express
+                bool lost = av && ((ptot != 0.0 && P4 != 0.0) || (pnb != 0.0 && dl_ != 0.0));
+
+                // MERGE copy(X) with extend(parent(X), last(X)): same dict key in the reference.  The
+                // parent's extension by last(X) is (pr_blank or pr_total of the parent) x the emission
+                // of last(X) in the parent's extend-context, and that emission is this beam's own
+                // copy emission dl_ (same context, same gate, same table value), so only the parent's
+                // two scores travel through shared memory.  Which pairs merge only changes when the
+                // beam set changes: the pairing (plane, prep, km) is state.
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ex_addr), "d"(ptot), "d"(pb) : "memory");
                 __syncwarp();
-                const int m = G + n_ext;
-                int new_rank = 255;
-                bool fast = (m <= NK);
-                {
-                    // rank = number of candidates with a strictly larger high word.  Exact whenever
-                    // the high words of the ranked candidates are all distinct, which the rank sum
-                    // proves (any tie makes the sum fall short of mv(mv-1)/2).
-                    uint32_t ke[EPL];
-                    int ce[EPL];
+                if (av && plane >= 0) {
+                    const double pv = sm.ex[plane * 2 + prep];
+                    const double v = __dmul_rn(pv, dl_);
+                    npnb = __dadd_rn(npnb, v);
+                    nptot = __dadd_rn(nptot, v);
+                    lost = lost || (pv != 0.0 && dl_ != 0.0);
+                }
+                lost = lost && (uint32_t)__double2hiint(nptot) < 0x00100000u;
+
+                // SELECT the best beam_width candidates (decode.py:145, 35-39).
+                // The rank order is kept as state (succ = lane of the next-ranked beam) and re-validated
+                // with one compare per beam; an extension matters only if it is not below the worst
+                // copy of a full beam.
+                const unsigned long long kcopy = (unsigned long long)__double_as_longlong(nptot);
+                const uint32_t kc32 = (uint32_t)(kcopy >> 32);  // zero on a dead lane: its scores are zero
+                const uint32_t ksucc = __shfl_sync(kFull, kc32, succ);
+                const uint32_t kworst = __shfl_sync(kFull, kc32, last_lane);
+                const bool prune = (na >= bw);
+                bool ranks_changed = false;
+
+                // EXTEND (decode.py:177-201)
+                const double2 P01 = *reinterpret_cast<const double2 *>(rec);
+                const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
+                double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
+                if (LM && gext && fgate) {
+                    const double2 q01 = *reinterpret_cast<const double2 *>(rec + 6);
+                    const double2 q23 = *reinterpret_cast<const double2 *>(rec + 8);
+                    const double Sh = rec[11];
+                    const double2 r01 = *reinterpret_cast<const double2 *>(&sm.row[li * 4]);
+                    const double2 r23 = *reinterpret_cast<const double2 *>(&sm.row[li * 4 + 2]);
+                    d0 = __dmul_rn(__dadd_rn(r01.x, q01.x), Sh);
+                    d1 = __dmul_rn(__dadd_rn(r01.y, q01.y), Sh);
+                    d2 = __dmul_rn(__dadd_rn(r23.x, q23.x), Sh);
+                    d3 = __dmul_rn(__dadd_rn(r23.y, q23.y), Sh);
+                }
+                // a repeated symbol continues only paths that ended in a blank (decode.py:192-195); for
+                // the empty labeling (last = 0 by convention) pb == ptot, so the rule is harmless there
+                const double e0 = __dmul_rn(last == 0 ? pb : ptot, d0);
+                const double e1 = __dmul_rn(last == 1 ? pb : ptot, d1);
+                const double e2 = __dmul_rn(last == 2 ? pb : ptot, d2);
+                const double e3 = __dmul_rn(last == 3 ? pb : ptot, d3);
+                const bool order_ok = GBALLOT(kc32 > ksucc || succ == lane) == GBITS;
+                // worst copy of the group: the last lane of the order when the order still holds.
+                // With room left in the beam every extension is a candidate (threshold 1: keys are
+                // or-ed with 1 so that a zero-probability extension of a live beam still counts).
+                uint32_t tau = (prune && kworst > 1u) ? kworst : 1u;
+                // extension keys, zeroed where the extension is merged into a child or the lane is dead
+                const uint32_t x0 = ((uint32_t)__double2hiint(e0) | 1u) & byte_sign_mask<0>(km);
+                const uint32_t x1 = ((uint32_t)__double2hiint(e1) | 1u) & byte_sign_mask<1>(km);
+                const uint32_t x2 = ((uint32_t)__double2hiint(e2) | 1u) & byte_sign_mask<2>(km);
+                const uint32_t x3 = ((uint32_t)__double2hiint(e3) | 1u) & byte_sign_mask<3>(km);
+                const uint32_t xmax = max(max(x0, x1), max(x2, x3));
+                if (!prune) {
+                    // with room in the beam an extension that underflowed would be ranked as a zero
+                    const double pe = ptot != 0.0 ? 1.0 : 0.0;  // (pb != 0 implies ptot != 0)
+                    lost = lost || (av && pe != 0.0 &&
+                                    ((x0 > 1u && x0 < 0x00100000u && d0 != 0.0 && (last == 0 ? pb : ptot) != 0.0) ||
+                                     (x1 > 1u && x1 < 0x00100000u && d1 != 0.0 && (last == 1 ? pb : ptot) != 0.0) ||
+                                     (x2 > 1u && x2 < 0x00100000u && d2 != 0.0 && (last == 2 ? pb : ptot) != 0.0) ||
+                                     (x3 > 1u && x3 < 0x00100000u && d3 != 0.0 && (last == 3 ? pb : ptot) != 0.0)));
+                }
+                if (__any_sync(kFull, lost)) {
+                    if (GBALLOT(lost) != 0u && run) GIVE_UP(RADIAN_READ_RANGE);
+                    REFRESH();
+                    continue;  // the other groups of the warp take this frame again: nothing was committed
+                }
+                // ---- which groups have something to decide
+                bool tied = false;  // two copies share a high word: their order needs all 64 bits
+                int base = rank;    // rank of my copy among the copies (unchanged while the order holds)
+                if (__any_sync(kFull, !order_ok)) {
+                    // some group's copies changed order: its worst copy is the minimum over the lanes,
+                    // and the copies are ranked among themselves on the high words
+                    uint32_t tmin = av ? kc32 : 0xffffffffu;
 #pragma unroll
-                    for (int e = 0; e < EPL; ++e) {
-                        ke[e] = sm.k32[G + e * G + li];
-                        ce[e] = 0;
+                    for (int o = G / 2; o > 0; o >>= 1) {
+                        const uint32_t x = __shfl_xor_sync(kFull, tmin, o);
+                        tmin = x < tmin ? x : tmin;
                     }
+                    if (!order_ok) tau = (prune && tmin > 1u) ? tmin : 1u;
+                    sm.k32[li] = kc32;
+                    __syncwarp();
                     int cc = 0;
                     const uint4 *kv = reinterpret_cast<const uint4 *>(sm.k32);
-                    // the copies, then only as many extension slots as some group of the warp
-                    // filled (the others hold zero and count for nothing)
-                    int jend = n_ext < NK - G ? n_ext : NK - G;
-#pragma unroll
-                    for (int o = 16; o >= G; o >>= 1) {
-                        const int x = __shfl_xor_sync(kFull, jend, o);
-                        jend = x > jend ? x : jend;
-                    }
-                    jend = (G + jend + 3) / 4;
 #pragma unroll
                     for (int j = 0; j < G / 4; ++j) {
                         const uint4 k4 = kv[j];
                         cc += (k4.x > kc32) + (k4.y > kc32) + (k4.z > kc32) + (k4.w > kc32);
-#pragma unroll
-                        for (int e = 0; e < EPL; ++e)
-                            ce[e] += (k4.x > ke[e]) + (k4.y > ke[e]) + (k4.z > ke[e]) + (k4.w > ke[e]);
                     }
-                    for (int j = G / 4; j < jend; ++j) {
-                        const uint4 k4 = kv[j];
-                        cc += (k4.x > kc32) + (k4.y > kc32) + (k4.z > kc32) + (k4.w > kc32);
-#pragma unroll
-                        for (int e = 0; e < EPL; ++e)
-                            ce[e] += (k4.x > ke[e]) + (k4.y > ke[e]) + (k4.z > ke[e]) + (k4.w > ke[e]);
-                    }
+                    // all high words distinct <=> the ranks add up (any tie makes the sum fall short)
                     int ssum = av ? cc : 0;
 #pragma unroll
-                    for (int e = 0; e < EPL; ++e)
-                        if (e * G + li < n_ext) ssum += ce[e];
-#pragma unroll
                     for (int o = G / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(kFull, ssum, o);
-                    const int mv = na + n_ext;
-                    fast = fast && (ssum == mv * (mv - 1) / 2);
-                    if (fast) {
-                        new_rank = av ? cc : 255;
-#pragma unroll
-                        for (int e = 0; e < EPL; ++e)
-                            if (e * G + li < n_ext) sm.rnk[G + e * G + li] = (uint8_t)ce[e];
+                    if (!order_ok) {
+                        base = cc;
+                        tied = ssum != na * (na - 1) / 2;
                     }
                 }
-                if (__any_sync(kFull, run && !fast)) {
-                    // exact path: (score desc, dict insertion position asc) on the full float64 bits;
-                    // a merged copy keeps the earlier of its two insertion positions
-                    if (run && !fast) {
-                        int pos_copy = 5 * rank;
-                        if (av && plane >= 0) {
-                            const int pp = 5 * (int)sm.lanerank[plane] + 1 + last;
+                const bool full = GBALLOT(run && xmax >= tau) != 0u;  // my group has extensions that compete
+
+                if (!__any_sync(kFull, full || !order_ok)) {
+                    // nothing competes after all (the integer bound is conservative) and the order
+                    // holds: (a dead lane's new values are zero as well)
+                    ptot = nptot;
+                    pnb = npnb;
+                    pb = npb;
+                } else {
+                    // Dict insertion position of my copy (decode.py:148-201: parents in rank order, copy
+                    // before its own extensions; a merged entry keeps the earlier of its two positions).
+                    // It decides between candidates whose scores are equal to the last bit.
+                    int pos_copy = kPosInvalid;
+                    if (av) {
+                        pos_copy = 5 * rank;
+                        if (plane >= 0) {
+                            const int pp = 5 * sm.c_rank[plane] + 1 + last;
                             pos_copy = pp < pos_copy ? pp : pos_copy;
                         }
+                    }
+                    bool near = false;
+                    if (__any_sync(kFull, tied)) {
+                        // copies that agree in their high words: exact order of the copies
                         sm.key[li] = kcopy;
-                        sm.pos[li] = av ? (uint16_t)pos_copy : kPosInvalid;
+                        sm.pos[li] = (uint16_t)pos_copy;
+                        __syncwarp();
+                        if (tied && av) {
+                            int cnt = 0;
+                            for (int j = 0; j < G; ++j) {
+                                const int pj = sm.pos[j];
+                                const unsigned long long kj = sm.key[j];
+                                cnt += (pj != kPosInvalid) && (kj > kcopy || (kj == kcopy && pj < pos_copy));
+                                if (COUNT) near = near || (j != li && pj != kPosInvalid && kcopy != 0ull && kj - kcopy + 4096ull < 8192ull);
+                            }
+                            base = cnt;
+                        }
+                        __syncwarp();
+                    }
+                    ranks_changed = run && (full || !order_ok);
+
+                    // ---- the extensions that compete, listed in dict order (parent rank, symbol) is not
+                    // needed: their positions travel with them
+                    int n_ext = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const double ec = c == 0 ? e0 : c == 1 ? e1 : c == 2 ? e2 : e3;
+                        const bool comp = full && (c == 0 ? x0 : c == 1 ? x1 : c == 2 ? x2 : x3) >= tau;
+                        const unsigned bal = GBALLOT(comp);
+                        if (comp) {
+                            const int idx = G + n_ext + __popc(bal & belowg);
+                            sm.key[idx] = (unsigned long long)__double_as_longlong(ec);
+                            sm.pos[idx] = (uint16_t)(5 * rank + 1 + c);
+                            sm.src[idx] = (uint8_t)(li * 4 + c);
+                        }
+                        n_ext += __popc(bal);
+                    }
+                    int nmax = n_ext;
+#pragma unroll
+                    for (int o = 16; o >= G; o >>= 1) {
+                        const int x = __shfl_xor_sync(kFull, nmax, o);
+                        nmax = x > nmax ? x : nmax;
                     }
                     __syncwarp();
-                    bool near = false;
-                    if (run && !fast) {
-                        for (int idx = li; idx < m; idx += G) {
-                            const uint16_t p = sm.pos[idx];
-                            if (p != kPosInvalid) {
-                                const unsigned long long k = sm.key[idx];
-                                int cnt = 0;
-                                for (int j = 0; j < m; ++j) {
-                                    const uint16_t pj = sm.pos[j];
-                                    const unsigned long long kj = sm.key[j];
-                                    cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
-                                    // two candidates within 2^-40 of each other: a decision that the
-                                    // log-domain reference takes on its own rounding noise
-                                    if (COUNT) near = near || (j != idx && pj != kPosInvalid && k != 0ull && kj - k + 4096ull < 8192ull);
+                    const int m = G + n_ext;
+                    int new_rank = av ? base : 255;
+                    int n_new = 0;
+                    if (nmax <= G) {
+                        // The usual case, a handful of extensions: lane e keeps extension e, and every
+                        // extension in turn is compared with all copies and all extensions at once,
+                        // exactly: (float64 bits desc, position asc).  rank of a copy = its rank among
+                        // the copies + the extensions that beat it; of an extension = the copies and
+                        // extensions that beat it.
+                        const bool mine = li < n_ext;
+                        const unsigned long long myk = mine ? sm.key[G + li] : 0ull;
+                        const int myp = mine ? (int)sm.pos[G + li] : kPosInvalid;
+                        int my_rank = 255;
+                        for (int e = 0; e < nmax; ++e) {
+                            const unsigned long long ke = sm.key[G + e];
+                            const int pe = sm.pos[G + e];
+                            const bool valid = e < n_ext;  // (a group with fewer extensions reads leftovers)
+                            const bool ibeat = av && (kcopy > ke || (kcopy == ke && pos_copy < pe));
+                            const bool xbeat = mine && (myk > ke || (myk == ke && myp < pe));
+                            const unsigned b1 = GBALLOT(ibeat), b2 = GBALLOT(xbeat);
+                            if (valid && av && !ibeat) ++new_rank;
+                            if (li == e) my_rank = __popc(b1) + __popc(b2);
+                            // two candidates within 2^-40 of each other: a decision that the log-domain
+                            // reference takes on its own rounding noise
+                            if (COUNT)
+                                near = near || (valid && ke != 0ull &&
+                                                ((av && kcopy - ke + 4096ull < 8192ull) ||
+                                                 (mine && li != e && myk - ke + 4096ull < 8192ull)));
+                        }
+                        const bool isnew = run && mine && my_rank < bw;
+                        const unsigned nbal = GBALLOT(isnew);
+                        if (mine) sm.rnk[G + li] = (uint8_t)my_rank;
+                        if (isnew) sm.newlist[__popc(nbal & belowg)] = (uint8_t)(G + li);
+                        n_new = __popc(nbal);
+                    } else {
+                        // More extensions than lanes (a beam that is still filling up): every candidate
+                        // is ranked against every other one, exactly
+                        sm.key[li] = kcopy;
+                        sm.pos[li] = (uint16_t)pos_copy;
+                        __syncwarp();
+                        if (run) {
+                            for (int idx = li; idx < m; idx += G) {
+                                const int p = sm.pos[idx];
+                                if (p != kPosInvalid) {
+                                    const unsigned long long k = sm.key[idx];
+                                    int cnt = 0;
+                                    for (int j = 0; j < m; ++j) {
+                                        const int pj = sm.pos[j];
+                                        const unsigned long long kj = sm.key[j];
+                                        cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
+                                        if (COUNT) near = near || (j != idx && pj != kPosInvalid && k != 0ull && kj - k + 4096ull < 8192ull);
+                                    }
+                                    sm.rnk[idx] = (uint8_t)(cnt > 255 ? 255 : cnt);
                                 }
-                                sm.rnk[idx] = (uint8_t)(cnt > 255 ? 255 : cnt);
                             }
                         }
-                    }
-                    __syncwarp();
-                    if (run && !fast) new_rank = av ? (int)sm.rnk[li] : 255;
-                    if (COUNT) n_tie += (GBALLOT(near) != 0u);
-                } else {
-                    __syncwarp();
-                }
-
-                const bool survive = av && new_rank < bw;
-                const unsigned evb = GBALLOT(av && !survive);
-                const unsigned survb = GBALLOT(survive);
-                const unsigned freeb = GBITS & ~survb;
-                int mmax = m;
-#pragma unroll
-                for (int o = 16; o >= G; o >>= 1) {
-                    const int x = __shfl_xor_sync(kFull, mmax, o);
-                    mmax = x > mmax ? x : mmax;
-                }
-                int n_new = 0;
-                for (int base = G; base < mmax; base += G) {
-                    const int idx = base + li;
-                    const bool isnew = run && idx < m && sm.rnk[idx] < bw;
-                    const unsigned bal = GBALLOT(isnew);
-                    if (isnew) sm.newlist[n_new + __popc(bal & belowg)] = (uint8_t)idx;
-                    n_new += __popc(bal);
-                }
-
-                if (__any_sync(kFull, n_new > 0)) {
-                    __syncwarp();
-                    const int ford = __popc(freeb & belowg);
-                    const bool take = run && !survive && ford < n_new;
-                    const int item = take ? (int)sm.newlist[ford] : 0;
-                    const int s = take ? (int)sm.src[item] : li * 4;
-                    const int ls = (s >> 2) + gshift;
-                    const int c = s & 3;
-                    // parent state, read before anybody overwrites it
-                    const uint32_t p_ctx = __shfl_sync(kFull, ctx, ls);
-                    const int p_len = __shfl_sync(kFull, len, ls);
-                    const int p_node = __shfl_sync(kFull, node, ls);
-                    const unsigned long long p_h = __shfl_sync(kFull, h, ls);
-                    const int p_last = __shfl_sync(kFull, last, ls);
-                    double p_r = 0.0;
-                    bool p_g = false;
-                    if (LM) {
-                        p_g = __shfl_sync(kFull, (int)gext, ls) != 0;
-                        // every lane waits for its own row first; the parent's row is then complete
-                        cp_async_wait_all();
                         __syncwarp();
-                        if (take && p_g) p_r = sm.row[(ls - gshift) * 4 + c];
-                        __syncwarp();  // all reads of parent rows done before any row is replaced
+                        if (run) new_rank = av ? (int)sm.rnk[li] : 255;
+                        for (int b0 = G; b0 < G + nmax; b0 += G) {
+                            const int idx = b0 + li;
+                            const bool isnew = run && idx < m && sm.rnk[idx] < bw;
+                            const unsigned bal = GBALLOT(isnew);
+                            if (isnew) sm.newlist[n_new + __popc(bal & belowg)] = (uint8_t)idx;
+                            n_new += __popc(bal);
+                        }
                     }
-                    if (survive) {
+                    if (COUNT) n_tie += (GBALLOT(near) != 0u);
+
+                    const bool survive = av && new_rank < bw;
+                    const unsigned evb = GBALLOT(av && !survive);
+                    const unsigned survb = GBALLOT(survive);
+                    const unsigned freeb = GBITS & ~survb;
+
+                    if (__any_sync(kFull, n_new > 0)) {
+                        __syncwarp();
+                        const int ford = __popc(freeb & belowg);
+                        const bool take = run && !survive && ford < n_new;
+                        const int item = take ? (int)sm.newlist[ford] : 0;
+                        const int s = take ? (int)sm.src[item] : li * 4;
+                        const int ls = (s >> 2) + gshift;
+                        const int c = s & 3;
+                        // parent state, read before anybody overwrites it
+                        const int lp = ls - gshift;
+                        const uint32_t p_ctx = sm.c_ctx[lp];
+                        const int p_len = sm.c_len[lp];
+                        const int p_node = sm.c_node[lp];
+                        const unsigned long long p_h = sm.c_h[lp];
+                        const int p_last = __shfl_sync(kFull, last, ls);
+                        double p_r = 0.0;
+                        bool p_g = false;
+                        int keyctx = -1;  // extend-context of my new beam if the model does not hold it
+                        if (LM) {
+                            p_g = __shfl_sync(kFull, (int)gext, ls) != 0;
+                            // every lane waits for its own row first; the parent's row is then complete
+                            cp_async_wait_all();
+                            __syncwarp();
+                            if (take && p_g) p_r = sm.row[(ls - gshift) * 4 + c];
+                        }
+                        __syncwarp();  // all reads of parent rows and parent state done before any is replaced
+                        int mylen = 0;  // length of the beam this lane holds after the frame (orphans and new beams)
+                        unsigned long long myh = 0;
+                        if (survive) {
+                            ptot = nptot;
+                            pnb = npnb;
+                            pb = npb;
+                            rank = new_rank;
+                            if (plane >= 0 && ((evb >> plane) & 1u)) plane = -1;
+                        } else if (take) {
+                            const double sc = __longlong_as_double((long long)sm.key[item]);
+                            ptot = sc;
+                            pnb = sc;
+                            pb = 0.0;
+                            rank = (int)sm.rnk[item];
+                            const int node = top + ford;
+                            const int len = p_len + 1;
+                            const uint32_t ctx = (p_ctx << 2) | (uint32_t)c;
+                            last = c;
+                            myh = hash_step(p_h, c);
+                            mylen = len;
+                            sm.c_node[li] = node;
+                            sm.c_len[li] = len;
+                            sm.c_ctx[li] = ctx;
+                            sm.c_hp[li] = p_h;
+                            sm.c_h[li] = myh;
+                            plane = ((survb >> (ls - gshift)) & 1u) ? (ls - gshift) : -1;
+                            prep = (c == p_last) ? 1 : 0;
+                            alive = true;
+                            arena[node] = ((uint32_t)p_node << 2) | (uint32_t)c;
+                            if (LM) {
+                                gcopy = p_g;
+                                rcopy = p_r;
+                                gext = false;
+                                if (len >= L) {
+                                    const uint32_t ci = ctx & ctx_mask;
+                                    const uint32_t gwd = __ldg(a.gate + (ci >> 5));
+                                    if (a.miss != nullptr && ((__ldg(a.miss + (ci >> 5)) >> (ci & 31u)) & 1u)) keyctx = (int)ci;
+                                    const double *row = a.table + (size_t)ci * 4;
+                                    cp_async<16>(&sm.row[li * 4], row);
+                                    cp_async<16>(&sm.row[li * 4 + 2], row + 2);
+                                    gext = (gwd >> (ci & 31u)) & 1u;
+                                }
+                            }
+                        } else if (run) {
+                            alive = false;
+                            ptot = pnb = pb = 0.0;
+                        }
+                        if (run) {
+                            top += n_new;
+                            na = __popc(survb) + n_new;
+                        }
+                        if (LM && a.miss != nullptr && __any_sync(kFull, keyctx >= 0)) {
+                            // A kept beam whose extend-context the model does not hold: the reference
+                            // raises KeyError at lm[context] (decode.py:83) when it processes the beam
+                            // in the next frame, best rank first; after the last frame it never looks.
+                            int rk = (keyctx >= 0 && tb + it0 + it + 1 < T) ? rank : 0x7fff;
+                            int rmin = rk;
+#pragma unroll
+                            for (int o = G / 2; o > 0; o >>= 1) {
+                                const int x = __shfl_xor_sync(kFull, rmin, o);
+                                rmin = x < rmin ? x : rmin;
+                            }
+                            if (run && rmin != 0x7fff) {
+                                if (rk == rmin) a.out_len[read] = keyctx;  // the context index, for the message
+                                GIVE_UP(RADIAN_READ_KEY_ERROR);
+                            }
+                        }
+                        // A surviving beam whose parent labeling was just (re)created points at it again.
+                        // One 64-bit match over the warp pairs them: a new beam offers hash + (length
+                        // + 1) x K, an orphan asks for parent hash + length x K, everybody else holds a
+                        // value of its own.
+                        {
+                            bool orphan = survive && plane < 0;
+                            if (orphan) mylen = sm.c_len[li];
+                            orphan = orphan && mylen > 0;
+                            if (__any_sync(kFull, orphan)) {
+                                constexpr unsigned long long kLenMix = 0xD6E8FEB86659FD93ull;
+                                unsigned long long mv = 0x8000000000000000ull + (unsigned)lane;
+                                if (orphan) mv = sm.c_hp[li] + (unsigned long long)mylen * kLenMix;
+                                if (take) mv = myh + (unsigned long long)(mylen + 1) * kLenMix;
+                                const unsigned same = __match_any_sync(kFull, mv);
+                                const unsigned cand = same & (GBALLOT(take) << gshift);
+                                const int pl = cand ? __ffs(cand) - 1 : lane;  // (at most one new beam per labeling)
+                                const int z_last = __shfl_sync(kFull, last, pl);
+                                if (orphan && cand) {
+                                    plane = pl - gshift;
+                                    prep = (z_last == last) ? 1 : 0;
+                                }
+                            }
+                        }
+                        // the beam set changed: refresh which extensions are merged into a live child
+                        sm.kill[li] = 0u;
+                        __syncwarp();
+                        if (run && alive && plane >= 0) reinterpret_cast<uint8_t *>(sm.kill)[plane * 4 + last] = 0x80;
+                        __syncwarp();
+                        if (run) km = alive ? (0x80808080u & ~sm.kill[li]) : 0u;
+                        if (LM && run && alive && gext) {
+                            // table part of the quiet-frame bound, over the symbols that are still
+                            // candidates of their own.  The row of a beam created in this frame is in
+                            // flight: until the next frame that comes this way it is bounded by the
+                            // largest entry of the whole table (a.rcap), so nobody waits for a gather.
+                            rmax = take ? a.rcap : row_bound(&sm.row[li * 4], km);
+                            rmax_prov = take;
+                        }
+                    } else if (survive) {
                         ptot = nptot;
                         pnb = npnb;
                         pb = npb;
                         rank = new_rank;
-                        if (plane >= 0 && ((evb >> plane) & 1u)) plane = -1;
-                    } else if (take) {
-                        const double sc = __longlong_as_double((long long)sm.key[item]);
-                        ptot = sc;
-                        pnb = sc;
-                        pb = 0.0;
-                        rank = (int)sm.rnk[item];
-                        node = top + ford;
-                        len = p_len + 1;
-                        ctx = (p_ctx << 2) | (uint32_t)c;
-                        last = c;
-                        hp = p_h;
-                        h = hash_step(p_h, c);
-                        plane = ((survb >> (ls - gshift)) & 1u) ? (ls - gshift) : -1;
-                        prep = (c == p_last) ? 1 : 0;
-                        alive = true;
-                        arena[node] = ((uint32_t)p_node << 2) | (uint32_t)c;
-                        if (LM) {
-                            gcopy = p_g;
-                            rcopy = p_r;
-                            gext = false;
-                            if (len >= L) {
-                                const uint32_t ci = ctx & ctx_mask;
-                                const uint32_t gwd = __ldg(a.gate + (ci >> 5));
-                                const double *row = a.table + (size_t)ci * 4;
-                                cp_async<16>(&sm.row[li * 4], row);
-                                cp_async<16>(&sm.row[li * 4 + 2], row + 2);
-                                gext = (gwd >> (ci & 31u)) & 1u;
-                            }
-                        }
-                    } else if (run) {
-                        alive = false;
-                        ptot = pnb = pb = 0.0;
                     }
+                }
+                if (__any_sync(kFull, ranks_changed)) {
+                    // successor lane of every beam and the lane of the best one
+                    __syncwarp();
+                    if (run && alive) sm.newlist[rank] = (uint8_t)li;
+                    __syncwarp();
                     if (run) {
-                        top += n_new;
-                        na = __popc(survb) + n_new;
+                        succ = (alive && rank + 1 < na) ? (int)sm.newlist[rank + 1] + gshift : lane;
+                        first_lane = (int)sm.newlist[0] + gshift;
+                        last_lane = (int)sm.newlist[na - 1] + gshift;
                     }
-                    // a surviving beam whose parent labeling was just (re)created points at it
-                    // again: the new beams publish hash + length, every orphan compares its parent
-                    // hash with them
-                    if (__any_sync(kFull, survive && plane < 0 && len > 0)) {
-                        __syncwarp();  // this frame's readers of key / k32 / lanerank are done
-                        if (take) {
-                            sm.key[ford] = h;
-                            sm.k32[ford] = (uint32_t)len | ((uint32_t)last << 30);  // len < 2^29 (arena limit)
-                            sm.lanerank[ford] = (uint8_t)li;
-                        }
-                        int nmax = n_new;
-#pragma unroll
-                        for (int o = 16; o >= G; o >>= 1) {
-                            const int x = __shfl_xor_sync(kFull, nmax, o);
-                            nmax = x > nmax ? x : nmax;
-                        }
-                        __syncwarp();
-                        for (int k = 0; k < nmax; ++k) {
-                            const unsigned long long zh = sm.key[k];
-                            const uint32_t zw = sm.k32[k];
-                            const int zlen = (int)(zw & 0x3fffffffu);
-                            if (k < n_new && survive && plane < 0 && len == zlen + 1 && hp == zh) {
-                                plane = (int)sm.lanerank[k];
-                                prep = ((int)(zw >> 30) == last) ? 1 : 0;
-                            }
-                        }
-                    }
-                    // the beam set changed: refresh which extensions are merged into a live child
-                    sm.kill[li] = 0u;
                     __syncwarp();
-                    if (run && alive && plane >= 0) reinterpret_cast<uint8_t *>(sm.kill)[plane * 4 + last] = 0x80;
-                    __syncwarp();
-                    if (run) km = alive ? (0x80808080u & ~sm.kill[li]) : 0u;
-                    rmax = kNoRmax;  // the merge mask (or the beam) changed
-                } else if (survive) {
-                    ptot = nptot;
-                    pnb = npnb;
-                    pb = npb;
-                    rank = new_rank;
                 }
-            }
-            if (__any_sync(kFull, ranks_changed)) {
-                // successor lane of every beam and the lane of the best one
-                __syncwarp();
-                if (run && alive) sm.newlist[rank] = (uint8_t)li;
-                __syncwarp();
-                if (run) {
-                    succ = (alive && rank + 1 < na) ? (int)sm.newlist[rank + 1] + gshift : lane;
-                    first_lane = (int)sm.newlist[0] + gshift;
-                    last_lane = (int)sm.newlist[na - 1] + gshift;
-                }
-                __syncwarp();
+                sm.c_rank[li] = rank;
+                REFRESH();
+                ++it;
             }
         }
         if (live) t += nrun;
@@ -796,9 +951,9 @@ decode_kernel(const DecodeArgs a)
             const long long seq_cap = a.seq_offsets[read + 1] - seq_off;
             const double ln2 = 0.693147180559945309417;
             if (status == 0 && lane == first_lane) {
-                const long long n = len;
+                const long long n = sm.c_len[li];
                 if (n > seq_cap) status = RADIAN_READ_SEQ_OVERFLOW;
-                int c = node;
+                int c = sm.c_node[li];
                 for (long long i = n - 1; i >= 0; --i) {
                     const uint32_t w = arena[c] & 0x7fffffffu;
                     if (i < seq_cap) a.out_seq[seq_off + i] = (uint8_t)(w & 3u);
@@ -812,13 +967,13 @@ decode_kernel(const DecodeArgs a)
                     a.out_counters[4 * read] = n_lookup;
                     a.out_counters[4 * read + 1] = n_combine;
                     a.out_counters[4 * read + 2] = n_tie;
-                    a.out_counters[4 * read + 3] = 0;
+                    a.out_counters[4 * read + 3] = n_stage2;
                 }
             }
             if (status == 0 && succ_first != first_lane && lane == succ_first)
                 a.out_score[2 * read + 1] = (ptot > 0.0) ? log(ptot) + (double)kacc * ln2 : -INFINITY;
-            if (status == RADIAN_READ_TRIE_OVERFLOW && li == 0) {
-                a.out_len[read] = 0;
+            if (status > RADIAN_READ_SEQ_OVERFLOW && li == 0) {
+                if (status != RADIAN_READ_KEY_ERROR) a.out_len[read] = 0;  // (KeyError: holds the context index)
                 a.out_score[2 * read] = NAN;
                 a.out_score[2 * read + 1] = NAN;
                 a.out_status[read] = status;
@@ -832,6 +987,9 @@ decode_kernel(const DecodeArgs a)
         }
     }
 #undef GBALLOT
+#undef REFRESH
+#undef GIVE_UP
+#undef RESCALE_CHECK
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -927,19 +1085,67 @@ int decode_max_slots(int device, int beam_width)
     return best;
 }
 
+// Resident CTAs per SM.  A warp alone on its scheduler needs about kLone cycles per frame (the
+// dependency chain of a frame; the frames that change the beam set are long); every further warp on
+// the scheduler adds about kShare cycles to everybody's frame (measured, scripts/ab_occupancy.sh).
+// Throughput therefore keeps growing with occupancy, but so does the time of the longest read, and a
+// batch that does not fill the machine many times over is finished when its longest read is.
+// Estimated time at w CTAs per SM (list-scheduling bound):
+//   (frames of the longest read + total frames / read slots(w)) x (kLone + (w - 1) x kShare).
+static int pick_ctas_per_sm(int max_ctas, int groups_per_block, int sm_count, int n_reads, int64_t max_frames,
+                            int64_t total_frames)
+{
+    static const char *env = getenv("RADIAN_CTAS_PER_SM");
+    if (env && atoi(env) > 0) return atoi(env) < max_ctas ? atoi(env) : max_ctas;
+    if (total_frames <= 0) total_frames = (int64_t)n_reads * max_frames;  // unknown: all reads as long as the longest
+    static const char *e1 = getenv("RADIAN_TUNE_LONE"), *e2 = getenv("RADIAN_TUNE_SHARE");
+    const double lone = e1 ? atof(e1) : 930.0, share = e2 ? atof(e2) : 260.0;
+    int best = max_ctas;
+    double best_t = 0;
+    for (int w = max_ctas; w >= 1; --w) {  // (ties go to the higher occupancy)
+        const double slots = (double)sm_count * w * groups_per_block;
+        const double est = ((double)max_frames + (double)total_frames / slots) * (lone + (w - 1) * share);
+        if (w == max_ctas || est < best_t) {
+            best_t = est;
+            best = w;
+        }
+    }
+    return best;
+}
+
 int decode_launch(const DecodeArgs &a, bool f64, int device, cudaStream_t stream)
 {
     const bool lm = a.table != nullptr;
     DecodeLaunch dl;
     int rc = decode_pick(device, a.beam_width, lm, f64, a.out_counters != nullptr, a.ready != nullptr, &dl);
     if (rc) return rc;
+    DeviceInfo di;
+    rc = device_info(device, &di);
+    if (rc) return rc;
+    int per_sm = dl.grid / di.sm_count;
+    if (a.beam_width <= 32 && a.ready == nullptr)  // (streamed batches arrive over time: keep every slot)
+        per_sm = pick_ctas_per_sm(per_sm, dl.groups_per_block, di.sm_count, a.n_reads, a.max_frames, a.total_frames);
     // no more groups than reads: extra CTAs would only touch the queue
     int64_t need = ((int64_t)a.n_reads + dl.groups_per_block - 1) / dl.groups_per_block;
-    int grid = (int)(need < dl.grid ? need : dl.grid);
+    const int64_t cap = (int64_t)di.sm_count * per_sm;
+    int grid = (int)(need < cap ? need : cap);
     if (grid < 1) grid = 1;
+    size_t smem = dl.smem;
+    if (per_sm < dl.grid / di.sm_count && need >= cap) {
+        // fewer CTAs per SM than would fit: pad the request with unused dynamic shared memory so that
+        // exactly per_sm of them fit an SM and the hardware spreads the grid evenly
+        cudaFuncAttributes fa;
+        RADIAN_CUDA(cudaFuncGetAttributes(&fa, dl.kernel));
+        const size_t per_cta = (size_t)di.smem_per_sm / per_sm;
+        const size_t fixed = fa.sharedSizeBytes + 1024;  // static + the 1 KB the system reserves per CTA
+        size_t dyn = per_cta > fixed ? ((per_cta - fixed) & ~(size_t)127) : 0;
+        if (dyn + fa.sharedSizeBytes > (size_t)di.max_smem_optin) dyn = (size_t)di.max_smem_optin - fa.sharedSizeBytes;
+        RADIAN_CUDA(cudaFuncSetAttribute(dl.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        smem = dyn;
+    }
     DecodeArgs args = a;
     void *params[] = {(void *)&args};
-    RADIAN_CUDA(cudaLaunchKernel(dl.kernel, dim3(grid), dim3(dl.block), params, dl.smem, stream));
+    RADIAN_CUDA(cudaLaunchKernel(dl.kernel, dim3(grid), dim3(dl.block), params, smem, stream));
     return 0;
 }
 

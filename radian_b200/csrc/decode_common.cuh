@@ -35,6 +35,32 @@ __device__ __forceinline__ unsigned long long hash_step(unsigned long long h, in
     return h ^ (h >> 29);
 }
 
+// shared-memory loads by 32-bit shared address (the quiet loop of decode.cu keeps its addresses that way)
+__device__ __forceinline__ double lds_f64(unsigned addr)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64_volatile(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_i32(unsigned addr)
+{
+    int v;
+    asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int4 lds_i4(unsigned addr)
+{
+    int4 v;
+    asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 // Asynchronous global -> shared copies (LDGSTS): no register staging, completion awaited with
 // cp_async_wait_all() by the issuing thread right before the data is needed.
 template <int BYTES>
@@ -67,32 +93,80 @@ __device__ __forceinline__ void prefetch_row(PT *dst, const PT *post, long long 
 // the hardware log decides it unless it lands within 1e-4 of the threshold, in which case the
 // reference's exact operation order is evaluated.
 //
-// EXT adds what decode.cu's quiet-frame test reads instead of the float64 values: the high words
-// of P0..P3 (int4 at double index 12 with the model, 6 without), of q0..q3 (int4 at 14), and
-// {gate, high word of S minus the exponent bias} (int2 at 16); rec[11] = S/2 (exact), so that
-// combine_dists' ((r + q)/2)*S is one add and one multiply: (r + q)*(S/2) rounds identically.
-template <bool LM, bool EXT>
+// Record layout (doubles; LM: 18 per frame, no model: 10):
+//   rec[0..4]  P0..P3, blank           rec[5]  entropy gate as 1.0 / 0.0
+//   rec[6..9]  p/S (gate open) or P0..P3 again (closed)      rec[10] 1.0
+//   rec[11]    S/2 (gate open; combine_dists' ((r + q)/2)*S is (r + q)*(S/2), which rounds
+//              identically) or 1.0 (closed)
+//   ints 24..27 (12..15 without the model): high words of P0..P3;  ints 28..31: of p/S;
+//   ints 32..35 (int 10 without the model): words of the quiet-frame test, see record_ext.
+// COMPACT (decode.cu) leaves the two arrays of high words out: 14 doubles per frame with the model
+// (test words at ints 24..27), 6 without (test word at int 10).
+// slack of the integer bound (see decode.cu): 2 * 0.0861 * 2^20 for p * P_c, one more 0.0861 for the
+// max(r, q) * S bound of a gated extension; both minus the exponent bias of one float64 factor
+constexpr int kSlackPlain = 181000 - 0x3ff00000;
+constexpr int kSlackGated = 272000 - 0x3ff00000;
+
+template <bool LM, bool EXT, bool COMPACT>
 __device__ __forceinline__ void record_ext(double *rec, const double *v, const double *q, double S, bool gate)
 {
     if (EXT) {
         int *ri = reinterpret_cast<int *>(rec);
-        *reinterpret_cast<int4 *>(ri + (LM ? 24 : 12)) =
-            make_int4(__double2hiint(v[0]), __double2hiint(v[1]), __double2hiint(v[2]), __double2hiint(v[3]));
+        const int h0 = __double2hiint(v[0]), h1 = __double2hiint(v[1]), h2 = __double2hiint(v[2]), h3 = __double2hiint(v[3]);
+        if (!COMPACT) *reinterpret_cast<int4 *>(ri + (LM ? 24 : 12)) = make_int4(h0, h1, h2, h3);
+        // first-stage bound of decode.cu's quiet-frame test: the largest high word over all four
+        // symbols, with the slack and the bias folded in
+        const int hmaxP = max(max(h0, h1), max(h2, h3)) + kSlackPlain;
         if (LM) {
-            rec[11] = 0.5 * S;
-            *reinterpret_cast<int4 *>(ri + 28) =
-                make_int4(__double2hiint(q[0]), __double2hiint(q[1]), __double2hiint(q[2]), __double2hiint(q[3]));
-            *reinterpret_cast<int2 *>(ri + 32) = make_int2(gate ? 1 : 0, __double2hiint(S) - 0x3ff00000);
+            // rec[6..9] and rec[11] are only meant for frames whose entropy gate is open; with the
+            // gate closed they repeat P0..P3 and hold 1.0, and rec[10] is always 1.0: decode.cu's
+            // copy emission (rcopy * rec[5] + rec[x]) * rec[y] then needs no branch (x, y per lane)
+            rec[10] = 1.0;
+            rec[11] = gate ? 0.5 * S : 1.0;
+            if (!gate) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rec[6 + i] = v[i];
+            }
+            const int g0 = __double2hiint(q[0]), g1 = __double2hiint(q[1]), g2 = __double2hiint(q[2]), g3 = __double2hiint(q[3]);
+            if (!COMPACT) *reinterpret_cast<int4 *>(ri + 28) = make_int4(g0, g1, g2, g3);
+            // {gate, hS, zP, zQ}: hS = high word of S + slack - 2 x bias; zP / zQ = first-stage words
+            // of a plain / gated lane, which takes max(zQ, rmax) + hS.  With the gate closed zQ is
+            // larger than any rmax and hS brings the sum back to zP (modulo 2^32).
+            const int hS = __double2hiint(S) - 0x3ff00000 + kSlackGated;
+            const int zQ = max(max(g0, g1), max(g2, g3));
+            *reinterpret_cast<int4 *>(ri + (COMPACT ? 24 : 32)) = gate ? make_int4(1, hS, hmaxP, zQ)
+                                                      : make_int4(0, (int)((unsigned)hmaxP - 0x7ff00000u), hmaxP, 0x7ff00000);
+        } else {
+            ri[10] = hmaxP;
         }
     }
 }
 
-template <bool LM, bool EXT = false>
-__device__ __forceinline__ void make_record(const double *raw, double s_thr, double *rec)
+// SCALE (float64 input only): a row whose largest entry is below 2^-64 is multiplied by an exact
+// power of two that brings it near 1; the exponent is returned and the caller adds it to the
+// read's score exponent.  Every quantity the search derives from the row (S, p/S, the entropy
+// gate, combine_dists) is invariant or scales exactly with it, so the result is the one the
+// reference computes in the log domain, where magnitude is no issue (decode.py:16-17).  Rows of
+// softmax outputs are never touched.  Returns k such that stored row = true row x 2^k.
+template <bool LM, bool EXT = false, bool SCALE = false, bool COMPACT = false>
+__device__ __forceinline__ int make_record(const double *raw, double s_thr, double *rec)
 {
     double v[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) v[i] = raw[i];
+    int k = 0;
+    if (SCALE) {
+        int emax = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) emax = max(emax, (__double2hiint(v[i]) >> 20) & 0x7ff);
+        if (emax < 1023 - 64) {
+            // subnormal rows first come up by 2^1000 (exact), the next rescale does the rest
+            k = emax == 0 ? 1000 : 1022 - emax;
+            const double sc = __hiloint2double((1023 + k) << 20, 0);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) v[i] = __dmul_rn(v[i], sc);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 5; ++i) rec[i] = v[i];
     if (LM) {
@@ -106,7 +180,6 @@ __device__ __forceinline__ void make_record(const double *raw, double s_thr, dou
             const float qf = (float)q[i];
             if (qf > 0.0f) Ha -= qf * __logf(qf);
         }
-        rec[10] = S;
         bool gate = Ha > (float)s_thr;
         if (!(fabsf(Ha - (float)s_thr) > 1e-4f)) {
             double H = 0.0;
@@ -116,14 +189,15 @@ __device__ __forceinline__ void make_record(const double *raw, double s_thr, dou
             gate = -H > s_thr;
         }
         rec[5] = gate ? 1.0 : 0.0;
-        record_ext<LM, EXT>(rec, v, q, S, gate);
+        record_ext<LM, EXT, COMPACT>(rec, v, q, S, gate);
     } else {
-        record_ext<LM, EXT>(rec, v, v, 0.0, false);
+        record_ext<LM, EXT, COMPACT>(rec, v, v, 0.0, false);
     }
+    return k;
 }
 
-template <bool LM, bool EXT = false>
-__device__ __forceinline__ void make_record(const float *raw, double s_thr, double *rec)
+template <bool LM, bool EXT = false, bool SCALE = false, bool COMPACT = false>
+__device__ __forceinline__ int make_record(const float *raw, double s_thr, double *rec)
 {
     float v[5];
 #pragma unroll
@@ -140,7 +214,6 @@ __device__ __forceinline__ void make_record(const float *raw, double s_thr, doub
             rec[6 + i] = (double)q[i];
             if (q[i] > 0.0f) Ha -= q[i] * __logf(q[i]);
         }
-        rec[10] = (double)S;
         bool gate = Ha > (float)s_thr;
         if (!(fabsf(Ha - (float)s_thr) > 1e-4f)) {
             float H = 0.0f;
@@ -152,11 +225,12 @@ __device__ __forceinline__ void make_record(const float *raw, double s_thr, doub
         rec[5] = gate ? 1.0 : 0.0;
         const double vd[4] = {(double)v[0], (double)v[1], (double)v[2], (double)v[3]};
         const double qd[4] = {(double)q[0], (double)q[1], (double)q[2], (double)q[3]};
-        record_ext<LM, EXT>(rec, vd, qd, (double)S, gate);
+        record_ext<LM, EXT, COMPACT>(rec, vd, qd, (double)S, gate);
     } else {
         const double vd[4] = {(double)v[0], (double)v[1], (double)v[2], (double)v[3]};
-        record_ext<LM, EXT>(rec, vd, vd, 0.0, false);
+        record_ext<LM, EXT, COMPACT>(rec, vd, vd, 0.0, false);
     }
+    return 0;  // float32-derived probabilities are >= 2^-149: no row scaling needed
 }
 
 }  // namespace radian

@@ -303,7 +303,8 @@ decode_wide_kernel(const DecodeArgs a)
                     int z = max(max(hx.x & (int)byte_sign_mask<0>(km[s]), hx.y & (int)byte_sign_mask<1>(km[s])),
                                 max(hx.z & (int)byte_sign_mask<2>(km[s]), hx.w & (int)byte_sign_mask<3>(km[s])));
                     if (LM && gated) z = max(z, rmax[s]) + hS;
-                    const int ub = __double2hiint(ptot[s]) + z + (((LM && gated) ? 272000 : 181000) - 0x3ff00000);
+                    // (the gated slack is folded into the record's hS word, decode_common.cuh)
+                    const int ub = __double2hiint(ptot[s]) + z + ((LM && gated) ? 0 : kSlackPlain);
                     quiet = quiet && ub < hw;
                 }
                 if (__all_sync(kFull, quiet)) {
@@ -525,6 +526,7 @@ decode_wide_kernel(const DecodeArgs a)
                     int ford[BPL], item[BPL];
                     double p_r[BPL];
                     int fbase = 0;
+                    int keyctx = -1, keyrank = 0x7fff;  // best-ranked new beam of this lane whose context the model lacks
 #pragma unroll
                     for (int s = 0; s < BPL; ++s) {
                         const unsigned freeb = ~survb[s];
@@ -584,6 +586,11 @@ decode_wide_kernel(const DecodeArgs a)
                                 if (len[s] >= L) {
                                     const uint32_t ci = ctx[s] & ctx_mask;
                                     const uint32_t gwd = __ldg(a.gate + (ci >> 5));
+                                    if (a.miss != nullptr && ((__ldg(a.miss + (ci >> 5)) >> (ci & 31u)) & 1u) &&
+                                        rank[s] < keyrank) {
+                                        keyrank = rank[s];
+                                        keyctx = (int)ci;
+                                    }
                                     const double *row = a.table + (size_t)ci * 4;
                                     cp_async<16>(&sm.row[b * 4], row);
                                     cp_async<16>(&sm.row[b * 4 + 2], row + 2);
@@ -597,6 +604,21 @@ decode_wide_kernel(const DecodeArgs a)
                     }
                     top += n_new;
                     na = n_surv + n_new;
+                    if (LM && a.miss != nullptr && t + 1 < T) {
+                        // a kept beam whose extend-context the model does not hold: KeyError at
+                        // lm[context] when the reference processes it in the next frame, best rank
+                        // first (decode.py:83); after the last frame it never looks
+                        int rmin = keyrank;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const int x = __shfl_xor_sync(kFull, rmin, o);
+                            rmin = x < rmin ? x : rmin;
+                        }
+                        if (rmin != 0x7fff) {
+                            if (keyrank == rmin) a.out_len[read] = keyctx;  // the context index, for the message
+                            status = RADIAN_READ_KEY_ERROR;
+                        }
+                    }
                     __syncwarp();  // parents' staged values have been consumed
                     // a surviving beam whose parent labeling was just (re)created points at it again
 #pragma unroll
@@ -699,7 +721,7 @@ decode_wide_kernel(const DecodeArgs a)
                     a.out_score[2 * read + 1] = (ptot[s] > 0.0) ? log(ptot[s]) + (double)kacc * ln2 : -INFINITY;
             }
         } else if (lane == 0) {
-            a.out_len[read] = 0;
+            if (status != RADIAN_READ_KEY_ERROR) a.out_len[read] = 0;  // (KeyError: holds the context index)
             a.out_score[2 * read] = NAN;
             a.out_score[2 * read + 1] = NAN;
             a.out_status[read] = status;

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <mutex>
+#include <vector>
 
 #include "radian_b200.h"
 
@@ -21,30 +22,47 @@ int cuda_fail(cudaError_t e, const char *what);
 struct DeviceInfo {
     int sm_count;
     int max_smem_optin;
+    int smem_per_sm;
 };
 int device_info(int device, DeviceInfo *out);
-int keep_pool(int device);
+// this library's private stream-ordered memory pool on `device` (created on first use)
+int keep_pool(int device, cudaMemPool_t *pool);
 // One host entry point at a time per device: while a streamed decode kernel waits for its input,
 // no other thread of this library may allocate, free or launch on that device.
 std::mutex &host_mutex(int device);
 
 }  // namespace radian
 
+// One gate mask per r_threshold the table has been used with: bit i = entropy(row i) < threshold
+// (decode.py:93).  Masks are immutable once built; `ready` is recorded behind the kernel that fills
+// the mask and every consuming stream waits for it.
+struct GateMask {
+    double threshold;
+    uint32_t *d_bits;
+    cudaEvent_t ready;
+    unsigned long long last_use;
+};
+
 struct radian_table {
-    int L;
-    int device;
-    size_t rows;
-    double *d_rows;      // rows x 4 float64 linear probabilities
-    double *d_entropy;   // rows float64, reference entropy() of each row (host libm)
-    uint32_t *d_gate;    // rows/32 words: bit = entropy < gate_threshold
-    double gate_threshold;
-    int gate_valid;
+    int L = 0;
+    int device = 0;
+    size_t rows = 0;
+    double *d_rows = nullptr;     // rows x 4 float64 linear probabilities
+    double *d_entropy = nullptr;  // rows float64, reference entropy() of each row (host libm)
+    uint32_t *d_miss = nullptr;   // rows/32 words, bit = context absent from the model (KeyError when a
+                                  // kept beam reaches it, decode.py:83); nullptr for a complete table
+    int rcap = 0;                 // high word of the largest entry of d_rows
+    mutable std::mutex mu;        // guards the mask cache below
+    mutable std::vector<GateMask> gates;
+    mutable unsigned long long tick = 0;
 };
 
 namespace radian {
 
-// (re)build table->d_gate for r_threshold on `stream` if it is not current
-int table_prepare_gate(radian_table *t, double r_threshold, cudaStream_t stream);
+// gate mask of `t` for r_threshold, built on `stream` if this threshold is new; `stream` is made to
+// wait for the mask either way.  Calls with different thresholds on different streams do not
+// disturb each other (a small LRU of masks).
+int table_get_gate(const radian_table *t, double r_threshold, cudaStream_t stream, const uint32_t **d_bits);
 
 struct DecodeArgs {
     const void *post;
@@ -52,9 +70,13 @@ struct DecodeArgs {
     const int32_t *order;
     int n_reads;
     int beam_width;
+    int64_t max_frames;      // frames of the longest read (launch shape only)
+    int64_t total_frames;    // frames of all reads, 0 = unknown (launch shape only)
     const double *table;     // nullptr = LM off
     const uint32_t *gate;
+    const uint32_t *miss;    // optional: contexts absent from the model (radian_table::d_miss)
     int L;
+    int rcap;                // high word of the largest table entry: bound of a row that is still in flight
     double s_thr;
     uint8_t *out_seq;
     const int64_t *seq_offsets;

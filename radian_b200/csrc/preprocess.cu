@@ -360,8 +360,9 @@ extern "C" int radian_normalise_batch_host(const int16_t *signal, const int64_t 
     const int64_t total = offsets[n_reads] - offsets[0];
     std::lock_guard<std::mutex> host_lock(host_mutex(device));
     RADIAN_CUDA(cudaSetDevice(device));
+    cudaMemPool_t pool_ = nullptr;  // this library's own stream-ordered pool on the device
     {
-        int krc = keep_pool(device);
+        int krc = keep_pool(device, &pool_);
         if (krc) return krc;
     }
     cudaStream_t st = nullptr;
@@ -376,11 +377,11 @@ extern "C" int radian_normalise_batch_host(const int16_t *signal, const int64_t 
     cudaError_t e;
 #define TRY(x)                                   \
     if (ret == RADIAN_OK && (e = (x)) != cudaSuccess) ret = cuda_fail(e, #x)
-    TRY(cudaMallocAsync(&d_sig, (size_t)(total ? total : 1) * 2, st));
-    TRY(cudaMallocAsync(&d_off, (size_t)(n_reads + 1) * 8, st));
-    TRY(cudaMallocAsync(&d_out, (size_t)(total ? total : 1) * 8, st));
-    TRY(cudaMallocAsync(&d_int, (size_t)n_reads * 4, st));
-    TRY(cudaMallocAsync(&d_status, (size_t)n_reads * 4, st));
+    TRY(cudaMallocFromPoolAsync(&d_sig, (size_t)(total ? total : 1) * 2, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_off, (size_t)(n_reads + 1) * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_out, (size_t)(total ? total : 1) * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_int, (size_t)n_reads * 4, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_status, (size_t)n_reads * 4, pool_, st));
     if (total) TRY(cudaMemcpyAsync(d_sig, signal + offsets[0], (size_t)total * 2, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_off, rel.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     if (ret == RADIAN_OK)
@@ -419,8 +420,9 @@ extern "C" int radian_windows_batch_host(const double *norm, const int64_t *offs
     const int64_t n_win = window_offsets[n_reads] - window_offsets[0];
     std::lock_guard<std::mutex> host_lock(host_mutex(device));
     RADIAN_CUDA(cudaSetDevice(device));
+    cudaMemPool_t pool_ = nullptr;  // this library's own stream-ordered pool on the device
     {
-        int krc = keep_pool(device);
+        int krc = keep_pool(device, &pool_);
         if (krc) return krc;
     }
     cudaStream_t st = nullptr;
@@ -433,10 +435,10 @@ extern "C" int radian_windows_batch_host(const double *norm, const int64_t *offs
     cudaError_t e;
 #define TRY(x)                                   \
     if (ret == RADIAN_OK && (e = (x)) != cudaSuccess) ret = cuda_fail(e, #x)
-    TRY(cudaMallocAsync(&d_in, (size_t)(total ? total : 1) * 8, st));
-    TRY(cudaMallocAsync(&d_out, (size_t)(n_win ? n_win : 1) * window * 8, st));
-    TRY(cudaMallocAsync(&d_off, (size_t)(n_reads + 1) * 8, st));
-    TRY(cudaMallocAsync(&d_woff, (size_t)(n_reads + 1) * 8, st));
+    TRY(cudaMallocFromPoolAsync(&d_in, (size_t)(total ? total : 1) * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_out, (size_t)(n_win ? n_win : 1) * window * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_off, (size_t)(n_reads + 1) * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_woff, (size_t)(n_reads + 1) * 8, pool_, st));
     if (total) TRY(cudaMemcpyAsync(d_in, norm + offsets[0], (size_t)total * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_off, rel.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_woff, wrel.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));

@@ -390,8 +390,9 @@ extern "C" int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *
     }
     std::lock_guard<std::mutex> host_lock(host_mutex(device));
     RADIAN_CUDA(cudaSetDevice(device));
+    cudaMemPool_t pool_ = nullptr;  // this library's own stream-ordered pool on the device
     {
-        int krc = keep_pool(device);
+        int krc = keep_pool(device, &pool_);
         if (krc) return krc;
     }
     static const bool trace = getenv("RADIAN_TRACE") != nullptr;
@@ -410,16 +411,16 @@ extern "C" int radian_stitch_batch_host(const uint8_t *frag_sym, const int64_t *
     cudaError_t e;
 #define TRY(x)                                   \
     if (ret == RADIAN_OK && (e = (x)) != cudaSuccess) ret = cuda_fail(e, #x)
-    TRY(cudaMallocAsync(&d_sym, (size_t)(n_sym ? n_sym : 1), st));
-    TRY(cudaMallocAsync(&d_seq, (size_t)(total_slots ? total_slots : 1), st));
-    TRY(cudaMallocAsync(&d_fstart, (size_t)n_frags * 8, st));
-    TRY(cudaMallocAsync(&d_flen, (size_t)n_frags * 8, st));
-    TRY(cudaMallocAsync(&d_rfr, (size_t)(n_reads + 1) * 8, st));
-    TRY(cudaMallocAsync(&d_ooff, (size_t)(n_reads + 1) * 8, st));
-    TRY(cudaMallocAsync(&d_len, (size_t)n_reads * 8, st));
-    TRY(cudaMallocAsync(&d_status, (size_t)n_reads * 4, st));
-    TRY(cudaMallocAsync(&d_ws, ws_bytes, st));
-    if (out_votes) TRY(cudaMallocAsync(&d_counts, (size_t)(total_slots ? total_slots : 1) * 16, st));
+    TRY(cudaMallocFromPoolAsync(&d_sym, (size_t)(n_sym ? n_sym : 1), pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_seq, (size_t)(total_slots ? total_slots : 1), pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_fstart, (size_t)n_frags * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_flen, (size_t)n_frags * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_rfr, (size_t)(n_reads + 1) * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_ooff, (size_t)(n_reads + 1) * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_len, (size_t)n_reads * 8, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_status, (size_t)n_reads * 4, pool_, st));
+    TRY(cudaMallocFromPoolAsync(&d_ws, ws_bytes, pool_, st));
+    if (out_votes) TRY(cudaMallocFromPoolAsync(&d_counts, (size_t)(total_slots ? total_slots : 1) * 16, pool_, st));
     if (n_sym) TRY(cudaMemcpyAsync(d_sym, frag_sym, (size_t)n_sym, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_fstart, frag_offsets, (size_t)n_frags * 8, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(d_flen, flen.data(), (size_t)n_frags * 8, cudaMemcpyHostToDevice, st));

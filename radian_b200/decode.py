@@ -26,7 +26,9 @@ class RnaTable:
     2-bit packed context (oldest symbol most significant, basecall.py:54-57), plus the row
     entropies the reference memoises in ``entr_cache`` (decode.py:86-90)."""
 
-    def __init__(self, dense: np.ndarray, device: int = 0):
+    def __init__(self, dense: np.ndarray, device: int = 0, present: "np.ndarray | None" = None):
+        """``present``: optional (4**L,) mask of the contexts the model holds; a read whose search
+        reaches an absent one fails with the reference's KeyError (decode.py:83)."""
         dense = np.ascontiguousarray(dense, dtype=np.float64)
         if dense.ndim != 2 or dense.shape[1] != 4:
             raise ValueError("table must have shape (4**L, 4)")
@@ -36,8 +38,16 @@ class RnaTable:
         if 4 ** L != dense.shape[0] or L < 1:
             raise ValueError(f"table has {dense.shape[0]} rows, not a power of 4")
         h = ctypes.c_void_p()
-        _native.check(lib.radian_table_create(_native.np_ptr(dense), L, int(device), ctypes.byref(h)))
+        if present is not None:
+            present = np.ascontiguousarray(present, dtype=np.uint8)
+            if present.shape != (dense.shape[0],):
+                raise ValueError("present must have one entry per context")
+            if present.all():
+                present = None
+        _native.check(lib.radian_table_create_sparse(_native.np_ptr(dense), _native.np_ptr(present), L, int(device),
+                                                     ctypes.byref(h)))
         self._h = h
+        self.complete = present is None
         self.L = L
         self.device = int(device)
 
@@ -45,10 +55,11 @@ class RnaTable:
     def from_dict(cls, lm: dict, len_context: int, device: int = 0) -> "RnaTable":
         """Dense copy of the dict built at basecall.py:50-57 ({tuple of ints: [pA,pC,pG,pT]}).
         A context missing from the dict is a KeyError in the reference when the search first
-        visits it (decode.py:83); here it is raised up front."""
+        visits it (decode.py:83), and so it is here: absent contexts are marked in the table and a
+        read that reaches one raises KeyError(context)."""
         L = int(len_context)
         n = 4 ** L
-        dense = np.empty((n, 4), dtype=np.float64)
+        dense = np.full((n, 4), 0.25, dtype=np.float64)
         seen = np.zeros(n, dtype=bool)
         for ctx, dist in lm.items():
             if len(ctx) != L:
@@ -58,11 +69,7 @@ class RnaTable:
                 idx = idx * 4 + int(c)
             dense[idx] = dist
             seen[idx] = True
-        if not seen.all():
-            missing = int(np.flatnonzero(~seen)[0])
-            ctx = tuple((missing >> (2 * (L - 1 - i))) & 3 for i in range(L))
-            raise KeyError(ctx)
-        return cls(dense, device)
+        return cls(dense, device, present=seen)
 
     @classmethod
     def from_json(cls, path: str, device: int = 0) -> "RnaTable":
@@ -93,7 +100,12 @@ class RnaTable:
                 pass
 
 
-_table_cache: "dict[tuple, RnaTable]" = {}
+# Tables built from plain dicts, most recently used last.  Bounded: a dense table is 32 B x 4^L of
+# HBM (128 MiB at L = 11), and plain dicts cannot be weak-referenced, so nothing else would ever
+# evict them.  A hit must match the dict's identity, size and a sample of its rows; an in-place edit
+# of other rows between two calls is not noticed -- pass an RnaTable to be explicit about lifetime.
+_TABLE_CACHE_MAX = 4
+_table_cache: "dict[tuple, tuple]" = {}
 _table_lock = threading.Lock()
 
 
@@ -113,20 +125,24 @@ def _resolve_table(lm, len_context, device):
         # id() of a dead dict can be reused by a new one: a hit also has to look like the same table
         mark = _fingerprint(lm, int(len_context))
         if hit is not None and hit[1] == mark:
+            _table_cache[key] = _table_cache.pop(key)  # most recently used last
             return hit[0]
         t = RnaTable.from_dict(lm, len_context, device)
+        _table_cache.pop(key, None)
         _table_cache[key] = (t, mark)
+        while len(_table_cache) > _TABLE_CACHE_MAX:
+            _table_cache.pop(next(iter(_table_cache)))  # the table is destroyed when its last user lets go
         try:
             weakref.finalize(lm, _table_cache.pop, key, None)
         except TypeError:
-            pass  # plain dicts cannot be weak-referenced: the entry lives until the id is reused
+            pass  # plain dicts cannot be weak-referenced: the entry lives until it is pushed out
         return t
 
 
 def _fingerprint(lm, L):
     """Size plus the rows of a few fixed contexts: cheap, and enough to tell two model dicts apart."""
     n = 4 ** L
-    picks = sorted({0, n - 1, n // 2, n // 3, (n * 2) // 3, n // 7, (n * 5) // 7, 1 % n})
+    picks = sorted({(i * 0x9E3779B1) % n for i in range(64)} | {0, n - 1})
     rows = []
     for i in picks:
         ctx = tuple((i >> (2 * (L - 1 - j))) & 3 for j in range(L))
@@ -228,6 +244,10 @@ def _decode_host(arrs, dt, beam_width, table, s_threshold, r_threshold, len_cont
         float(s_threshold) if table else 0.0, float(r_threshold) if table else 0.0,
         _native.np_ptr(seq), _native.np_ptr(so), _native.np_ptr(ln), _native.np_ptr(score),
         _native.np_ptr(status), _native.np_ptr(cnt), device)
+    if rc == _native.E_READ and (status == _native.READ_KEY_ERROR).any():
+        bad = int(np.flatnonzero(status == _native.READ_KEY_ERROR)[0])
+        L, ci = int(len_context), int(ln[bad])
+        raise KeyError(tuple((ci >> (2 * (L - 1 - i))) & 3 for i in range(L)))  # decode.py:83
     if rc == _native.E_READ and (status == _native.READ_RANGE).any():
         bad = int(np.flatnonzero(status == _native.READ_RANGE)[0])
         raise FloatingPointError(
@@ -257,6 +277,7 @@ class DeviceDecodeResult:
     status: "object"       # int32 CUDA tensor (n)
     counters: "object"     # uint64-as-int64 CUDA tensor (n, 4) or None
     table: "object" = None  # keeps the RnaTable alive while the launch that uses it is in flight
+    workspace: "object" = None  # ... and the launch's workspace
 
     def strings(self, bases="ACGT"):
         seq = self.seq.cpu().numpy()
@@ -266,17 +287,14 @@ class DeviceDecodeResult:
         return [lut[seq[so[i]:so[i] + ln[i]]].tobytes().decode("ascii") for i in range(len(ln))]
 
 
-_workspaces: dict = {}
-
-
 def _workspace(device: int, nbytes: int):
+    """Queue head + back-pointer arenas of one launch.  Allocated per call from torch's caching
+    allocator on the current stream (stream-ordered reuse: a later call on the same stream may get
+    the same block back, a call on another stream never gets it while this launch can still be
+    running), and kept alive by the result object."""
     import torch
 
-    ws = _workspaces.get(device)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{device}")
-        _workspaces[device] = ws
-    return ws
+    return torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{device}")
 
 
 def decode_batch_device(post, frame_offsets, beam_width, table=None, s_threshold=0.0, r_threshold=0.0,
@@ -311,7 +329,7 @@ def decode_batch_device(post, frame_offsets, beam_width, table=None, s_threshold
     stream = torch.cuda.current_stream(post.device).cuda_stream
     rc = lib.radian_decode_batch_dev(
         post.data_ptr(), int(post.dtype == torch.float64), frame_offsets.data_ptr(), n,
-        order.data_ptr() if order is not None else None, int(max_frames), int(beam_width),
+        order.data_ptr() if order is not None else None, int(max_frames), int(post.shape[0]), int(beam_width),
         table._h if table is not None else None, table.L if table is not None else 0,
         float(s_threshold), float(r_threshold), out.seq.data_ptr(), out.seq_offsets.data_ptr(),
         out.lengths.data_ptr(), out.scores.data_ptr(), out.status.data_ptr(),
@@ -319,4 +337,5 @@ def decode_batch_device(post, frame_offsets, beam_width, table=None, s_threshold
         ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream))
     _native.check(rc)
     out.table = table
+    out.workspace = ws
     return out

@@ -170,16 +170,17 @@ def test_float64_dynamic_range(bw):
 
 
 def test_float64_range_is_wide():
-    """Entries down to 1e-300 on every frame (best beam loses ~1000 bits per frame) with a beam
-    spread of ~2^-830 between kept candidates: inside the supported range, exact."""
+    """Entries down to 1e-300 on every frame (best beam loses ~500 bits per frame) with ~2^-500
+    between a kept candidate and the next class of candidates, i.e. beams 2^-1000 apart in the first
+    frames: inside the supported range, exact."""
     from radian_b200 import decode
 
     rng = np.random.default_rng(7)
     T = 64
     p = np.full((T, 5), 1e-300)
-    p[:, 4] = 1e-290
-    p[np.arange(T), rng.integers(0, 4, T)] = 1e-50  # one base 2^-830 above the rest
-    p[::3, 4] = 1e-60
+    p[:, 4] = 1e-160
+    p[np.arange(T), rng.integers(0, 4, T)] = 1e-150  # one base 2^-498 above the rest
+    p[::3, 4] = 1e-151
     want, wsc, _ = oracle_batch([p], 16, None, 0)
     seqs, scores, _ = decode.beam_search_batch([p], 16, None, None, None, None, return_details=True)
     assert seqs[0] == want[0]

@@ -75,11 +75,43 @@ def test_dropin_signature_and_lm_quirks():
     assert decode.beam_search(np.zeros((0, 5), np.float32), "ACGT", 3, None, None, None, None, None) == ""
     with pytest.raises(TypeError):
         decode.beam_search(m, "ACGT", 3, "None", 0.5, 0.5, 2, {})
-    with pytest.raises(KeyError):
-        decode.beam_search(m, "ACGT", 3, {(0, 1): [0.25] * 4}, 0.5, 0.5, 2, {})
+    # a model that lacks contexts fails only when the search reaches one (decode.py:83): three
+    # uniform frames never keep a two-symbol labeling, nine do (answers recorded from the reference)
+    assert decode.beam_search(m, "ACGT", 3, {(0, 1): [0.25] * 4}, 0.5, 0.5, 2, {}) == "A"
+    with pytest.raises(KeyError, match=r"\(1, 0\)"):
+        decode.beam_search(np.full((9, 5), 0.2, np.float32), "ACGT", 3, {(0, 1): [0.25] * 4}, 0.5, 0.5, 2, {})
     tab = decode.RnaTable(golden_io.table(2, 1))
     with pytest.raises(KeyError):
         decode.beam_search(m, "ACGT", 3, tab, 0.5, 0.5, 3, {})
+
+
+def test_sparse_model_keyerror_like_reference():
+    """A dict that lacks contexts: KeyError exactly when the reference's search reaches a missing one
+    (decode.py:83, recorded from the reference in decode_sparse.npz), the same result otherwise."""
+    import os
+
+    from radian_b200 import decode, synth
+
+    z = np.load(os.path.join(golden_io.GOLDEN, "decode_sparse.npz"))
+    po = so = mo = 0
+    n_err = 0
+    for T, L, bw, tseed, err, nseq, is64 in z["meta"]:
+        mat = z["post"][po:po + T].astype(np.float64 if is64 else np.float32)
+        po += T
+        want = "".join("ACGT"[c] for c in z["seq"][so:so + nseq])
+        so += nseq
+        present = z["present"][mo:mo + 4 ** L]
+        mo += 4 ** L
+        tab = synth.make_table(int(L), int(tseed))
+        lm = {tuple((int(i) >> (2 * (int(L) - 1 - j))) & 3 for j in range(int(L))): tab[i].tolist()
+              for i in np.flatnonzero(present)}
+        if err:
+            n_err += 1
+            with pytest.raises(KeyError):
+                decode.beam_search(mat, "ACGT", int(bw), lm, 0.5, 0.5, int(L), {})
+        else:
+            assert decode.beam_search(mat, "ACGT", int(bw), lm, 0.5, 0.5, int(L), {}) == want
+    assert 10 < n_err < 35
 
 
 def test_dict_lm_equals_dense_table():
