@@ -123,7 +123,10 @@ int radian_table_entropies(const radian_table_t *t, double *out_host);
  *                frames whose selection ranked two candidates within 2^-40 of each other (the
  *                reference decides those on the rounding noise of its log-domain sums; a read
  *                whose sequence differs from the reference's has a non-zero count here and, for
- *                a tie of the final beams, equal out_score entries), and a reserved zero.
+ *                a tie of the final beams, equal out_score entries), and a diagnostic word: high 32
+ *                bits = frames whose signal entropy gate was open (H_s > s_threshold, decode.py:93),
+ *                low 32 bits = frames in which the kernel had to look at extensions at all (the
+ *                others only updated the scores of the kept beams).
  */
 /*
  *  max_frames    frames of the longest read; total_frames: frames of all reads (= frame_offsets[n_reads],
@@ -131,7 +134,7 @@ int radian_table_entropies(const radian_table_t *t, double *out_host);
  *                the launch: a batch that does not fill the GPU several times over runs with fewer
  *                resident warps per SM, which finishes its longest read sooner.
  *  arena_nodes   capacity of the per-read back-pointer arena; 0 picks a default from max_frames
- *                (exact worst case for small problems, else beam lanes x max_frames/16).  A read
+ *                (exact worst case for small problems, else beam lanes x max_frames/64).  A read
  *                that needs more gets RADIAN_READ_TRIE_OVERFLOW; lanes x (T+1) always suffices.
  *                The _host entry point retries such reads by itself.
  */
@@ -153,6 +156,17 @@ int radian_decode_batch_host(const void *post, int post_is_f64, const int64_t *f
                              uint8_t *out_seq, const int64_t *seq_offsets, int64_t *out_len,
                              double *out_score, int32_t *out_status, uint64_t *out_counters,
                              int device);
+
+/* The same for reads that are separate matrices in host memory (what the reference's callers hold:
+ * one numpy array per read or per window, basecall.py:99-120): reads[r] points at read r's
+ * n_frames[r] x 5 values.  Nothing is concatenated on the host; the reads are gathered straight into
+ * the transfer. */
+int radian_decode_batch_host_reads(const void *const *reads, const int64_t *n_frames, int post_is_f64,
+                                   int n_reads, int beam_width, const radian_table_t *table,
+                                   int len_context, double s_threshold, double r_threshold,
+                                   uint8_t *out_seq, const int64_t *seq_offsets, int64_t *out_len,
+                                   double *out_score, int32_t *out_status, uint64_t *out_counters,
+                                   int device);
 
 /*
  * Merge of overlapping chunk posteriors for a batch of reads (matrix_assembly.py:6-53,
@@ -269,6 +283,18 @@ int radian_windows_batch_host(const double *norm, const int64_t *offsets, int n_
                               const int64_t *window_offsets, double *out, int device);
 int radian_windows_batch_dev(const double *norm, const int64_t *offsets, const int64_t *window_offsets,
                              int n_reads, int window, int step, double *out, radian_stream_t stream);
+
+/*
+ * FASTA records of a decoded batch as the reference writes them (radian/basecall.py:129):
+ * ">{read_id}\n{sequence reversed to 5'->3'}\n" per read.  seq / seq_offsets / len are the outputs of
+ * a radian_decode_batch_* or radian_stitch_batch_* call (host copies); ids holds all read ids back to
+ * back, id_offsets[n_reads+1] delimits them; bases: the 4 output letters ("ACGT").  Record r is
+ * written at out + out_offsets[r] and must have exactly 1 + id length + 1 + len[r] + 1 bytes there
+ * (out_offsets[n_reads+1] is a running sum of those sizes).  Host only, no device needed.
+ */
+int radian_fasta_records_host(const uint8_t *seq, const int64_t *seq_offsets, const int64_t *len,
+                              int n_reads, const char *ids, const int64_t *id_offsets, const char *bases,
+                              char *out, const int64_t *out_offsets);
 
 #ifdef __cplusplus
 }

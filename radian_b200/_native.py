@@ -12,6 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_
 from . import build as _build
 
 OK, E_ARG, E_CUDA, E_CONTEXT, E_READ, E_GAP = 0, -1, -2, -3, -4, -5
+READ_SEQ_OVERFLOW = 1  # RADIAN_READ_SEQ_OVERFLOW
 READ_RANGE = 6  # RADIAN_READ_RANGE
 READ_KEY_ERROR = 7  # RADIAN_READ_KEY_ERROR
 MAX_BEAM_WIDTH = 128
@@ -21,10 +22,11 @@ EXPORTS = [
     "radian_last_error", "radian_version", "radian_device_count", "radian_trim_memory",
     "radian_table_create", "radian_table_create_sparse", "radian_table_destroy", "radian_table_context_len", "radian_table_entropies",
     "radian_decode_workspace_bytes", "radian_decode_batch_dev", "radian_decode_batch_host",
+    "radian_decode_batch_host_reads",
     "radian_assemble_plan", "radian_assemble_batch_dev", "radian_assemble_batch_host",
     "radian_stitch_batch_host", "radian_stitch_batch_dev", "radian_stitch_workspace_bytes",
     "radian_normalise_batch_host", "radian_normalise_batch_dev", "radian_windows_plan",
-    "radian_windows_batch_host", "radian_windows_batch_dev",
+    "radian_windows_batch_host", "radian_windows_batch_dev", "radian_fasta_records_host",
 ]
 
 
@@ -62,6 +64,10 @@ def _load():
     lib.radian_decode_batch_host.argtypes = [
         c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_double, c_double,
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]
+    lib.radian_decode_batch_host_reads.restype = c_int
+    lib.radian_decode_batch_host_reads.argtypes = [
+        c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_double, c_double,
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]
     lib.radian_assemble_plan.restype = c_int
     lib.radian_assemble_plan.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int32)]
     lib.radian_assemble_batch_dev.restype = c_int
@@ -91,6 +97,9 @@ def _load():
     lib.radian_windows_plan.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.radian_windows_batch_host.restype = c_int
     lib.radian_windows_batch_host.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int]
+    lib.radian_fasta_records_host.restype = c_int
+    lib.radian_fasta_records_host.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_char_p, c_void_p,
+                                              c_void_p]
     return lib
 
 

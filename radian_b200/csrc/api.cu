@@ -448,18 +448,61 @@ static void *pinned_scratch(size_t bytes)
 }
 
 
+// Streams and events of the calling host thread's decode calls, made once per (thread, device) and
+// kept: the reference's own calling pattern is one read per call (basecall.py:70-123), which should
+// not pay for five creations and destructions every time.
+struct HostStreams {
+    int device = -1;
+    cudaStream_t st = nullptr, cs[2] = {nullptr, nullptr};
+    cudaEvent_t ev = nullptr, ev_last = nullptr;
+};
+
+static HostStreams *host_streams(int device)
+{
+    static thread_local HostStreams hs[4];
+    HostStreams *h = nullptr;
+    for (auto &x : hs)
+        if (x.device == device) return &x;
+    for (auto &x : hs)
+        if (x.device < 0) {
+            h = &x;
+            break;
+        }
+    if (!h) {  // more than four devices driven by one thread: recycle the first slot
+        h = &hs[0];
+        cudaStreamDestroy(h->st);
+        cudaStreamDestroy(h->cs[0]);
+        cudaStreamDestroy(h->cs[1]);
+        cudaEventDestroy(h->ev);
+        cudaEventDestroy(h->ev_last);
+        *h = HostStreams();
+    }
+    if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->cs[0], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->cs[1], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming) != cudaSuccess) {
+        cuda_fail(cudaGetLastError(), "host_streams");
+        return nullptr;
+    }
+    h->device = device;
+    return h;
+}
+
 // ---- staged upload -----------------------------------------------------------------------------
 // Pageable host memory reaches the device at ~10 GB/s through cudaMemcpyAsync (the driver stages
 // it on the calling thread), and page-locked memory at 80 % of the link when every read is its own
 // transfer.  Here host threads gather the reads, in queue order, into a ring of page-locked slots
 // and the calling thread sends every filled slot with one large copy: the source may be any
-// memory, and the copy engine only sees 32 MB transfers.
-constexpr int kStageSlots = 4;
-constexpr size_t kStageBytes = (size_t)32 << 20;
+// memory, and the copy engine only sees 16 MB transfers.
+// (one host thread fills one slot at a time at 6-8 GB/s: the number of slots is the number of threads
+// that can work ahead of the copy engine, and it takes about eight of them to outrun the link)
+constexpr int kStageSlots = 12;
+constexpr size_t kStageBytes = (size_t)16 << 20;
 
 struct StageRing {
-    char *slot[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    char *slot[kStageSlots] = {};
+    cudaEvent_t ev[kStageSlots] = {};
     int *flags = nullptr;  // page-locked flag values
     size_t bytes = 0, n_flags = 0;
 };
@@ -529,8 +572,8 @@ static int stage_plan(const std::vector<int64_t> &fo, size_t row, StagePlan *pla
     return RADIAN_OK;
 }
 
-// reads in queue order k = 0..n-1: source frames src_frame[k], device frames fo[k]..fo[k+1]
-static int staged_upload(const char *post, size_t row, const std::vector<int64_t> &src_frame,
+// reads in queue order k = 0..n-1: source src[k], device frames fo[k]..fo[k+1]
+static int staged_upload(size_t row, const std::vector<const char *> &src,
                          const std::vector<int64_t> &fo, const StagePlan &plan, char *d_post, int *d_ready,
                          cudaStream_t cs[2], cudaEvent_t ev_last, int device)
 {
@@ -559,7 +602,7 @@ static int staged_upload(const char *post, size_t row, const std::vector<int64_t
                 char *dst = ring->slot[slot];
                 for (int k = segs[sgm].k0; k < segs[sgm].k1; ++k) {
                     const size_t bytes = (size_t)(fo[k + 1] - fo[k]) * row;
-                    memcpy(dst, post + (size_t)src_frame[k] * row, bytes);
+                    memcpy(dst, src[k], bytes);
                     dst += bytes;
                 }
                 filled[sgm].store(1, std::memory_order_release);
@@ -614,7 +657,7 @@ static int staged_upload(const char *post, size_t row, const std::vector<int64_t
 // many reads have landed (`ready`); a read group that pops a read which is still in flight waits
 // for it.  The transfer, which is the slower of the two at ~20 B per frame, is therefore the only
 // thing on the critical path; the decode of read k overlaps the copies of reads k+1...
-static int decode_host_pass(const void *post, int post_is_f64, const int64_t *frame_offsets,
+static int decode_host_pass(const void *post, const void *const *read_ptrs, int post_is_f64, const int64_t *frame_offsets,
                             const std::vector<int32_t> &sel, int beam_width, const radian_table_t *table,
                             int len_context, double s_threshold, double r_threshold, uint8_t *out_seq,
                             const int64_t *seq_offsets, int64_t *out_len, double *out_score, int32_t *out_status,
@@ -636,12 +679,47 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
         if (trace) tr[i] = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     };
     stamp(0);
-    constexpr size_t kPublishBytes = 8u << 20;  // a flag update after at most this much payload
-    // queue position k holds read sel[q[k]]: longest first, ties in caller order
+    constexpr size_t kPublishBytes = 16u << 20;  // a copy (and a flag update) after at most this much payload
+    // Queue position k holds read sel[q[k]].  The queue order is also the order in which the reads
+    // travel, and a read can only be started once it has landed; the link moves a frame ~750 times
+    // faster than one read group decodes it, so a long read must not arrive late.  But the link also
+    // wants large copies (a copy costs ~4 us before its first byte: 16 MB copies reach 98 % of the
+    // link, one copy per read 80 %).  So the caller's buffer is cut into chunks of adjacent reads
+    // (up to 16 MB, 1/64 of the batch for small ones) and the chunks travel in the order of their
+    // longest read, longest first; inside a chunk the caller's order stands.
     std::vector<int32_t> q(n);
-    for (int i = 0; i < n; ++i) q[i] = i;
     auto T_of = [&](int i) { return frame_offsets[sel[i] + 1] - frame_offsets[sel[i]]; };
-    std::stable_sort(q.begin(), q.end(), [&](int32_t x, int32_t y) { return T_of(x) > T_of(y); });
+    // where read sel[i] is in host memory: one buffer with offsets, or one pointer per read
+    auto src_of = [&](int i) -> const char * {
+        return read_ptrs ? (const char *)read_ptrs[sel[i]] : (const char *)post + (size_t)frame_offsets[sel[i]] * row;
+    };
+    {
+        int64_t total = 0;
+        for (int i = 0; i < n; ++i) total += T_of(i);
+        size_t chunk_bytes = (size_t)total * row / 64;
+        chunk_bytes = chunk_bytes < ((size_t)256 << 10) ? ((size_t)256 << 10) : chunk_bytes > kPublishBytes ? kPublishBytes : chunk_bytes;
+        struct Chunk {
+            int first, last;  // reads [first, last) of sel
+            int64_t longest;
+        };
+        std::vector<Chunk> chunks;
+        for (int i = 0; i < n;) {
+            int j = i + 1;
+            size_t bytes = (size_t)T_of(i) * row;
+            int64_t longest = T_of(i);
+            while (j < n && src_of(j) == src_of(j - 1) + (size_t)T_of(j - 1) * row && bytes + (size_t)T_of(j) * row <= chunk_bytes) {
+                bytes += (size_t)T_of(j) * row;
+                longest = std::max(longest, T_of(j));
+                ++j;
+            }
+            chunks.push_back({i, j, longest});
+            i = j;
+        }
+        std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk &x, const Chunk &y) { return x.longest > y.longest; });
+        int k = 0;
+        for (const Chunk &c : chunks)
+            for (int i = c.first; i < c.last; ++i) q[k++] = i;
+    }
     // the device sees the reads renumbered by queue position and packed in that order
     std::vector<int64_t> fo(n + 1, 0), so(n + 1, 0);
     int64_t max_frames = 0;
@@ -662,7 +740,9 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     // copy plan: runs of queue-adjacent reads that are also adjacent in the caller's buffer go in
     // one transfer; `pub` = reads published after the transfer
     struct Xfer {
-        int64_t dst_frame, src_frame, n_frames;
+        int64_t dst_frame;
+        const char *src;
+        int64_t n_frames;
         int pub;  // reads landed after this transfer, or 0 when no flag update follows it
     };
     std::vector<Xfer> plan;
@@ -670,13 +750,13 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     for (int k = 0; k < n;) {
         int j = k;
         size_t bytes = (size_t)T_of(q[k]) * row;
-        while (j + 1 < n && sel[q[j + 1]] == sel[q[j]] + 1 && bytes < kPublishBytes) {
+        while (j + 1 < n && src_of(q[j + 1]) == src_of(q[j]) + (size_t)T_of(q[j]) * row && bytes < kPublishBytes) {
             ++j;
             bytes += (size_t)T_of(q[j]) * row;
         }
         unpublished += bytes;
         const bool pub = unpublished >= kPublishBytes || j + 1 == n;
-        plan.push_back({fo[k], frame_offsets[sel[q[k]]], fo[j + 1] - fo[k], pub ? j + 1 : 0});
+        plan.push_back({fo[k], src_of(q[k]), fo[j + 1] - fo[k], pub ? j + 1 : 0});
         if (pub) unpublished = 0;
         k = j + 1;
     }
@@ -704,7 +784,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     bool staged = getenv("RADIAN_HOST_STAGE") != nullptr && getenv("RADIAN_HOST_STAGE")[0] != '0';
     if (!staged && getenv("RADIAN_HOST_STAGE") == nullptr && frames > 0) {
         cudaPointerAttributes pa;
-        if (cudaPointerGetAttributes(&pa, post) != cudaSuccess) {
+        if (cudaPointerGetAttributes(&pa, src_of(q[0])) != cudaSuccess) {
             cudaGetLastError();
             staged = true;
         } else {
@@ -716,13 +796,10 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
         const int prc = stage_plan(fo, row, &splan);
         if (prc) return prc;
     }
-    cudaStream_t st = nullptr, cs[2] = {nullptr, nullptr};
-    cudaEvent_t ev = nullptr, ev_last = nullptr;
-    RADIAN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    RADIAN_CUDA(cudaStreamCreateWithFlags(&cs[0], cudaStreamNonBlocking));
-    RADIAN_CUDA(cudaStreamCreateWithFlags(&cs[1], cudaStreamNonBlocking));
-    RADIAN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    RADIAN_CUDA(cudaEventCreateWithFlags(&ev_last, cudaEventDisableTiming));
+    HostStreams *hs = host_streams(device);
+    if (!hs) return RADIAN_E_CUDA;
+    cudaStream_t st = hs->st, cs[2] = {hs->cs[0], hs->cs[1]};
+    cudaEvent_t ev = hs->ev, ev_last = hs->ev_last;
     void *d_post = nullptr, *d_ws = nullptr;
     int64_t *d_fo = nullptr, *d_so = nullptr, *d_len = nullptr;
     int32_t *d_status = nullptr, *d_order = nullptr;
@@ -765,9 +842,9 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     // streams, so that the fixed gap between stream-ordered copies of one stream is covered by
     // the other stream's transfer; stream s publishes into d_ready[s].
     if (staged && ret == RADIAN_OK) {
-        std::vector<int64_t> src_frame((size_t)n);
-        for (int k = 0; k < n; ++k) src_frame[k] = frame_offsets[sel[q[k]]];
-        ret = staged_upload((const char *)post, row, src_frame, fo, splan, (char *)d_post, d_ready, cs, ev_last, device);
+        std::vector<const char *> src((size_t)n);
+        for (int k = 0; k < n; ++k) src[k] = src_of(q[k]);
+        ret = staged_upload(row, src, fo, splan, (char *)d_post, d_ready, cs, ev_last, device);
     }
     int which = 0;
     const char *stall_env = getenv("RADIAN_TEST_STALL_MS");  // test hook: hold the copies back midway
@@ -780,7 +857,7 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
         }
         if (x.n_frames > 0)
             TRY(cudaMemcpyAsync((char *)d_post + (size_t)x.dst_frame * row,
-                                (const char *)post + (size_t)x.src_frame * row, (size_t)x.n_frames * row,
+                                x.src, (size_t)x.n_frames * row,
                                 cudaMemcpyHostToDevice, cs[which]));
         if (x.pub) {
             TRY(cudaMemcpyAsync(d_ready + which, &h_flag[i], 4, cudaMemcpyHostToDevice, cs[which]));
@@ -844,11 +921,6 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     for (void *p : frees)
         if (p) cudaFreeAsync(p, st);
     cudaStreamSynchronize(st);
-    cudaStreamDestroy(st);
-    cudaStreamDestroy(cs[0]);
-    cudaStreamDestroy(cs[1]);
-    cudaEventDestroy(ev);
-    cudaEventDestroy(ev_last);
     if (ret != RADIAN_OK) return ret;
     for (int k = 0; k < n; ++k) {
         const int r = sel[q[k]];
@@ -872,11 +944,11 @@ static int decode_host_pass(const void *post, int post_is_f64, const int64_t *fr
     return RADIAN_OK;
 }
 
-extern "C" int radian_decode_batch_host(const void *post, int post_is_f64, const int64_t *frame_offsets, int n_reads,
-                                        int beam_width, const radian_table_t *table, int len_context,
-                                        double s_threshold, double r_threshold, uint8_t *out_seq,
-                                        const int64_t *seq_offsets, int64_t *out_len, double *out_score,
-                                        int32_t *out_status, uint64_t *out_counters, int device)
+static int decode_batch_host_impl(const void *post, const void *const *read_ptrs, int post_is_f64,
+                                  const int64_t *frame_offsets, int n_reads, int beam_width, const radian_table_t *table,
+                                  int len_context, double s_threshold, double r_threshold, uint8_t *out_seq,
+                                  const int64_t *seq_offsets, int64_t *out_len, double *out_score, int32_t *out_status,
+                                  uint64_t *out_counters, int device)
 {
     int rc = check_decode_args(post, frame_offsets, n_reads, beam_width, table, len_context, out_seq, seq_offsets,
                                out_len, out_score, out_status);
@@ -896,7 +968,7 @@ extern "C" int radian_decode_batch_host(const void *post, int post_is_f64, const
             return RADIAN_E_ARG;
         }
     }
-    rc = decode_host_pass(post, post_is_f64, frame_offsets, sel, beam_width, table, len_context, s_threshold,
+    rc = decode_host_pass(post, read_ptrs, post_is_f64, frame_offsets, sel, beam_width, table, len_context, s_threshold,
                           r_threshold, out_seq, seq_offsets, out_len, out_score, out_status, out_counters, 0, device);
     if (rc) return rc;
     // reads whose labelings outgrew the default arena: once more with the exact worst case
@@ -909,9 +981,9 @@ extern "C" int radian_decode_batch_host(const void *post, int post_is_f64, const
             worst = T > worst ? T : worst;
         }
     if (!again.empty()) {
-        rc = decode_host_pass(post, post_is_f64, frame_offsets, again, beam_width, table, len_context, s_threshold,
-                              r_threshold, out_seq, seq_offsets, out_len, out_score, out_status, out_counters,
-                              (int64_t)128 * (worst + 1) + 64, device);
+        rc = decode_host_pass(post, read_ptrs, post_is_f64, frame_offsets, again, beam_width, table, len_context,
+                              s_threshold, r_threshold, out_seq, seq_offsets, out_len, out_score, out_status,
+                              out_counters, (int64_t)128 * (worst + 1) + 64, device);
         if (rc) return rc;
     }
     for (int i = 0; i < n_reads; ++i)
@@ -919,5 +991,85 @@ extern "C" int radian_decode_batch_host(const void *post, int post_is_f64, const
             set_error("radian_decode_batch_host: read %d failed with status %d", i, out_status[i]);
             return RADIAN_E_READ;
         }
+    return RADIAN_OK;
+}
+
+extern "C" int radian_decode_batch_host(const void *post, int post_is_f64, const int64_t *frame_offsets, int n_reads,
+                                        int beam_width, const radian_table_t *table, int len_context,
+                                        double s_threshold, double r_threshold, uint8_t *out_seq,
+                                        const int64_t *seq_offsets, int64_t *out_len, double *out_score,
+                                        int32_t *out_status, uint64_t *out_counters, int device)
+{
+    return decode_batch_host_impl(post, nullptr, post_is_f64, frame_offsets, n_reads, beam_width, table, len_context,
+                                  s_threshold, r_threshold, out_seq, seq_offsets, out_len, out_score, out_status,
+                                  out_counters, device);
+}
+
+extern "C" int radian_decode_batch_host_reads(const void *const *reads, const int64_t *n_frames, int post_is_f64,
+                                              int n_reads, int beam_width, const radian_table_t *table,
+                                              int len_context, double s_threshold, double r_threshold,
+                                              uint8_t *out_seq, const int64_t *seq_offsets, int64_t *out_len,
+                                              double *out_score, int32_t *out_status, uint64_t *out_counters,
+                                              int device)
+{
+    if (n_reads < 0 || (n_reads > 0 && (!reads || !n_frames))) {
+        set_error("radian_decode_batch_host_reads: null argument");
+        return RADIAN_E_ARG;
+    }
+    std::vector<int64_t> fo((size_t)n_reads + 1, 0);
+    for (int i = 0; i < n_reads; ++i) {
+        if (n_frames[i] < 0 || (n_frames[i] > 0 && !reads[i])) {
+            set_error("radian_decode_batch_host_reads: read %d has no matrix", i);
+            return RADIAN_E_ARG;
+        }
+        fo[i + 1] = fo[i] + n_frames[i];
+    }
+    return decode_batch_host_impl(nullptr, reads, post_is_f64, fo.data(), n_reads, beam_width, table, len_context,
+                                  s_threshold, r_threshold, out_seq, seq_offsets, out_len, out_score, out_status,
+                                  out_counters, device);
+}
+
+// FASTA text of a decoded batch, formed on the host by a few threads (basecall.py:129 writes
+// f">{read.read_id}\n{sequence[::-1]}\n" per read: the decoder's output is in sequencing order,
+// 3'->5', and is reversed here).
+extern "C" int radian_fasta_records_host(const uint8_t *seq, const int64_t *seq_offsets, const int64_t *len,
+                                         int n_reads, const char *ids, const int64_t *id_offsets, const char *bases,
+                                         char *out, const int64_t *out_offsets)
+{
+    if (n_reads < 0 || (n_reads > 0 && (!seq || !seq_offsets || !len || !ids || !id_offsets || !bases || !out || !out_offsets))) {
+        set_error("radian_fasta_records_host: null argument");
+        return RADIAN_E_ARG;
+    }
+    for (int r = 0; r < n_reads; ++r) {
+        const int64_t need = 1 + (id_offsets[r + 1] - id_offsets[r]) + 1 + len[r] + 1;
+        if (len[r] < 0 || out_offsets[r + 1] - out_offsets[r] != need) {
+            set_error("radian_fasta_records_host: record %d needs %lld bytes, its slot has %lld", r, (long long)need,
+                      (long long)(out_offsets[r + 1] - out_offsets[r]));
+            return RADIAN_E_ARG;
+        }
+    }
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : nt > 16 ? 16 : nt;
+    if (n_reads < 256) nt = 1;
+    auto work = [&](int lo, int hi) {
+        for (int r = lo; r < hi; ++r) {
+            char *o = out + out_offsets[r];
+            const int64_t idn = id_offsets[r + 1] - id_offsets[r];
+            *o++ = '>';
+            memcpy(o, ids + id_offsets[r], (size_t)idn);
+            o += idn;
+            *o++ = '\n';
+            const uint8_t *s = seq + seq_offsets[r];
+            for (int64_t i = len[r] - 1; i >= 0; --i) *o++ = bases[s[i] & 3];
+            *o = '\n';
+        }
+    };
+    if (nt == 1) {
+        work(0, n_reads);
+    } else {
+        std::vector<std::thread> th;
+        for (unsigned k = 0; k < nt; ++k) th.emplace_back(work, (int)((int64_t)n_reads * k / nt), (int)((int64_t)n_reads * (k + 1) / nt));
+        for (auto &t : th) t.join();
+    }
     return RADIAN_OK;
 }

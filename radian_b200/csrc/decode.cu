@@ -41,12 +41,10 @@
 namespace radian {
 
 constexpr int kWarpsPerBlock = 4;
-// resident CTAs per SM asked from ptxas (A/B on B200, profiles/r1_minblocks_ab.txt): 6 CTAs =
-// 24 warps at <= 80 registers once the tile prefetch and the RNA rows moved to shared memory
-// (A/B on B200, scripts/ab_variants.sh: trading the pb/ptot selects of the extension scores for one
-// more float64 multiply lost 6 %: the FP64 pipe is the scarce unit, so the frame loop avoids it)
+// resident CTAs per SM asked from ptxas.  A/B on B200 (profiles/r2_history.md): 5 CTAs = 20 warps at
+// <= 96 registers beat 6 CTAs at <= 80 by 15-20 %: at 80 the frames that change the beam set spill.
 #ifndef RADIAN_MIN_BLOCKS
-#define RADIAN_MIN_BLOCKS 6
+#define RADIAN_MIN_BLOCKS 5
 #endif
 
 template <int G, bool LM, typename PT>
@@ -58,10 +56,11 @@ struct __align__(16) GroupSmem {
     double row[LM ? G * 4 : 4];       // RNA table row of every lane's extend-context (cp.async target)
     PT raw[G * 5];                    // next tile of posterior rows, landed by cp.async
     double ex[G * 2];                 // {pr_total, pr_blank} of every lane before the frame (copy/extend merge)
+    double ex2[G * 2];                // the same for the second frame of a pair (quiet loop, two frames per turn)
     double zero[2];                   // 0.0: what a beam without a live parent reads as its parent's score
                                       // (two of them: the arrays below are read with 16-byte loads)
     unsigned long long key[5 * G];    // candidate list: [0,G) copies by lane, [G,..) extensions
-    uint32_t k32[G];                  // high words of the copies (ranking of the copies among themselves)
+    uint32_t k32[2 * G];              // high words of the copies [0,G) and of the listed extensions [G,2G)
     uint32_t kill[G];                 // byte c of word l: extension (l,c) merged into a copy
     uint16_t pos[5 * G];              // dict insertion position of the candidate
     uint8_t src[5 * G];               // lane*4+c of an extension candidate
@@ -112,13 +111,94 @@ __device__ __forceinline__ int row_bound(const double *row, uint32_t km)
                max(rb.y & (int)byte_sign_mask<2>(km), rb.w & (int)byte_sign_mask<3>(km)));
 }
 
-// -DRADIAN_STAGE_STATS: the COUNT instantiations report, in the reserved fourth counter of a read,
-// (frames that needed the second stage of the quiet test << 32) | frames that took the long way
-#ifdef RADIAN_STAGE_STATS
+// The COUNT instantiations also report, in the fourth counter of a read, (frames whose entropy gate
+// H_s > s_threshold was open << 32) | frames that took the long way (see include/radian_b200.h)
 #define RADIAN_STAT(x) if (COUNT) { x }
-#else
-#define RADIAN_STAT(x)
+
+// (A/B on B200, profiles/r2_history.md: with one frame in eight taking the long way, a pair loop spends
+// on discarded second frames what it saves on votes; it only pays for a warp that is alone on its
+// scheduler.  Off by default.)
+#ifndef RADIAN_PAIRS
+#define RADIAN_PAIRS 0
 #endif
+// Two frames per turn: the second frame is formed from the first one's results before anybody
+// knows whether the first was quiet, and one vote decides for both (the vote and the branch on it
+// are the longest link of a frame's dependency chain).  If only the first of the pair was quiet it
+// is committed alone and the loop ends at the second.
+#define RADIAN_QUIET_PAIRS(IDLE)                                                                             \
+    _Pragma("unroll 1") for (; it + 1 < nend; it += 2)                                                      \
+    {                                                                                                        \
+        const unsigned rb = q_rb0 + (unsigned)it * (unsigned)(REC * 8);                                      \
+        constexpr unsigned RB2 = REC * 8;                                                                    \
+        const double P4a = lds_f64(rb + 32), P4b = lds_f64(rb + RB2 + 32);                                   \
+        double dla = lds_f64(rb + q_ox), dlb = lds_f64(rb + RB2 + q_ox);                                     \
+        int za, zb;                                                                                          \
+        bool fga = false, fgb = false;                                                                       \
+        if (LM) {                                                                                            \
+            const double ya = lds_f64(rb + q_oy), yb = lds_f64(rb + RB2 + q_oy);                             \
+            const double ga = lds_f64(rb + 40), gb = lds_f64(rb + RB2 + 40);                                 \
+            const int4 gia = lds_i4(rb + 96), gib = lds_i4(rb + RB2 + 96);                                   \
+            dla = __dmul_rn(__dadd_rn(__dmul_rn(rcopy, ga), dla), ya);                                       \
+            dlb = __dmul_rn(__dadd_rn(__dmul_rn(rcopy, gb), dlb), yb);                                       \
+            za = gext ? max(gia.w, rmax) + gia.y : gia.z;                                                    \
+            zb = gext ? max(gib.w, rmax) + gib.y : gib.z;                                                    \
+            fga = gia.x != 0;                                                                                \
+            fgb = gib.x != 0;                                                                                \
+        } else {                                                                                             \
+            za = lds_i32(rb + 40);                                                                           \
+            zb = lds_i32(rb + RB2 + 40);                                                                     \
+        }                                                                                                    \
+        /* first frame */                                                                                    \
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ex_addr), "d"(ptot), "d"(pb) : "memory");      \
+        double npnbA = __dmul_rn(pnb, dla);                                                                  \
+        const double npbA = __dmul_rn(ptot, P4a);                                                            \
+        double nptotA = __dadd_rn(npbA, npnbA);                                                              \
+        __syncwarp();                                                                                        \
+        {                                                                                                    \
+            const double v = __dmul_rn(lds_f64_volatile(q_paddr), dla);                                      \
+            npnbA = __dadd_rn(npnbA, v);                                                                     \
+            nptotA = __dadd_rn(nptotA, v);                                                                   \
+        }                                                                                                    \
+        /* second frame, from the first one's results */                                                     \
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ex_addr + (unsigned)(G * 16)), "d"(nptotA), "d"(npbA) : "memory"); \
+        double npnbB = __dmul_rn(npnbA, dlb);                                                                \
+        const double npbB = __dmul_rn(nptotA, P4b);                                                          \
+        double nptotB = __dadd_rn(npbB, npnbB);                                                              \
+        __syncwarp();                                                                                        \
+        {                                                                                                    \
+            const double v = __dmul_rn(lds_f64_volatile(q_paddr2), dlb);                                     \
+            npnbB = __dadd_rn(npnbB, v);                                                                     \
+            nptotB = __dadd_rn(nptotB, v);                                                                   \
+        }                                                                                                    \
+        const uint32_t kA = (uint32_t)__double2hiint(nptotA), kB = (uint32_t)__double2hiint(nptotB);         \
+        const uint32_t ksA = __shfl_sync(kFull, kA, q_succ), ksB = __shfl_sync(kFull, kB, q_succ);           \
+        const uint32_t kwA = __shfl_sync(kFull, kA, last_lane), kwB = __shfl_sync(kFull, kB, last_lane);     \
+        const bool quietA = (IDLE && q_idle) || (kA >= ksA + q_inc && kwA >= 0x00100000u &&                  \
+                                                 __double2hiint(ptot) + za < (int)kwA);                      \
+        const bool quietB = (IDLE && q_idle) || (kB >= ksB + q_inc && kwB >= 0x00100000u && (int)kA + zb < (int)kwB); \
+        if (!__all_sync(kFull, quietA && quietB)) {                                                          \
+            pair_broke = true;                                                                               \
+            if (!__all_sync(kFull, quietA)) break;                                                           \
+            if (COUNT && LM) {                                                                               \
+                n_lookup += (unsigned)c_lookup;                                                              \
+                if (fga) n_combine += (unsigned)c_combine;                                                   \
+                if (fga) n_stage2 += 1ull << 32;                                                             \
+            }                                                                                                \
+            ptot = nptotA;                                                                                   \
+            pnb = npnbA;                                                                                     \
+            pb = npbA;                                                                                       \
+            ++it;                                                                                            \
+            break;                                                                                           \
+        }                                                                                                    \
+        if (COUNT && LM) {                                                                                   \
+            n_lookup += 2u * (unsigned)c_lookup;                                                             \
+            n_combine += (fga ? (unsigned)c_combine : 0u) + (fgb ? (unsigned)c_combine : 0u);                \
+            n_stage2 += ((unsigned long long)(fga ? 1 : 0) + (fgb ? 1 : 0)) << 32;                           \
+        }                                                                                                    \
+        ptot = nptotB; /* (a dead lane's new values are zero as well) */                                     \
+        pnb = npnbB;                                                                                         \
+        pb = npbB;                                                                                           \
+    }
 
 // The quiet loop (see the comment where it is used).  IDLE: some group of the warp has no read to
 // run (its lanes hold zeros and must not block the vote); a separate copy of the loop, so that the
@@ -166,6 +246,7 @@ __device__ __forceinline__ int row_bound(const double *row, uint32_t km)
         if (COUNT && LM) {                                                                                   \
             n_lookup += (unsigned)c_lookup;                                                                  \
             if (fgate_) n_combine += (unsigned)c_combine;                                                    \
+            if (fgate_) n_stage2 += 1ull << 32;                                                              \
         }                                                                                                    \
         ptot = nptot; /* (a dead lane's new values are zero as well) */                                      \
         pnb = npnb;                                                                                          \
@@ -241,7 +322,7 @@ decode_kernel(const DecodeArgs a)
     bool q_idle = true;
     const unsigned q_rb0 = (unsigned)__cvta_generic_to_shared(&sm.rec[0]);
     const unsigned q_zero = (unsigned)__cvta_generic_to_shared(&sm.zero[0]);
-    unsigned q_paddr = q_zero, q_ox = 0, q_oy = 80, q_inc = 0;
+    unsigned q_paddr = q_zero, q_paddr2 = q_zero, q_ox = 0, q_oy = 80, q_inc = 0;
     int q_succ = lane;
     int c_lookup = 0, c_combine = 0;  // COUNT: lm[context] reads / combine_dists calls of a gated frame
     if (li == 0) sm.zero[0] = sm.zero[1] = 0.0;
@@ -251,6 +332,7 @@ decode_kernel(const DecodeArgs a)
         const bool full_ = na >= bw;                                                                       \
         q_idle = !run_;                                                                                    \
         q_paddr = (run_ && alive && plane >= 0) ? (unsigned)__cvta_generic_to_shared(&sm.ex[plane * 2 + prep]) : q_zero; \
+        q_paddr2 = (run_ && alive && plane >= 0) ? (unsigned)__cvta_generic_to_shared(&sm.ex2[plane * 2 + prep]) : q_zero; \
         /* copy emission: rec[6 + last] and rec[11] for a gated copy-context, rec[last] and rec[10] otherwise */ \
         q_ox = (unsigned)(((LM && gcopy) ? 6 + last : last) * 8);                                          \
         q_oy = (LM && gcopy) ? 88u : 80u;                                                                  \
@@ -498,8 +580,16 @@ decode_kernel(const DecodeArgs a)
                 // over the unmerged symbols of h(r_c), is a per-beam constant (rmax).
                 // Such a frame is one vote and three score updates per beam; the loop carries
                 // nothing but the three scores.
+                bool pair_broke = false;
                 if (__any_sync(kFull, q_idle)) {
                     RADIAN_QUIET_LOOP(true)
+                } else if (RADIAN_PAIRS) {
+                    RADIAN_QUIET_PAIRS(false)
+                    // (a pair loop that stopped at a frame which is not quiet leaves it to the long way;
+                    // one that ran out of pairs leaves at most the last frame of the tile)
+                    if (it + 1 == nend && !pair_broke) {
+                        RADIAN_QUIET_LOOP(false)
+                    }
                 } else {
                     RADIAN_QUIET_LOOP(false)
                 }
@@ -528,6 +618,7 @@ decode_kernel(const DecodeArgs a)
                 if (LM) fgate = reci[24] != 0;
                 // (a dead lane computes on stale flags; all its scores are zero and stay zero)
                 if (COUNT && LM) {
+                    if (fgate && run) n_stage2 += 1ull << 32;
                     const int len_c = sm.c_len[li];
                     const bool lm_copy = av && len_c >= L + 1;  // decode.py:157
                     const bool lm_ext = av && len_c >= L;       // decode.py:180
@@ -535,7 +626,8 @@ decode_kernel(const DecodeArgs a)
                     n_combine += __popc(GBALLOT(lm_copy && gcopy && fgate)) + __popc(GBALLOT(lm_ext && gext && fgate));
                 }
 
-                // COPY (decode.py:150-175)
+                // COPY (decode.py:150-175).  (Everything is formed again here; handing the quiet loop's
+                // values over instead was 7 % slower on B200: eight more registers live across the loop.)
                 // the empty labeling and dead lanes have pnb == 0, so their copy needs no special case
                 double dl_ = rec[last];
                 // (gcopy implies len >= L+1 and gext implies len >= L: both are set when the beam is created)
@@ -719,30 +811,58 @@ decode_kernel(const DecodeArgs a)
                     int new_rank = av ? base : 255;
                     int n_new = 0;
                     if (nmax <= G) {
-                        // The usual case, a handful of extensions: lane e keeps extension e, and every
-                        // extension in turn is compared with all copies and all extensions at once,
-                        // exactly: (float64 bits desc, position asc).  rank of a copy = its rank among
-                        // the copies + the extensions that beat it; of an extension = the copies and
-                        // extensions that beat it.
+                        // The usual case, at most one extension per lane: lane e keeps extension e.
+                        // rank of a copy = its rank among the copies (known) + the extensions above it;
+                        // rank of an extension = the copies and the extensions above it.  Counted on
+                        // the high words, every lane against all candidates; exact whenever the high
+                        // words are all distinct, which the sum of the ranks proves (any tie makes
+                        // it fall short of mv(mv-1)/2).
                         const bool mine = li < n_ext;
                         const unsigned long long myk = mine ? sm.key[G + li] : 0ull;
                         const int myp = mine ? (int)sm.pos[G + li] : kPosInvalid;
-                        int my_rank = 255;
-                        for (int e = 0; e < nmax; ++e) {
-                            const unsigned long long ke = sm.key[G + e];
-                            const int pe = sm.pos[G + e];
-                            const bool valid = e < n_ext;  // (a group with fewer extensions reads leftovers)
-                            const bool ibeat = av && (kcopy > ke || (kcopy == ke && pos_copy < pe));
-                            const bool xbeat = mine && (myk > ke || (myk == ke && myp < pe));
-                            const unsigned b1 = GBALLOT(ibeat), b2 = GBALLOT(xbeat);
-                            if (valid && av && !ibeat) ++new_rank;
-                            if (li == e) my_rank = __popc(b1) + __popc(b2);
-                            // two candidates within 2^-40 of each other: a decision that the log-domain
-                            // reference takes on its own rounding noise
-                            if (COUNT)
-                                near = near || (valid && ke != 0ull &&
-                                                ((av && kcopy - ke + 4096ull < 8192ull) ||
-                                                 (mine && li != e && myk - ke + 4096ull < 8192ull)));
+                        const uint32_t myx = (uint32_t)(myk >> 32);
+                        sm.k32[li] = kc32;
+                        sm.k32[G + li] = myx;  // (zero beyond the list: counts for nothing)
+                        __syncwarp();
+                        int my_rank = 0, up = 0;
+                        const uint4 *kv = reinterpret_cast<const uint4 *>(sm.k32);
+#pragma unroll
+                        for (int j = 0; j < G / 4; ++j) {
+                            const uint4 k4 = kv[j];
+                            my_rank += (k4.x > myx) + (k4.y > myx) + (k4.z > myx) + (k4.w > myx);
+                        }
+                        const int jend = G / 4 + (nmax + 3) / 4;
+                        for (int j = G / 4; j < jend; ++j) {
+                            const uint4 k4 = kv[j];
+                            my_rank += (k4.x > myx) + (k4.y > myx) + (k4.z > myx) + (k4.w > myx);
+                            up += (k4.x > kc32) + (k4.y > kc32) + (k4.z > kc32) + (k4.w > kc32);
+                        }
+                        if (av) new_rank = base + up;
+                        int ssum = (av ? new_rank : 0) + (mine ? my_rank : 0);
+#pragma unroll
+                        for (int o = G / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(kFull, ssum, o);
+                        const int mv = na + n_ext;
+                        const bool xtie = run && ssum != mv * (mv - 1) / 2;
+                        if (__any_sync(kFull, xtie)) {
+                            // two candidates agree in their high words: every extension in turn against
+                            // all copies and all extensions, exactly (float64 bits desc, position asc)
+                            if (xtie) new_rank = av ? base : 255;
+                            for (int e = 0; e < nmax; ++e) {
+                                const unsigned long long ke = sm.key[G + e];
+                                const int pe = sm.pos[G + e];
+                                const bool valid = xtie && e < n_ext;
+                                const bool ibeat = av && (kcopy > ke || (kcopy == ke && pos_copy < pe));
+                                const bool xbeat = mine && (myk > ke || (myk == ke && myp < pe));
+                                const unsigned b1 = GBALLOT(ibeat), b2 = GBALLOT(xbeat);
+                                if (valid && av && !ibeat) ++new_rank;
+                                if (valid && li == e) my_rank = __popc(b1) + __popc(b2);
+                                // two candidates within 2^-40 of each other: a decision that the log-domain
+                                // reference takes on its own rounding noise
+                                if (COUNT)
+                                    near = near || (valid && ke != 0ull &&
+                                                    ((av && kcopy - ke + 4096ull < 8192ull) ||
+                                                     (mine && li != e && myk - ke + 4096ull < 8192ull)));
+                            }
                         }
                         const bool isnew = run && mine && my_rank < bw;
                         const unsigned nbal = GBALLOT(isnew);
@@ -949,7 +1069,6 @@ decode_kernel(const DecodeArgs a)
         if (live && t >= T) {
             const long long seq_off = a.seq_offsets[read];
             const long long seq_cap = a.seq_offsets[read + 1] - seq_off;
-            const double ln2 = 0.693147180559945309417;
             if (status == 0 && lane == first_lane) {
                 const long long n = sm.c_len[li];
                 if (n > seq_cap) status = RADIAN_READ_SEQ_OVERFLOW;
@@ -960,7 +1079,7 @@ decode_kernel(const DecodeArgs a)
                     c = (int)(w >> 2);
                 }
                 a.out_len[read] = n;
-                a.out_score[2 * read] = (ptot > 0.0) ? log(ptot) + (double)kacc * ln2 : -INFINITY;
+                a.out_score[2 * read] = final_log_score(ptot, kacc);
                 if (succ_first == first_lane) a.out_score[2 * read + 1] = NAN;
                 a.out_status[read] = status;
                 if (a.out_counters) {
@@ -971,7 +1090,7 @@ decode_kernel(const DecodeArgs a)
                 }
             }
             if (status == 0 && succ_first != first_lane && lane == succ_first)
-                a.out_score[2 * read + 1] = (ptot > 0.0) ? log(ptot) + (double)kacc * ln2 : -INFINITY;
+                a.out_score[2 * read + 1] = final_log_score(ptot, kacc);
             if (status > RADIAN_READ_SEQ_OVERFLOW && li == 0) {
                 if (status != RADIAN_READ_KEY_ERROR) a.out_len[read] = 0;  // (KeyError: holds the context index)
                 a.out_score[2 * read] = NAN;
@@ -1027,13 +1146,14 @@ int decode_nursery() { return kNursery; }
 int64_t decode_arena_cap(int beam_width, int64_t max_frames, int64_t arena_nodes)
 {
     // Old generation <= beam_width x decoded length (see the header comment); decoded length <= T.
-    // Small problems get the exact worst case; large ones assume >= 16 frames per base and report
+    // Small problems get the exact worst case; large ones get lanes x T/64 nodes (the labelings of a
+    // read share nearly all their symbols: measured use is about T/40 nodes in total) and report
     // RADIAN_READ_TRIE_OVERFLOW otherwise (the caller retries those reads with arena_nodes set).
     const int64_t G = group_size(beam_width);
     const int64_t exact = G * (max_frames + 1) + kNursery + 64;
     if (arena_nodes > 0) return arena_nodes < exact ? arena_nodes + kNursery : exact;
     if (exact <= (1 << 16)) return exact;
-    int64_t cap = G * (max_frames / 16 + 64) + kNursery;
+    int64_t cap = G * (max_frames / 64 + 64) + kNursery;
     return cap < (1 << 16) ? (1 << 16) : cap;
 }
 

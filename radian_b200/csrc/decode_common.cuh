@@ -35,6 +35,16 @@ __device__ __forceinline__ unsigned long long hash_step(unsigned long long h, in
     return h ^ (h >> 29);
 }
 
+// natural log of p x 2^kacc (a read's final score).  The value is split into mantissa and exponent
+// first, so that the result does not depend on where the read happened to be rescaled.
+__device__ __forceinline__ double final_log_score(double p, long long kacc)
+{
+    if (!(p > 0.0)) return -INFINITY;
+    int e;
+    const double m = frexp(p, &e);
+    return log(m) + (double)(kacc + e) * 0.693147180559945309417;
+}
+
 // shared-memory loads by 32-bit shared address (the quiet loop of decode.cu keeps its addresses that way)
 __device__ __forceinline__ double lds_f64(unsigned addr)
 {

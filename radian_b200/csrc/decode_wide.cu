@@ -683,7 +683,6 @@ decode_wide_kernel(const DecodeArgs a)
         __syncwarp();
 
         // ------------------------------------------------------------ end of read
-        const double ln2 = 0.693147180559945309417;
         if (status == 0) {
             const long long seq_off = a.seq_offsets[read];
             const long long seq_cap = a.seq_offsets[read + 1] - seq_off;
@@ -707,7 +706,7 @@ decode_wide_kernel(const DecodeArgs a)
                         c = (int)(w >> 2);
                     }
                     a.out_len[read] = n;
-                    a.out_score[2 * read] = (ptot[s] > 0.0) ? log(ptot[s]) + (double)kacc * ln2 : -INFINITY;
+                    a.out_score[2 * read] = final_log_score(ptot[s], kacc);
                     if (second == first) a.out_score[2 * read + 1] = NAN;
                     a.out_status[read] = st;
                     if (a.out_counters) {
@@ -718,7 +717,7 @@ decode_wide_kernel(const DecodeArgs a)
                     }
                 }
                 if (second != first && b == second)
-                    a.out_score[2 * read + 1] = (ptot[s] > 0.0) ? log(ptot[s]) + (double)kacc * ln2 : -INFINITY;
+                    a.out_score[2 * read + 1] = final_log_score(ptot[s], kacc);
             }
         } else if (lane == 0) {
             if (status != RADIAN_READ_KEY_ERROR) a.out_len[read] = 0;  // (KeyError: holds the context index)

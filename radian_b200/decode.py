@@ -72,16 +72,11 @@ class RnaTable:
         return cls(dense, device, present=seen)
 
     @classmethod
-    def from_json(cls, path: str, device: int = 0) -> "RnaTable":
-        """Load the reference's RNA model JSON ({"ACGT...": [pA,pC,pG,pT]}, basecall.py:50-57)."""
-        import json
-
-        with open(path, "r") as f:
-            raw = json.load(f)
-        code = {"A": 0, "C": 1, "G": 2, "T": 3}
-        L = len(next(iter(raw)))
-        lm = {tuple(code[b] for b in k): v for k, v in raw.items()}
-        return cls.from_dict(lm, L, device)
+    def from_json(cls, path: str, device: int = 0, cache: bool = True) -> "RnaTable":
+        """Load the reference's RNA model JSON ({"ACGT...": [pA,pC,pG,pT]}, basecall.py:50-57); the
+        dense form is cached on disk (see ``load_rna_json``)."""
+        dense, present = load_rna_json(path, cache=cache)
+        return cls(dense, device, present=present)
 
     def entropies(self) -> np.ndarray:
         out = np.empty(4 ** self.L, dtype=np.float64)
@@ -104,6 +99,61 @@ class RnaTable:
 # HBM (128 MiB at L = 11), and plain dicts cannot be weak-referenced, so nothing else would ever
 # evict them.  A hit must match the dict's identity, size and a sample of its rows; an in-place edit
 # of other rows between two calls is not noticed -- pass an RnaTable to be explicit about lifetime.
+def _cache_path(path: str) -> str:
+    """Where the dense form of the model JSON at `path` is kept: next to the JSON if that directory
+    is writable, else under $XDG_CACHE_HOME / ~/.cache; the name carries size and mtime of the JSON,
+    so an edited model never meets a stale cache."""
+    import hashlib
+    import os
+
+    st = os.stat(path)
+    tag = f"{st.st_size:x}-{st.st_mtime_ns:x}"
+    d = os.path.dirname(os.path.abspath(path))
+    if os.access(d, os.W_OK):
+        return os.path.join(d, f".{os.path.basename(path)}.{tag}.radian_dense.npz")
+    root = os.path.join(os.environ.get("XDG_CACHE_HOME", os.path.join(os.path.expanduser("~"), ".cache")), "radian_b200")
+    os.makedirs(root, exist_ok=True)
+    return os.path.join(root, hashlib.sha1(os.path.abspath(path).encode()).hexdigest()[:16] + f"-{tag}.npz")
+
+
+def load_rna_json(path: str, cache: bool = True):
+    """The reference's RNA model JSON (basecall.py:47-57: {"ACGT...": [pA,pC,pG,pT]}, key = context,
+    oldest base first) as ``(dense (4**L, 4) float64, present (4**L,) uint8)``.  Parsing the 4^11 keys of
+    the real model takes many seconds of pure Python; the dense form is therefore written beside the JSON
+    (uncompressed .npz) and a later start reads that instead (a fraction of a second)."""
+    import json
+    import os
+
+    cp = _cache_path(path) if cache else None
+    if cp and os.path.exists(cp):
+        try:
+            z = np.load(cp)
+            return z["dense"], z["present"]
+        except Exception:
+            pass  # unreadable cache: rebuild it
+    with open(path, "r") as f:
+        raw = json.load(f)
+    if not raw:
+        raise ValueError(f"{path}: empty RNA model")
+    L = len(next(iter(raw)))
+    n = 4 ** L
+    tr = str.maketrans("ACGTU", "01233")
+    keys = [k for k in raw if len(k) == L]
+    idx = np.fromiter((int(k.translate(tr), 4) for k in keys), dtype=np.int64, count=len(keys))
+    dense = np.full((n, 4), 0.25, dtype=np.float64)
+    present = np.zeros(n, dtype=np.uint8)
+    dense[idx] = np.array([raw[k] for k in keys], dtype=np.float64).reshape(len(keys), 4)
+    present[idx] = 1
+    if cp:
+        try:
+            tmp = cp + f".{os.getpid()}.tmp.npz"
+            np.savez(tmp, dense=dense, present=present)
+            os.replace(tmp, cp)
+        except OSError:
+            pass  # read-only location: the next start parses again
+    return dense, present
+
+
 _TABLE_CACHE_MAX = 4
 _table_cache: "dict[tuple, tuple]" = {}
 _table_lock = threading.Lock()
@@ -225,25 +275,31 @@ def beam_search_batch(mats, beam_width, lm=None, s_threshold=None, r_threshold=N
     return (out, score, cnt) if return_details else out
 
 
-def _decode_host(arrs, dt, beam_width, table, s_threshold, r_threshold, len_context, device, want_counters):
-    """One radian_decode_batch_host call on same-dtype matrices -> (symbol arrays, scores, counters)."""
+def _decode_host(arrs, dt, beam_width, table, s_threshold, r_threshold, len_context, device, want_counters,
+                 full_slots=False):
+    """One radian_decode_batch_host_reads call on same-dtype matrices -> (symbol arrays, scores, counters)."""
     n = len(arrs)
-    fo = np.zeros(n + 1, dtype=np.int64)
-    fo[1:] = np.cumsum([a.shape[0] for a in arrs])
-    post = np.concatenate(arrs) if fo[-1] else np.zeros((0, 5), dt)
+    nf = np.array([a.shape[0] for a in arrs], dtype=np.int64)
+    # one pointer per read: the library gathers the matrices itself, nothing is concatenated here
+    ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data if a.shape[0] else None for a in arrs])
+    # output slots: a decoded read is far shorter than its frame count (a symbol needs a frame, real
+    # reads take dozens); T/4 + 64 symbols, and the whole batch again with T if some read needs more
     so = np.zeros(n + 1, dtype=np.int64)
-    so[1:] = np.cumsum(np.maximum(fo[1:] - fo[:-1], 1))
-    seq = np.zeros(int(so[-1]), dtype=np.uint8)
+    so[1:] = np.cumsum(np.maximum(nf, 1) if full_slots else nf // 4 + 64)
+    seq = np.empty(int(so[-1]), dtype=np.uint8)
     ln = np.zeros(n, dtype=np.int64)
     score = np.zeros((n, 2), dtype=np.float64)
     status = np.zeros(n, dtype=np.int32)
     cnt = np.zeros((n, 4), dtype=np.uint64) if want_counters else None
-    rc = lib.radian_decode_batch_host(
-        _native.np_ptr(post), int(dt == np.float64), _native.np_ptr(fo), n, int(beam_width),
+    rc = lib.radian_decode_batch_host_reads(
+        ptrs, _native.np_ptr(nf), int(dt == np.float64), n, int(beam_width),
         table._h if table else None, int(len_context) if table else 0,
         float(s_threshold) if table else 0.0, float(r_threshold) if table else 0.0,
         _native.np_ptr(seq), _native.np_ptr(so), _native.np_ptr(ln), _native.np_ptr(score),
         _native.np_ptr(status), _native.np_ptr(cnt), device)
+    if rc == _native.E_READ and not full_slots and (status == _native.READ_SEQ_OVERFLOW).any():
+        return _decode_host(arrs, dt, beam_width, table, s_threshold, r_threshold, len_context, device, want_counters,
+                            full_slots=True)
     if rc == _native.E_READ and (status == _native.READ_KEY_ERROR).any():
         bad = int(np.flatnonzero(status == _native.READ_KEY_ERROR)[0])
         L, ci = int(len_context), int(ln[bad])
@@ -325,7 +381,8 @@ def decode_batch_device(post, frame_offsets, beam_width, table=None, s_threshold
     nbytes = lib.radian_decode_workspace_bytes(dev, int(beam_width), int(n), int(max_frames), int(arena_nodes))
     if nbytes == 0:
         raise _native.RadianError(f"no CUDA device / bad beam width: {_native.last_error()}")
-    ws = _workspace(dev, nbytes)
+    # (a result object that is filled again brings its workspace along: same caller, same stream)
+    ws = out.workspace if out.workspace is not None and out.workspace.numel() >= nbytes else _workspace(dev, nbytes)
     stream = torch.cuda.current_stream(post.device).cuda_stream
     rc = lib.radian_decode_batch_dev(
         post.data_ptr(), int(post.dtype == torch.float64), frame_offsets.data_ptr(), n,

@@ -82,15 +82,18 @@ def read_lengths(n_reads: int, seed: int, median: float = 1300.0, sigma: float =
 
 
 def make_reads(n_bases, seed: int, device="cpu", zero_frac: float = 1e-3,
-               frames_per_base: float = 43.0, dtype=None):
+               frames_per_base: float = 43.0, dtype=None, second_spike: float = 0.3):
     """Synthetic posteriors for a batch of reads, concatenated along time.
 
     Returns (post, frame_offsets): ``post`` is a (sum T, 5) float32 tensor of softmax rows
     with the blank in column 4 (reference: decode.py:124), ``frame_offsets`` an int64
     tensor of n_reads+1 row offsets.  Per base: dwell = max(2, floor(Gamma(4, fpb/4)))
     frames; N(0,1) logits with +6 on the blank; a 1-3 frame spike (+12,+10,+8) on the true
-    base; with p=0.3 a second spike (+11,+9,+7) on a random base; ``zero_frac`` of the
-    base entries forced to exact 0 so that the -inf paths of decode.py:16-17 are used.
+    base; with p = ``second_spike`` (0.3) a second spike (+11,+9,+7) on a random base: the knob for
+    how ambiguous the posteriors are, i.e. for the fraction of frames whose base distribution has
+    entropy above ``--sig-threshold`` and for how often the beam changes (bench.py
+    reports the measured fractions); ``zero_frac`` of the base entries forced to exact 0 so that
+    the -inf paths of decode.py:16-17 are used.
     """
     import torch
 
@@ -133,7 +136,7 @@ def make_reads(n_bases, seed: int, device="cpu", zero_frac: float = 1e-3,
     true_base = torch.randint(0, 4, (nb_tot,), generator=g, device=dev)
     spikes((12.0, 10.0, 8.0), 2.0, true_base)
     other = torch.randint(0, 4, (nb_tot,), generator=g, device=dev)
-    spikes((11.0, 9.0, 7.0), 0.3, other)
+    spikes((11.0, 9.0, 7.0), float(second_spike), other)
 
     post = torch.softmax(logits, dim=1)
     del logits
