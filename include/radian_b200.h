@@ -134,7 +134,7 @@ int radian_table_entropies(const radian_table_t *t, double *out_host);
  *                the launch: a batch that does not fill the GPU several times over runs with fewer
  *                resident warps per SM, which finishes its longest read sooner.
  *  arena_nodes   capacity of the per-read back-pointer arena; 0 picks a default from max_frames
- *                (exact worst case for small problems, else beam lanes x max_frames/64).  A read
+ *                (exact worst case for small problems, else beam lanes x max_frames/32).  A read
  *                that needs more gets RADIAN_READ_TRIE_OVERFLOW; lanes x (T+1) always suffices.
  *                The _host entry point retries such reads by itself.
  */

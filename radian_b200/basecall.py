@@ -100,6 +100,40 @@ def basecall_batch(read_ids, chunk_lists, args, table):
     return [lut[seq[off[r]:off[r + 1]]].tobytes().decode("ascii") for r in range(len(chunk_lists))]
 
 
+def load_posterior_batch(path):
+    """A batch of window posteriors from a ``.npz`` file -> (read ids, list of window-matrix lists).
+    Per read ``<id>`` either a ``(n_windows, rows, 5)`` array (all windows full), or a ``(total rows, 5)``
+    array of all windows back to back plus ``<id>__lens`` with the row count of every window (the last
+    one is trimmed, basecall.py:96).  Arrays of Python objects are pickles, and unpickling a file
+    executes what is in it: they are only read with ``RADIAN_ALLOW_PICKLE=1`` in the environment."""
+    import os
+
+    allow = os.environ.get("RADIAN_ALLOW_PICKLE", "") not in ("", "0")
+    z = np.load(path, allow_pickle=allow)
+    read_ids, chunk_lists = [], []
+    for key in z.files:
+        if key.endswith("__lens"):
+            continue
+        try:
+            arr = z[key]
+        except ValueError as e:
+            raise ValueError(f"{path}: '{key}' is an object array (a pickle); store (rows, 5) float32 plus "
+                             f"'{key}__lens', or set RADIAN_ALLOW_PICKLE=1 for files you trust") from e
+        if arr.dtype == object:
+            mats = [np.asarray(m, dtype=np.float32) for m in arr]
+        elif key + "__lens" in z.files:
+            arr = np.asarray(arr, dtype=np.float32).reshape(-1, 5)
+            ends = np.cumsum(z[key + "__lens"])
+            mats = [arr[e - n:e] for e, n in zip(ends, z[key + "__lens"])]
+        elif arr.ndim == 3:
+            mats = list(np.asarray(arr, dtype=np.float32))
+        else:
+            raise ValueError(f"{path}: '{key}' needs '{key}__lens' or the shape (n_windows, rows, 5)")
+        read_ids.append(key)
+        chunk_lists.append(mats)
+    return read_ids, chunk_lists
+
+
 def windows_from_fast5(path, args):
     """basecall.py:70-83 for every read of one fast5 file: raw signal -> mad_normalise ->
     get_windows, all reads of the file in two GPU calls.  -> list of (read_id, windows, pad).
@@ -149,9 +183,7 @@ def main(argv=None, sig_model=None):
         print(f"Basecalled {len(read_ids)} reads of {path.name} in {time() - start_t:.2f} sec.")
     for path in sorted(Path(args.fast5_dir).rglob("*.npz")):
         start_t = time()
-        z = np.load(path, allow_pickle=True)
-        read_ids = list(z.files)
-        chunk_lists = [[np.asarray(m, dtype=np.float32) for m in z[r]] for r in read_ids]
+        read_ids, chunk_lists = load_posterior_batch(path)
         seqs = basecall_batch(read_ids, chunk_lists, args, table)
         for rid, seq in zip(read_ids, seqs):
             fasta.write(rid, seq)

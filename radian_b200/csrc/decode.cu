@@ -36,6 +36,8 @@
 //     beam_width x decoded length.  The best labeling is read back by one walk at the end.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "decode_common.cuh"
 
 namespace radian {
@@ -376,7 +378,31 @@ decode_kernel(const DecodeArgs a)
     while (true) {
         // ------------------------------------------------------------ fetch a read
         {
-            const bool want = active && read < 0;
+            // EXCLUSIVE reads.  A warp carries 32/G reads and every one of them pays for the frames in
+            // which one of the others changes its beam set; a read that is alone in its warp runs
+            // about twice as fast.  For a batch that is finished when its longest reads are (the
+            // host decides: a.excl_frames > 0), reads of at least that many frames -- they are at the
+            // head of the longest-first queue -- are therefore only started by the first group of an
+            // empty warp, and nothing else is started in that warp until they are done.
+            bool may = true;
+            if (!STREAM && a.excl_frames > 0 && GPW > 1) {
+                const bool excl_now = __any_sync(kFull, read >= 0 && T >= a.excl_frames);
+                const bool busy = __any_sync(kFull, read >= 0);
+                int head_T = 0;
+                if (lane == 0) {
+                    const int qh = *(volatile const int *)a.queue;
+                    if (qh < a.n_reads) {
+                        const int r = a.order ? a.order[qh] : qh;
+                        head_T = (int)(a.frame_offsets[r + 1] - a.frame_offsets[r]);
+                    }
+                }
+                head_T = __shfl_sync(kFull, head_T, 0);
+                if (excl_now)
+                    may = false;
+                else if (head_T >= a.excl_frames)
+                    may = gw == 0 && !busy;
+            }
+            const bool want = active && read < 0 && may;
             int idx = pend;
             if (want && li == 0 && idx < 0) idx = atomicAdd(a.queue, 1);
             idx = __shfl_sync(kFull, idx, gshift);
@@ -1146,14 +1172,15 @@ int decode_nursery() { return kNursery; }
 int64_t decode_arena_cap(int beam_width, int64_t max_frames, int64_t arena_nodes)
 {
     // Old generation <= beam_width x decoded length (see the header comment); decoded length <= T.
-    // Small problems get the exact worst case; large ones get lanes x T/64 nodes (the labelings of a
-    // read share nearly all their symbols: measured use is about T/40 nodes in total) and report
+    // Small problems get the exact worst case; large ones get lanes x T/32 nodes (the labelings of a
+    // read that differ at an old ambiguous position carry separate chains from there on: up to lanes x
+    // decoded length nodes, i.e. lanes x T/32 at 32 frames per base or more) and report
     // RADIAN_READ_TRIE_OVERFLOW otherwise (the caller retries those reads with arena_nodes set).
     const int64_t G = group_size(beam_width);
     const int64_t exact = G * (max_frames + 1) + kNursery + 64;
     if (arena_nodes > 0) return arena_nodes < exact ? arena_nodes + kNursery : exact;
     if (exact <= (1 << 16)) return exact;
-    int64_t cap = G * (max_frames / 64 + 64) + kNursery;
+    int64_t cap = G * (max_frames / 32 + 64) + kNursery;
     return cap < (1 << 16) ? (1 << 16) : cap;
 }
 
@@ -1205,32 +1232,38 @@ int decode_max_slots(int device, int beam_width)
     return best;
 }
 
-// Resident CTAs per SM.  A warp alone on its scheduler needs about kLone cycles per frame (the
-// dependency chain of a frame; the frames that change the beam set are long); every further warp on
-// the scheduler adds about kShare cycles to everybody's frame (measured, scripts/ab_occupancy.sh).
-// Throughput therefore keeps growing with occupancy, but so does the time of the longest read, and a
-// batch that does not fill the machine many times over is finished when its longest read is.
-// Estimated time at w CTAs per SM (list-scheduling bound):
-//   (frames of the longest read + total frames / read slots(w)) x (kLone + (w - 1) x kShare).
-static int pick_ctas_per_sm(int max_ctas, int groups_per_block, int sm_count, int n_reads, int64_t max_frames,
-                            int64_t total_frames)
+// Launch shape of a resident batch.  Measured on B200 (scripts/ab_occupancy.sh, profiles/r2_history.md):
+// a read group needs about 750 cycles per frame when its warp is alone on its scheduler and ~90 more
+// for every further warp there, so throughput keeps growing with occupancy (3.1e9 frames/s at one CTA
+// per SM, 1.05e10 at five) -- but a batch that does not fill the machine many times over is finished
+// when its longest read is, and that read wants the opposite: few warps per scheduler, and no
+// warp-mates (a read pays for the frames in which its warp-mates change their beam sets; alone in its
+// warp it needs about kAlone of the time).  So:
+//   * CTAs per SM: the fewest that still decode the bulk of the batch within the time the longest
+//     read needs alone, i.e. slots(w) >= total frames / (kAlone x frames of the longest read);
+//   * reads of at least excl_frames = max(kAlone x longest, total / slots) frames are run one per
+//     warp (decode_kernel, "EXCLUSIVE reads"); none if that is not below the longest read.
+// Batches that fill the machine get the full occupancy and no exclusive reads.
+static void plan_launch(int max_ctas, int groups_per_block, int warps_per_block, int sm_count, int n_reads,
+                        int64_t max_frames, int64_t total_frames, int *per_sm, int *excl_frames)
 {
-    static const char *env = getenv("RADIAN_CTAS_PER_SM");
-    if (env && atoi(env) > 0) return atoi(env) < max_ctas ? atoi(env) : max_ctas;
+    static const char *env_w = getenv("RADIAN_CTAS_PER_SM"), *env_x = getenv("RADIAN_EXCL_FRAMES"),
+                      *env_a = getenv("RADIAN_TUNE_ALONE");
+    *per_sm = max_ctas;
+    *excl_frames = 0;
+    const int gpw = groups_per_block / warps_per_block;
     if (total_frames <= 0) total_frames = (int64_t)n_reads * max_frames;  // unknown: all reads as long as the longest
-    static const char *e1 = getenv("RADIAN_TUNE_LONE"), *e2 = getenv("RADIAN_TUNE_SHARE");
-    const double lone = e1 ? atof(e1) : 930.0, share = e2 ? atof(e2) : 260.0;
-    int best = max_ctas;
-    double best_t = 0;
-    for (int w = max_ctas; w >= 1; --w) {  // (ties go to the higher occupancy)
-        const double slots = (double)sm_count * w * groups_per_block;
-        const double est = ((double)max_frames + (double)total_frames / slots) * (lone + (w - 1) * share);
-        if (w == max_ctas || est < best_t) {
-            best_t = est;
-            best = w;
-        }
+    const double alone = env_a ? atof(env_a) : (gpw >= 4 ? 0.4 : gpw == 2 ? 0.6 : 1.0);
+    if (max_frames > 0 && n_reads > 0) {
+        const double need_slots = (double)total_frames / (alone * (double)max_frames);
+        int w = (int)(need_slots / ((double)sm_count * groups_per_block)) + 1;
+        *per_sm = w < 1 ? 1 : w > max_ctas ? max_ctas : w;
+        const double slots = (double)sm_count * *per_sm * groups_per_block;
+        const double x = std::max(alone * (double)max_frames, (double)total_frames / slots);
+        if (gpw > 1 && x < (double)max_frames) *excl_frames = (int)std::max(x, 1.0);
     }
-    return best;
+    if (env_w && atoi(env_w) > 0) *per_sm = atoi(env_w) < max_ctas ? atoi(env_w) : max_ctas;
+    if (env_x) *excl_frames = atoi(env_x);
 }
 
 int decode_launch(const DecodeArgs &a, bool f64, int device, cudaStream_t stream)
@@ -1242,9 +1275,10 @@ int decode_launch(const DecodeArgs &a, bool f64, int device, cudaStream_t stream
     DeviceInfo di;
     rc = device_info(device, &di);
     if (rc) return rc;
-    int per_sm = dl.grid / di.sm_count;
+    int per_sm = dl.grid / di.sm_count, excl_frames = 0;
     if (a.beam_width <= 32 && a.ready == nullptr)  // (streamed batches arrive over time: keep every slot)
-        per_sm = pick_ctas_per_sm(per_sm, dl.groups_per_block, di.sm_count, a.n_reads, a.max_frames, a.total_frames);
+        plan_launch(per_sm, dl.groups_per_block, dl.block / 32, di.sm_count, a.n_reads, a.max_frames, a.total_frames,
+                    &per_sm, &excl_frames);
     // no more groups than reads: extra CTAs would only touch the queue
     int64_t need = ((int64_t)a.n_reads + dl.groups_per_block - 1) / dl.groups_per_block;
     const int64_t cap = (int64_t)di.sm_count * per_sm;
@@ -1264,6 +1298,7 @@ int decode_launch(const DecodeArgs &a, bool f64, int device, cudaStream_t stream
         smem = dyn;
     }
     DecodeArgs args = a;
+    args.excl_frames = excl_frames;
     void *params[] = {(void *)&args};
     RADIAN_CUDA(cudaLaunchKernel(dl.kernel, dim3(grid), dim3(dl.block), params, smem, stream));
     return 0;

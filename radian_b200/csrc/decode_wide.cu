@@ -149,9 +149,16 @@ decode_wide_kernel(const DecodeArgs a)
             if ((t & 31) == 0) {
                 cp_async_wait_all();
                 __syncwarp();
-                if (t + lane < T) make_record<LM, true>(&sm.raw[lane * 5], a.s_thr, &sm.rec[lane * REC]);
+                int kf = 0;
+                if (t + lane < T) kf = make_record<LM, true, sizeof(PT) == 8>(&sm.raw[lane * 5], a.s_thr, &sm.rec[lane * REC]);
                 __syncwarp();
                 if (t + 32 + lane < T) prefetch_row(&sm.raw[lane * 5], rp, t + 32 + lane);
+                if (sizeof(PT) == 8 && __any_sync(kFull, kf != 0)) {
+                    // exponents taken out of tiny rows (make_record): stored score = true score x 2^-kacc
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) kf += __shfl_xor_sync(kFull, kf, o);
+                    kacc -= kf;
+                }
             }
 
             // -------------------------------------------------------- nursery collection
@@ -207,8 +214,10 @@ decode_wide_kernel(const DecodeArgs a)
                 }
             }
 
-            // RESCALE by an exact power of two when the best beam has fallen below 2^-256 (checked
-            // every frame: a float32-derived probability is >= 2^-149)
+            // RESCALE by an exact power of two when the best beam has left [2^300, 2^900): back to
+            // 2^600 (checked every frame).  The quiet test refuses a frame in which the worst kept
+            // beam is not a normal number, and the long way reports RADIAN_READ_RANGE for a beam
+            // that underflows with non-zero factors: nothing is lost silently (see decode.cu).
             {
                 int hi = 0;
 #pragma unroll
@@ -216,16 +225,18 @@ decode_wide_kernel(const DecodeArgs a)
                     const int x = __shfl_sync(kFull, __double2hiint(ptot[s]), first & 31);
                     if ((first >> 5) == s) hi = x;
                 }
-                const int exb = hi >> 20;
-                if (exb != 0 && exb < 1023 - 256) {
-                    const double sc = __hiloint2double((2046 - exb) << 20, 0);
+                const int exb = (hi >> 20) & 0x7ff;
+                if ((unsigned)(exb - (1023 + 300)) >= 600u) {
+                    const int k1 = exb == 0 ? 1000 : 1023 - exb;  // a subnormal best first comes up by 2^1000
+                    const double s1 = __hiloint2double((1023 + k1) << 20, 0);
+                    const double s2 = __hiloint2double((1023 + 600) << 20, 0);
 #pragma unroll
                     for (int s = 0; s < BPL; ++s) {
-                        ptot[s] *= sc;
-                        pnb[s] *= sc;
-                        pb[s] *= sc;
+                        ptot[s] = __dmul_rn(__dmul_rn(ptot[s], s1), s2);
+                        pnb[s] = __dmul_rn(__dmul_rn(pnb[s], s1), s2);
+                        pb[s] = __dmul_rn(__dmul_rn(pb[s], s1), s2);
                     }
-                    kacc += exb - 1023;
+                    kacc -= k1 + 600;
                 }
             }
 
@@ -321,6 +332,7 @@ decode_wide_kernel(const DecodeArgs a)
 
             // EXTEND (decode.py:177-201)
             unsigned long long ke[BPL][4];
+            bool lost = false;  // see below
             {
                 const double2 P01 = *reinterpret_cast<const double2 *>(rec);
                 const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
@@ -346,6 +358,30 @@ decode_wide_kernel(const DecodeArgs a)
                     ke[s][1] = (unsigned long long)__double_as_longlong(__dmul_rn(last[s] == 1 ? pb[s] : ptot[s], d1));
                     ke[s][2] = (unsigned long long)__double_as_longlong(__dmul_rn(last[s] == 2 ? pb[s] : ptot[s], d2));
                     ke[s][3] = (unsigned long long)__double_as_longlong(__dmul_rn(last[s] == 3 ? pb[s] : ptot[s], d3));
+                    if (na < bw && alive[s]) {
+                        // with room in the beam every extension is kept: one that underflowed would be
+                        // ranked as a zero
+                        const double dd[4] = {d0, d1, d2, d3};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            lost = lost || (((km[s] >> (8 * c + 7)) & 1u) && (last[s] == c ? pb[s] : ptot[s]) != 0.0 &&
+                                            dd[c] != 0.0 && (uint32_t)(ke[s][c] >> 32) < 0x00100000u);
+                    }
+                }
+            }
+            {
+                // a kept beam (or, with room in the beam, an extension) that is not a normal number
+                // although its factors are not zero: the spread of the beam exceeds what the rescaled
+                // float64 scores can express
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) {
+                    bool nz = (ptot[s] != 0.0 && P4 != 0.0) || (pnb[s] != 0.0 && dl[s] != 0.0);
+                    if (alive[s] && plane[s] >= 0) nz = nz || (sm.ex[plane[s] * 2 + prep[s]] != 0.0 && dl[s] != 0.0);
+                    lost = lost || (alive[s] && nz && (uint32_t)(kcopy[s] >> 32) < 0x00100000u);
+                }
+                if (__any_sync(kFull, lost)) {
+                    status = RADIAN_READ_RANGE;
+                    break;
                 }
             }
             unsigned long long tau = 0ull;  // with room left in the beam every extension is a candidate
@@ -416,21 +452,47 @@ decode_wide_kernel(const DecodeArgs a)
                     }
                 const int m = NB + n_ext;
                 __syncwarp();
-                // ---- incremental ranks: when the copies kept their order, a copy moves down by the
+                // ---- incremental ranks: a copy moves down from its rank among the copies by the
                 // number of extensions that outrank it, and an extension ranks behind the copies and
                 // extensions above it.  Counted on the high words; any equal pair of high words
                 // sends the frame to the exact ranking below.
-                bool inc = order_ok && n_ext <= 2 * NB;
-                if (inc) {
-                    uint32_t kc32[BPL];
-                    int add[BPL];
+                uint32_t kc32[BPL];
+                int base[BPL];  // rank of a copy among the copies
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) {
+                    kc32[s] = alive[s] ? (uint32_t)(kcopy[s] >> 32) : 0u;
+                    sm.k32[s * 32 + lane] = kc32[s];
+                    base[s] = rank[s];
+                }
+                __syncwarp();
+                bool copies_ok = order_ok;
+                if (!order_ok) {
+                    // the copies changed order: ranked among themselves on the high words, which is
+                    // exact when they are all distinct; the sum of the ranks proves it (a tie makes it
+                    // fall short of na(na-1)/2) and otherwise the exact ranking below takes over
+                    const uint4 *kv = reinterpret_cast<const uint4 *>(sm.k32);
+                    int ssum = 0;
 #pragma unroll
                     for (int s = 0; s < BPL; ++s) {
-                        kc32[s] = alive[s] ? (uint32_t)(kcopy[s] >> 32) : 0u;
-                        sm.k32[s * 32 + lane] = kc32[s];
-                        add[s] = 0;
+                        int cnt = 0;
+                        const uint32_t k = kc32[s];
+#pragma unroll 4
+                        for (int j4 = 0; j4 < NB / 4; ++j4) {
+                            const uint4 q = kv[j4];
+                            cnt += (q.x > k) + (q.y > k) + (q.z > k) + (q.w > k);
+                        }
+                        base[s] = cnt;
+                        ssum += alive[s] ? cnt : 0;
                     }
-                    __syncwarp();
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(kFull, ssum, o);
+                    copies_ok = ssum == na * (na - 1) / 2;
+                }
+                bool inc = copies_ok && n_ext <= 2 * NB;
+                if (inc) {
+                    int add[BPL];
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) add[s] = 0;
                     bool tie = false;
                     for (int j = 0; j < n_ext; ++j) {
                         const uint32_t kj = sm.k32[NB + j];
@@ -462,7 +524,7 @@ decode_wide_kernel(const DecodeArgs a)
                     } else {
 #pragma unroll
                         for (int s = 0; s < BPL; ++s)
-                            sm.rnk[s * 32 + lane] = alive[s] ? (uint16_t)(rank[s] + add[s]) : (uint16_t)0xffff;
+                            sm.rnk[s * 32 + lane] = alive[s] ? (uint16_t)(base[s] + add[s]) : (uint16_t)0xffff;
                     }
                     __syncwarp();
                 }

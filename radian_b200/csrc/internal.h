@@ -72,6 +72,7 @@ struct DecodeArgs {
     int beam_width;
     int64_t max_frames;      // frames of the longest read (launch shape only)
     int64_t total_frames;    // frames of all reads, 0 = unknown (launch shape only)
+    int excl_frames;         // > 0: reads of at least this many frames get a warp to themselves (set by decode_launch)
     const double *table;     // nullptr = LM off
     const uint32_t *gate;
     const uint32_t *miss;    // optional: contexts absent from the model (radian_table::d_miss)

@@ -252,3 +252,26 @@ def test_fast5_chunk_filters():
     assert np.array_equal(np.frombuffer(got, "<i2"), x)
     with pytest.raises(NotImplementedError, match="VBZ"):
         fast5.unfilter(b"abc", [fast5.FILTER_VBZ], 0, 2)
+
+
+def test_posterior_batch_files_without_pickles(tmp_path, monkeypatch):
+    """The CLI's posterior batches are plain arrays; object arrays (pickles) are refused unless the
+    user opts in."""
+    from radian_b200 import basecall
+
+    rng = np.random.default_rng(3)
+    w = [rng.random((1024, 5), dtype=np.float32) for _ in range(3)] + [rng.random((77, 5), dtype=np.float32)]
+    np.savez(tmp_path / "a.npz", r1=np.concatenate(w), r1__lens=np.array([len(m) for m in w]),
+             r2=np.stack(w[:3]))
+    ids, lists = basecall.load_posterior_batch(tmp_path / "a.npz")
+    assert ids == ["r1", "r2"] and [len(x) for x in lists] == [4, 3]
+    assert all(np.array_equal(a, b) for a, b in zip(lists[0], w))
+    obj = np.empty(2, dtype=object)
+    obj[0], obj[1] = w[0], w[3]
+    np.savez(tmp_path / "b.npz", r3=obj)
+    monkeypatch.delenv("RADIAN_ALLOW_PICKLE", raising=False)
+    with pytest.raises(ValueError, match="pickle"):
+        basecall.load_posterior_batch(tmp_path / "b.npz")
+    monkeypatch.setenv("RADIAN_ALLOW_PICKLE", "1")
+    ids, lists = basecall.load_posterior_batch(tmp_path / "b.npz")
+    assert ids == ["r3"] and lists[0][1].shape == (77, 5)
