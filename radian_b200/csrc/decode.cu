@@ -242,9 +242,18 @@ __device__ __forceinline__ int row_bound(const double *row, uint32_t km)
         const uint32_t kc32 = (uint32_t)__double2hiint(nptot);                                               \
         const uint32_t ksucc = __shfl_sync(kFull, kc32, q_succ);                                             \
         const uint32_t kworst = __shfl_sync(kFull, kc32, last_lane);                                         \
-        const bool quiet = (IDLE && q_idle) || (kc32 >= ksucc + q_inc && kworst >= 0x00100000u &&            \
-                                                __double2hiint(ptot) + z < (int)kworst);                     \
-        if (!__all_sync(kFull, quiet)) break;                                                                \
+        const bool rest = kworst >= 0x00100000u && __double2hiint(ptot) + z < (int)kworst;                   \
+        if (!__all_sync(kFull, (IDLE && q_idle) || (kc32 >= ksucc + q_inc && rest))) {                       \
+            /* Two copies next to each other in the order may agree in their high words for thousands of   \
+               frames (two readings of an old ambiguous position, multiplied by the same factors ever       \
+               since): then the low words decide, and for equal scores the insertion positions (tie_ok). */ \
+            const bool hitie = q_succ != lane && kc32 == ksucc;                                              \
+            if (!__any_sync(kFull, hitie)) break;                                                            \
+            const uint32_t lo = (uint32_t)__double2loint(nptot);                                             \
+            const uint32_t los = __shfl_sync(kFull, lo, q_succ);                                             \
+            const bool ord = hitie ? (lo > los || (lo == los && tie_ok)) : kc32 >= ksucc + q_inc;            \
+            if (!__all_sync(kFull, (IDLE && q_idle) || (ord && rest))) break;                                \
+        }                                                                                                    \
         if (COUNT && LM) {                                                                                   \
             n_lookup += (unsigned)c_lookup;                                                                  \
             if (fgate_) n_combine += (unsigned)c_combine;                                                    \
@@ -310,6 +319,7 @@ decode_kernel(const DecodeArgs a)
     bool gext = false, gcopy = false;
     bool rmax_prov = false;  // rmax is the table-wide bound: this beam's row was in flight when it was set
     int succ = 0;        // absolute lane of the beam ranked right after this one (own lane: none)
+    bool tie_ok = false; // a successor with exactly my score is still in the right place (its insertion position is later)
     uint32_t km = 0;     // byte c = 0x80: this lane holds a beam and its extension by c is a candidate
                          // of its own (not merged into a live child's copy); 0 for a dead lane
     // ---- per-read (group-uniform) state
@@ -318,6 +328,9 @@ decode_kernel(const DecodeArgs a)
     long long kacc = 0;
     const PT *rp = (const PT *)a.post;
     unsigned long long n_lookup = 0, n_combine = 0, n_tie = 0, n_stage2 = 0;
+#ifdef RADIAN_READ_TIMES
+    unsigned long long t_read0 = 0;
+#endif
     bool active = true;
     // ---- what the quiet loop reads besides the scores; derived from the state above by REFRESH()
     // whenever the beam set, the order or the read changes
@@ -459,6 +472,7 @@ decode_kernel(const DecodeArgs a)
                     last = 0;
                     gext = gcopy = false;
                     succ = lane;
+                    tie_ok = false;
                     km = alive ? 0x80808080u : 0u;
                     first_lane = gshift;
                     last_lane = gshift;
@@ -468,6 +482,9 @@ decode_kernel(const DecodeArgs a)
                     status = 0;
                     kacc = 0;
                     n_lookup = n_combine = n_tie = n_stage2 = 0;
+#ifdef RADIAN_READ_TIMES
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_read0));
+#endif
                 }
             }
         }
@@ -688,7 +705,6 @@ decode_kernel(const DecodeArgs a)
                 // copy of a full beam.
                 const unsigned long long kcopy = (unsigned long long)__double_as_longlong(nptot);
                 const uint32_t kc32 = (uint32_t)(kcopy >> 32);  // zero on a dead lane: its scores are zero
-                const uint32_t ksucc = __shfl_sync(kFull, kc32, succ);
                 const uint32_t kworst = __shfl_sync(kFull, kc32, last_lane);
                 const bool prune = (na >= bw);
                 bool ranks_changed = false;
@@ -714,7 +730,8 @@ decode_kernel(const DecodeArgs a)
                 const double e1 = __dmul_rn(last == 1 ? pb : ptot, d1);
                 const double e2 = __dmul_rn(last == 2 ? pb : ptot, d2);
                 const double e3 = __dmul_rn(last == 3 ? pb : ptot, d3);
-                const bool order_ok = GBALLOT(kc32 > ksucc || succ == lane) == GBITS;
+                const unsigned long long ks64 = __shfl_sync(kFull, kcopy, succ);
+                const bool order_ok = GBALLOT(kcopy > ks64 || (kcopy == ks64 && tie_ok) || succ == lane) == GBITS;
                 // worst copy of the group: the last lane of the order when the order still holds.
                 // With room left in the beam every extension is a candidate (threshold 1: keys are
                 // or-ed with 1 so that a zero-probability extension of a live beam still counts).
@@ -1075,15 +1092,24 @@ decode_kernel(const DecodeArgs a)
                     // successor lane of every beam and the lane of the best one
                     __syncwarp();
                     if (run && alive) sm.newlist[rank] = (uint8_t)li;
+                    sm.c_rank[li] = rank;
                     __syncwarp();
                     if (run) {
                         succ = (alive && rank + 1 < na) ? (int)sm.newlist[rank + 1] + gshift : lane;
                         first_lane = (int)sm.newlist[0] + gshift;
                         last_lane = (int)sm.newlist[na - 1] + gshift;
                     }
+                    // should my successor ever have exactly my score: is it rightly behind me?  (dict
+                    // insertion position of the next frame's copies, from the new ranks)
+                    int npos = 5 * rank;
+                    if (run && alive && plane >= 0) {
+                        const int pp = 5 * sm.c_rank[plane] + 1 + last;
+                        npos = pp < npos ? pp : npos;
+                    }
+                    const int spos = __shfl_sync(kFull, npos, succ);
+                    if (run) tie_ok = npos < spos;
                     __syncwarp();
                 }
-                sm.c_rank[li] = rank;
                 REFRESH();
                 ++it;
             }
@@ -1112,6 +1138,12 @@ decode_kernel(const DecodeArgs a)
                     a.out_counters[4 * read] = n_lookup;
                     a.out_counters[4 * read + 1] = n_combine;
                     a.out_counters[4 * read + 2] = n_tie;
+#ifdef RADIAN_READ_TIMES
+                    // (diagnostic build: nanoseconds this read spent in its group instead of the gate count)
+                    unsigned long long now_;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));
+                    n_stage2 = ((now_ - t_read0) << 32) | (n_stage2 & 0xffffffffull);
+#endif
                     a.out_counters[4 * read + 3] = n_stage2;
                 }
             }
@@ -1253,7 +1285,7 @@ static void plan_launch(int max_ctas, int groups_per_block, int warps_per_block,
     *excl_frames = 0;
     const int gpw = groups_per_block / warps_per_block;
     if (total_frames <= 0) total_frames = (int64_t)n_reads * max_frames;  // unknown: all reads as long as the longest
-    const double alone = env_a ? atof(env_a) : (gpw >= 4 ? 0.4 : gpw == 2 ? 0.6 : 1.0);
+    const double alone = env_a ? atof(env_a) : (gpw > 1 ? 0.6 : 1.0);  // measured: 234 vs 384 ns per frame, four reads per warp
     if (max_frames > 0 && n_reads > 0) {
         const double need_slots = (double)total_frames / (alone * (double)max_frames);
         int w = (int)(need_slots / ((double)sm_count * groups_per_block)) + 1;
@@ -1279,8 +1311,10 @@ int decode_launch(const DecodeArgs &a, bool f64, int device, cudaStream_t stream
     if (a.beam_width <= 32 && a.ready == nullptr)  // (streamed batches arrive over time: keep every slot)
         plan_launch(per_sm, dl.groups_per_block, dl.block / 32, di.sm_count, a.n_reads, a.max_frames, a.total_frames,
                     &per_sm, &excl_frames);
-    // no more groups than reads: extra CTAs would only touch the queue
-    int64_t need = ((int64_t)a.n_reads + dl.groups_per_block - 1) / dl.groups_per_block;
+    // no more groups than reads: extra CTAs would only touch the queue (with exclusive reads a warp
+    // may take a single read, and how many reads are that long is only known on the device)
+    const int reads_per_block = excl_frames > 0 ? dl.block / 32 : dl.groups_per_block;
+    int64_t need = ((int64_t)a.n_reads + reads_per_block - 1) / reads_per_block;
     const int64_t cap = (int64_t)di.sm_count * per_sm;
     int grid = (int)(need < cap ? need : cap);
     if (grid < 1) grid = 1;
