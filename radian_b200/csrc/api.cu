@@ -324,8 +324,8 @@ extern "C" size_t radian_decode_workspace_bytes(int device, int beam_width, int 
     int slots = decode_max_slots(device, beam_width);
     if (slots <= 0) return 0;
     // one arena per resident read group; a launch never uses more warps than reads (a warp may hold a
-    // single, exclusive read: up to four groups per read), rounded up to whole CTAs of 16 groups
-    const int64_t need = ((int64_t)n_reads + 3) / 4 * 16;
+    // single, exclusive read: up to four groups per read), plus the rounding to whole CTAs
+    const int64_t need = ((int64_t)n_reads + 4) * 4;
     if (need < slots) slots = (int)(need < 16 ? 16 : need);
     const size_t cap = (size_t)decode_arena_cap(beam_width, max_frames, arena_nodes);
     return 256 + (size_t)slots * (cap + (size_t)decode_nursery()) * sizeof(uint32_t);

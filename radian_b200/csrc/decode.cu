@@ -34,6 +34,7 @@
 //     live beam are slid down onto the old generation (never revisited) and the rest is dropped.
 //     Every lineage promotes each of its symbols once, so the old generation is bounded by
 //     beam_width x decoded length.  The best labeling is read back by one walk at the end.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -42,7 +43,10 @@
 
 namespace radian {
 
-constexpr int kWarpsPerBlock = 4;
+#ifndef RADIAN_WARPS
+#define RADIAN_WARPS 4
+#endif
+constexpr int kWarpsPerBlock = RADIAN_WARPS;
 // resident CTAs per SM asked from ptxas.  A/B on B200 (profiles/r2_history.md): 5 CTAs = 20 warps at
 // <= 96 registers beat 6 CTAs at <= 80 by 15-20 %: at 80 the frames that change the beam set spill.
 #ifndef RADIAN_MIN_BLOCKS
@@ -116,6 +120,23 @@ __device__ __forceinline__ int row_bound(const double *row, uint32_t km)
 // The COUNT instantiations also report, in the fourth counter of a read, (frames whose entropy gate
 // H_s > s_threshold was open << 32) | frames that took the long way (see include/radian_b200.h)
 #define RADIAN_STAT(x) if (COUNT) { x }
+
+// -DRADIAN_CHECKS: bounds checks of our own on every index the long way computes (arena, forwarding
+// table, candidate lists); a violation prints where and traps, which fails the launch.  compute-sanitizer
+// is closed on the build pool (profiles/r2_sanitizer_closed.txt); the test-suite is run once with this
+// build instead (profiles/r2_checks_build.txt).
+#ifdef RADIAN_CHECKS
+#define RADIAN_ASSERT(c)                                                                       \
+    do {                                                                                       \
+        if (!(c)) {                                                                            \
+            printf("radian check failed: %s (decode.cu:%d, block %d thread %d)\n", #c, __LINE__, \
+                   (int)blockIdx.x, (int)threadIdx.x);                                         \
+            __trap();                                                                          \
+        }                                                                                      \
+    } while (0)
+#else
+#define RADIAN_ASSERT(c)
+#endif
 
 // (A/B on B200, profiles/r2_history.md: with one frame in eight taking the long way, a pair loop spends
 // on discarded second frames what it saves on votes; it only pays for a warp that is alone on its
@@ -450,6 +471,7 @@ decode_kernel(const DecodeArgs a)
                     pend = -1;
                     if (STREAM || (RADIAN_RESIDENT_KEEPS_POLL && a.ready != nullptr)) __threadfence();
                     read = a.order ? a.order[idx] : idx;
+                    RADIAN_ASSERT(read >= 0 && read < a.n_reads);
                     const long long foff = a.frame_offsets[read];
                     T = (int)(a.frame_offsets[read + 1] - foff);
                     rp = (const PT *)a.post + foff * 5;
@@ -584,6 +606,7 @@ decode_kernel(const DecodeArgs a)
                     }
                     __syncwarp();
                     if (mk) {
+                        RADIAN_ASSERT(ni >= 0 && ni < cap && ni <= i && i - old_top < kNursery && npar < ni);
                         arena[ni] = ((uint32_t)npar << 2) | (w & 3u);
                         fwd[i - old_top] = (uint32_t)ni;
                     }
@@ -837,6 +860,7 @@ decode_kernel(const DecodeArgs a)
                         const unsigned bal = GBALLOT(comp);
                         if (comp) {
                             const int idx = G + n_ext + __popc(bal & belowg);
+                            RADIAN_ASSERT(idx < 5 * G);
                             sm.key[idx] = (unsigned long long)__double_as_longlong(ec);
                             sm.pos[idx] = (uint16_t)(5 * rank + 1 + c);
                             sm.src[idx] = (uint8_t)(li * 4 + c);
@@ -910,6 +934,7 @@ decode_kernel(const DecodeArgs a)
                         const bool isnew = run && mine && my_rank < bw;
                         const unsigned nbal = GBALLOT(isnew);
                         if (mine) sm.rnk[G + li] = (uint8_t)my_rank;
+                        RADIAN_ASSERT(__popc(nbal) <= G);
                         if (isnew) sm.newlist[__popc(nbal & belowg)] = (uint8_t)(G + li);
                         n_new = __popc(nbal);
                     } else {
@@ -940,6 +965,7 @@ decode_kernel(const DecodeArgs a)
                             const int idx = b0 + li;
                             const bool isnew = run && idx < m && sm.rnk[idx] < bw;
                             const unsigned bal = GBALLOT(isnew);
+                            RADIAN_ASSERT(!isnew || n_new + __popc(bal & belowg) < G);
                             if (isnew) sm.newlist[n_new + __popc(bal & belowg)] = (uint8_t)idx;
                             n_new += __popc(bal);
                         }
@@ -1005,6 +1031,7 @@ decode_kernel(const DecodeArgs a)
                             plane = ((survb >> (ls - gshift)) & 1u) ? (ls - gshift) : -1;
                             prep = (c == p_last) ? 1 : 0;
                             alive = true;
+                            RADIAN_ASSERT(node > 0 && node < cap && p_node >= 0 && p_node < node && item >= G && item < 5 * G);
                             arena[node] = ((uint32_t)p_node << 2) | (uint32_t)c;
                             if (LM) {
                                 gcopy = p_g;
@@ -1091,6 +1118,7 @@ decode_kernel(const DecodeArgs a)
                 if (__any_sync(kFull, ranks_changed)) {
                     // successor lane of every beam and the lane of the best one
                     __syncwarp();
+                    RADIAN_ASSERT(!(run && alive) || (rank >= 0 && rank < na && na <= G));
                     if (run && alive) sm.newlist[rank] = (uint8_t)li;
                     sm.c_rank[li] = rank;
                     __syncwarp();
@@ -1126,6 +1154,7 @@ decode_kernel(const DecodeArgs a)
                 if (n > seq_cap) status = RADIAN_READ_SEQ_OVERFLOW;
                 int c = sm.c_node[li];
                 for (long long i = n - 1; i >= 0; --i) {
+                    RADIAN_ASSERT(c > 0 && c < cap);
                     const uint32_t w = arena[c] & 0x7fffffffu;
                     if (i < seq_cap) a.out_seq[seq_off + i] = (uint8_t)(w & 3u);
                     c = (int)(w >> 2);

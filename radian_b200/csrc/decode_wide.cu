@@ -74,6 +74,7 @@ decode_wide_kernel(const DecodeArgs a)
     uint32_t ctx[BPL], km[BPL];
     int len[BPL], node[BPL], rank[BPL], plane[BPL], last[BPL], succ[BPL];
     bool alive[BPL], gext[BPL], gcopy[BPL];
+    bool tie_ok[BPL];  // a successor with exactly my score is still in the right place (later insertion position)
     int prep[BPL];  // 1 if the live parent (plane) ends in the same symbol as this beam
     int rmax[BPL];  // max high word of the unmerged entries of this beam's table row, or kNoRmaxW
 
@@ -131,6 +132,7 @@ decode_wide_kernel(const DecodeArgs a)
             plane[s] = -1;
             last[s] = 0;
             succ[s] = s * 32 + lane;
+            tie_ok[s] = false;
             km[s] = alive[s] ? 0x80808080u : 0u;
             gext[s] = gcopy[s] = false;
             prep[s] = 0;
@@ -292,7 +294,12 @@ decode_wide_kernel(const DecodeArgs a)
             bool ok = true;
 #pragma unroll
             for (int s = 0; s < BPL; ++s)
-                if (alive[s] && succ[s] != s * 32 + lane) ok = ok && (kcopy[s] > sm.key[succ[s]]);
+                if (alive[s] && succ[s] != s * 32 + lane) {
+                    // (bit-equal scores of two readings of one old ambiguity can last for the rest of the read:
+                    // then the dict insertion positions decide, see decode.cu)
+                    const unsigned long long ks = sm.key[succ[s]];
+                    ok = ok && (kcopy[s] > ks || (kcopy[s] == ks && tie_ok[s]));
+                }
             const unsigned long long kworst = sm.key[last_b];
             {
                 // QUIET frame: order intact, beam full, and by the integer log bound of decode.cu no
@@ -738,6 +745,23 @@ decode_wide_kernel(const DecodeArgs a)
                     succ[s] = (alive[s] && rank[s] + 1 < na) ? (int)sm.byrank[rank[s] + 1] : s * 32 + lane;
                 first = (int)sm.byrank[0];
                 last_b = (int)sm.byrank[na - 1];
+                // dict insertion positions the next frame's copies will have, from the new ranks: is a
+                // successor with exactly my score rightly behind me?
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) sm.srank[s * 32 + lane] = (uint16_t)rank[s];
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) {
+                    int npos = 5 * rank[s];
+                    if (alive[s] && plane[s] >= 0) {
+                        const int pp = 5 * (int)sm.srank[plane[s]] + 1 + last[s];
+                        npos = pp < npos ? pp : npos;
+                    }
+                    sm.pos[s * 32 + lane] = (uint16_t)npos;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) tie_ok[s] = alive[s] && sm.pos[s * 32 + lane] < sm.pos[succ[s]];
                 __syncwarp();
             }
         }

@@ -185,3 +185,62 @@ def test_float64_range_is_wide():
     seqs, scores, _ = decode.beam_search_batch([p], 16, None, None, None, None, return_details=True)
     assert seqs[0] == want[0]
     assert close(scores[0, 0], wsc[0])
+
+
+def tie_read(T, seed, dtype):
+    """A read whose first base is an exact two-way tie (P_A == P_C bit for bit): the labelings 'A...'
+    and 'C...' are multiplied by the same factors ever after and keep bit-equal scores for the rest of
+    the read (oracle == reference on these reads was checked in the build container)."""
+    rng = np.random.default_rng(seed)
+    p = np.zeros((T, 5), dtype)
+    p[:, 4] = 0.9
+    p[:, :4] = 0.025
+    p[5] = [0.3, 0.3, 0.0, 0.0, 0.4]
+    t = 12
+    while t < T - 3:
+        c = rng.integers(0, 4)
+        p[t] = 0.01
+        p[t, c] = 0.95
+        p[t, 4] = 0.02
+        t += rng.integers(4, 12)
+    return p
+
+
+@pytest.mark.parametrize("bw", [2, 6, 16, 40])
+def test_persistent_exact_ties(bw):
+    """Kept beams with bit-equal scores over thousands of frames: ordered by the reference's dict
+    insertion positions (stable sort, decode.py:35-39) in every frame, including the frames that only
+    update the scores."""
+    from radian_b200 import decode
+
+    mats = [tie_read(3000, s, np.float32 if s % 2 else np.float64) for s in range(6)]
+    want, wsc, _ = oracle_batch([m for m in mats if m.dtype == np.float32], bw, None, 0)
+    want64, wsc64, _ = oracle_batch([m for m in mats if m.dtype == np.float64], bw, None, 0)
+    seqs, scores, _ = decode.beam_search_batch(mats, bw, None, None, None, None, return_details=True)
+    assert [s for s, m in zip(seqs, mats) if m.dtype == np.float32] == want
+    assert [s for s, m in zip(seqs, mats) if m.dtype == np.float64] == want64
+    assert all(len(s) > 300 for s in seqs)
+
+
+def test_resident_batch_with_one_long_read(table12):
+    """The resident entry point on a batch that one long read dominates: the launch planner gives that
+    read a warp to itself and fewer CTAs per SM (csrc/decode.cu, plan_launch); results as ever."""
+    import torch
+
+    from radian_b200 import decode, synth
+
+    tab, lm = table12
+    nb = np.concatenate([np.full(40, 200), [6000], np.full(7, 900)])
+    post, off = synth.make_reads(nb, seed=91, device="cuda")
+    T = off[1:] - off[:-1]
+    order = torch.argsort(T, descending=True).to(torch.int32)
+    res = decode.decode_batch_device(post, off, 16, lm, 0.5, 0.5, max_frames=int(T.max()), order=order, counters=True)
+    torch.cuda.synchronize()
+    assert int(res.status.abs().sum()) == 0
+    got = res.strings()
+    p, o = post.cpu().numpy(), off.cpu().numpy()
+    want, wsc, wcnt = oracle_batch(split(p, o), 16, tab, 12)
+    assert got == want
+    assert np.array_equal(res.counters.cpu().numpy()[:, :2].astype(np.uint64), wcnt)
+    sc = res.scores.cpu().numpy()
+    assert all(close(sc[i, 0], wsc[i]) for i in range(len(nb)))
