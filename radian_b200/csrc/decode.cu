@@ -263,18 +263,9 @@ __device__ __forceinline__ int row_bound(const double *row, uint32_t km)
         const uint32_t kc32 = (uint32_t)__double2hiint(nptot);                                               \
         const uint32_t ksucc = __shfl_sync(kFull, kc32, q_succ);                                             \
         const uint32_t kworst = __shfl_sync(kFull, kc32, last_lane);                                         \
-        const bool rest = kworst >= 0x00100000u && __double2hiint(ptot) + z < (int)kworst;                   \
-        if (!__all_sync(kFull, (IDLE && q_idle) || (kc32 >= ksucc + q_inc && rest))) {                       \
-            /* Two copies next to each other in the order may agree in their high words for thousands of   \
-               frames (two readings of an old ambiguous position, multiplied by the same factors ever       \
-               since): then the low words decide, and for equal scores the insertion positions (tie_ok). */ \
-            const bool hitie = q_succ != lane && kc32 == ksucc;                                              \
-            if (!__any_sync(kFull, hitie)) break;                                                            \
-            const uint32_t lo = (uint32_t)__double2loint(nptot);                                             \
-            const uint32_t los = __shfl_sync(kFull, lo, q_succ);                                             \
-            const bool ord = hitie ? (lo > los || (lo == los && tie_ok)) : kc32 >= ksucc + q_inc;            \
-            if (!__all_sync(kFull, (IDLE && q_idle) || (ord && rest))) break;                                \
-        }                                                                                                    \
+        const bool quiet = (IDLE && q_idle) || (kc32 >= ksucc + q_inc && kworst >= 0x00100000u &&            \
+                                                __double2hiint(ptot) + z < (int)kworst);                     \
+        if (!__all_sync(kFull, quiet)) break;                                                                \
         if (COUNT && LM) {                                                                                   \
             n_lookup += (unsigned)c_lookup;                                                                  \
             if (fgate_) n_combine += (unsigned)c_combine;                                                    \
@@ -341,6 +332,13 @@ decode_kernel(const DecodeArgs a)
     bool rmax_prov = false;  // rmax is the table-wide bound: this beam's row was in flight when it was set
     int succ = 0;        // absolute lane of the beam ranked right after this one (own lane: none)
     bool tie_ok = false; // a successor with exactly my score is still in the right place (its insertion position is later)
+    // Two copies next to each other in the order may agree in their high words for thousands of frames (two
+    // readings of an old ambiguous position, multiplied by the same factors ever since).  The quiet loop only
+    // compares high words; for such a pair, once the long way has confirmed the order on all 64 bits, it
+    // accepts equal high words (hitie).  The low words could cross unseen while the high words stay equal; the
+    // next frame that takes the long way re-checks all 64 bits, nothing in between uses the order, and the end
+    // of the read picks its best beam exactly.
+    bool hitie = false;
     uint32_t km = 0;     // byte c = 0x80: this lane holds a beam and its extension by c is a candidate
                          // of its own (not merged into a live child's copy); 0 for a dead lane
     // ---- per-read (group-uniform) state
@@ -373,9 +371,10 @@ decode_kernel(const DecodeArgs a)
         q_ox = (unsigned)(((LM && gcopy) ? 6 + last : last) * 8);                                          \
         q_oy = (LM && gcopy) ? 88u : 80u;                                                                  \
         /* order check kc32 >= k(succ) + inc: strict for a beam with a successor, void for the last one    \
-           (succ == lane); a beam with room left is never quiet: every extension is a candidate */        \
+           (succ == lane) and not strict for a pair that shares its high word (hitie, below); a beam with  \
+           room left is never quiet: every extension is a candidate */                                     \
         q_succ = full_ ? succ : lane;                                                                      \
-        q_inc = (full_ && succ == lane) ? 0u : 1u;                                                         \
+        q_inc = (full_ && (succ == lane || hitie)) ? 0u : 1u;                                              \
         if (COUNT && LM) {                                                                                 \
             const int len_ = sm.c_len[li];                                                                \
             const bool lc_ = run_ && alive && len_ >= L + 1, le_ = run_ && alive && len_ >= L;               \
@@ -495,6 +494,7 @@ decode_kernel(const DecodeArgs a)
                     gext = gcopy = false;
                     succ = lane;
                     tie_ok = false;
+                    hitie = false;
                     km = alive ? 0x80808080u : 0u;
                     first_lane = gshift;
                     last_lane = gshift;
@@ -1138,6 +1138,12 @@ decode_kernel(const DecodeArgs a)
                     if (run) tie_ok = npos < spos;
                     __syncwarp();
                 }
+                {
+                    const unsigned long long mine = (unsigned long long)__double_as_longlong(ptot);
+                    const unsigned long long next = __shfl_sync(kFull, mine, succ);
+                    hitie = run && alive && succ != lane && (mine >> 32) == (next >> 32) &&
+                            (mine > next || (mine == next && tie_ok));
+                }
                 REFRESH();
                 ++it;
             }
@@ -1145,11 +1151,23 @@ decode_kernel(const DecodeArgs a)
         if (live) t += nrun;
 
         // ------------------------------------------------------------ end of read
-        const int succ_first = __shfl_sync(kFull, succ, first_lane);  // lane of the second best beam
+        int succ_first = __shfl_sync(kFull, succ, first_lane);  // lane of the second best beam
+        int best_lane = first_lane;
+        {
+            // the best two beams, exactly: if they share their high word, their low words may have crossed
+            // since the order was last checked on all 64 bits (hitie)
+            const unsigned long long mine = (unsigned long long)__double_as_longlong(ptot);
+            const unsigned long long p1 = __shfl_sync(kFull, mine, first_lane), p2 = __shfl_sync(kFull, mine, succ_first);
+            const bool t1 = __shfl_sync(kFull, (int)tie_ok, first_lane) != 0;
+            if (succ_first != first_lane && (p2 > p1 || (p2 == p1 && !t1))) {
+                best_lane = succ_first;
+                succ_first = first_lane;
+            }
+        }
         if (live && t >= T) {
             const long long seq_off = a.seq_offsets[read];
             const long long seq_cap = a.seq_offsets[read + 1] - seq_off;
-            if (status == 0 && lane == first_lane) {
+            if (status == 0 && lane == best_lane) {
                 const long long n = sm.c_len[li];
                 if (n > seq_cap) status = RADIAN_READ_SEQ_OVERFLOW;
                 int c = sm.c_node[li];
@@ -1161,7 +1179,7 @@ decode_kernel(const DecodeArgs a)
                 }
                 a.out_len[read] = n;
                 a.out_score[2 * read] = final_log_score(ptot, kacc);
-                if (succ_first == first_lane) a.out_score[2 * read + 1] = NAN;
+                if (succ_first == best_lane) a.out_score[2 * read + 1] = NAN;
                 a.out_status[read] = status;
                 if (a.out_counters) {
                     a.out_counters[4 * read] = n_lookup;
@@ -1176,7 +1194,7 @@ decode_kernel(const DecodeArgs a)
                     a.out_counters[4 * read + 3] = n_stage2;
                 }
             }
-            if (status == 0 && succ_first != first_lane && lane == succ_first)
+            if (status == 0 && succ_first != best_lane && lane == succ_first)
                 a.out_score[2 * read + 1] = final_log_score(ptot, kacc);
             if (status > RADIAN_READ_SEQ_OVERFLOW && li == 0) {
                 if (status != RADIAN_READ_KEY_ERROR) a.out_len[read] = 0;  // (KeyError: holds the context index)

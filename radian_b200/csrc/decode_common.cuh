@@ -37,7 +37,7 @@ __device__ __forceinline__ unsigned long long hash_step(unsigned long long h, in
 
 // natural log of p x 2^kacc (a read's final score).  The value is split into mantissa and exponent
 // first, so that the result does not depend on where the read happened to be rescaled.
-__device__ __forceinline__ double final_log_score(double p, long long kacc)
+__device__ __noinline__ double final_log_score(double p, long long kacc)
 {
     if (!(p > 0.0)) return -INFINITY;
     int e;
@@ -152,6 +152,29 @@ __device__ __forceinline__ void record_ext(double *rec, const double *v, const d
     }
 }
 
+// The entropy gate H_s > s_threshold in the reference's exact operation order (decode.py:73-76, 93), for
+// the frames whose float32 estimate lands within 1e-4 of the threshold.  Out of line: four double
+// logarithms are a few hundred instructions that the frame loop's instruction cache should never see.
+__device__ __noinline__ bool exact_gate(double q0, double q1, double q2, double q3, double s_thr)
+{
+    const double q[4] = {q0, q1, q2, q3};
+    double H = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (q[i] > 0.0) H = __dadd_rn(H, __dmul_rn(q[i], log(q[i])));
+    return -H > s_thr;
+}
+// float32 input: numpy >= 2 keeps the sum and the products in float32 and compares in float32
+__device__ __noinline__ bool exact_gate(float q0, float q1, float q2, float q3, double s_thr)
+{
+    const float q[4] = {q0, q1, q2, q3};
+    float H = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (q[i] > 0.0f) H = __fadd_rn(H, __fmul_rn(q[i], __double2float_rn(log((double)q[i]))));
+    return -H > (float)s_thr;
+}
+
 // SCALE (float64 input only): a row whose largest entry is below 2^-64 is multiplied by an exact
 // power of two that brings it near 1; the exponent is returned and the caller adds it to the
 // read's score exponent.  Every quantity the search derives from the row (S, p/S, the entropy
@@ -191,13 +214,7 @@ __device__ __forceinline__ int make_record(const double *raw, double s_thr, doub
             if (qf > 0.0f) Ha -= qf * __logf(qf);
         }
         bool gate = Ha > (float)s_thr;
-        if (!(fabsf(Ha - (float)s_thr) > 1e-4f)) {
-            double H = 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (q[i] > 0.0) H = __dadd_rn(H, __dmul_rn(q[i], log(q[i])));
-            gate = -H > s_thr;
-        }
+        if (!(fabsf(Ha - (float)s_thr) > 1e-4f)) gate = exact_gate(q[0], q[1], q[2], q[3], s_thr);
         rec[5] = gate ? 1.0 : 0.0;
         record_ext<LM, EXT, COMPACT>(rec, v, q, S, gate);
     } else {
@@ -225,13 +242,7 @@ __device__ __forceinline__ int make_record(const float *raw, double s_thr, doubl
             if (q[i] > 0.0f) Ha -= q[i] * __logf(q[i]);
         }
         bool gate = Ha > (float)s_thr;
-        if (!(fabsf(Ha - (float)s_thr) > 1e-4f)) {
-            float H = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (q[i] > 0.0f) H = __fadd_rn(H, __fmul_rn(q[i], __double2float_rn(log((double)q[i]))));
-            gate = -H > (float)s_thr;
-        }
+        if (!(fabsf(Ha - (float)s_thr) > 1e-4f)) gate = exact_gate(q[0], q[1], q[2], q[3], s_thr);
         rec[5] = gate ? 1.0 : 0.0;
         const double vd[4] = {(double)v[0], (double)v[1], (double)v[2], (double)v[3]};
         const double qd[4] = {(double)q[0], (double)q[1], (double)q[2], (double)q[3]};

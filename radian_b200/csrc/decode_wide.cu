@@ -141,7 +141,7 @@ decode_wide_kernel(const DecodeArgs a)
         int first = 0, last_b = 0;  // beam ids of the best and the worst ranked beam
         int top = 1, old_top = 1, na = 1, status = 0;  // node 0 = the empty labeling
         long long kacc = 0;
-        unsigned long long n_lookup = 0, n_combine = 0, n_tie = 0;
+        unsigned long long n_lookup = 0, n_combine = 0, n_tie = 0, n_diag = 0;  // n_diag: see include/radian_b200.h
 
         __syncwarp();
         if (lane < T) prefetch_row(&sm.raw[lane * 5], rp, lane);
@@ -325,6 +325,7 @@ decode_wide_kernel(const DecodeArgs a)
                     const int ub = __double2hiint(ptot[s]) + z + ((LM && gated) ? 0 : kSlackPlain);
                     quiet = quiet && ub < hw;
                 }
+                if (COUNT && fgate) n_diag += 1ull << 32;
                 if (__all_sync(kFull, quiet)) {
 #pragma unroll
                     for (int s = 0; s < BPL; ++s) {
@@ -335,6 +336,7 @@ decode_wide_kernel(const DecodeArgs a)
                     continue;
                 }
             }
+            if (COUNT) n_diag += 1;  // a frame that has to look at extensions
             const bool order_ok = __all_sync(kFull, ok);
 
             // EXTEND (decode.py:177-201)
@@ -799,7 +801,7 @@ decode_wide_kernel(const DecodeArgs a)
                         a.out_counters[4 * read] = n_lookup;
                         a.out_counters[4 * read + 1] = n_combine;
                         a.out_counters[4 * read + 2] = n_tie;
-                        a.out_counters[4 * read + 3] = 0;
+                        a.out_counters[4 * read + 3] = n_diag;
                     }
                 }
                 if (second != first && b == second)

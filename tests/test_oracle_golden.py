@@ -98,3 +98,31 @@ def test_preprocess_matches_reference():
             assert w.shape == (int(nw), int(W)) and p == int(pad)
             assert golden_io.window_checksum(w) == (s0, s1)
     assert n_err == 4 and n_int == 3
+
+
+@pytest.mark.reference
+def test_persistent_tie_reads_match_reference():
+    """The reads of tests/test_gpu_headline.py::test_persistent_exact_ties (two labelings with bit-equal
+    scores for the whole read): the oracle orders them as the unmodified reference does (stable sort
+    over dict insertion order, decode.py:35-39).  Build container only."""
+    from oracle import ref_loader
+
+    dec, _, _ = ref_loader.load()
+    rng_T = 300
+    for seed in range(3):
+        for bw in (2, 6, 16, 40):
+            rng = np.random.default_rng(seed)
+            p = np.zeros((rng_T, 5), np.float32 if seed % 2 else np.float64)
+            p[:, 4] = 0.9
+            p[:, :4] = 0.025
+            p[5] = [0.3, 0.3, 0.0, 0.0, 0.4]
+            t = 12
+            while t < rng_T - 3:
+                c = rng.integers(0, 4)
+                p[t] = 0.01
+                p[t, c] = 0.95
+                p[t, 4] = 0.02
+                t += rng.integers(4, 12)
+            want = dec.beam_search(p, "ACGT", bw, None, None, None, None, None)
+            got = "".join("ACGT"[s] for s in oracle.beam_search(p, bw)[0])
+            assert got == want
