@@ -117,6 +117,45 @@ __device__ __forceinline__ int row_bound(const double *row, uint32_t km)
                max(rb.y & (int)byte_sign_mask<2>(km), rb.w & (int)byte_sign_mask<3>(km)));
 }
 
+// ---- rare, bulky pieces of the long way, out of line: the frame loop's instruction cache holds the
+// usual route only (ncu on the bench launch: with everything inline the kernel was 80 KB of code and
+// stalled 2.2 cycles per issued instruction on instruction fetch; profiles/r2_history.md)
+
+// exact rank of one candidate among the first `m` candidates of the group's list: (float64 bits desc,
+// dict insertion position asc); bit 16 of the result: another candidate within 2^-40 of it
+template <typename SM, bool COUNT>
+__device__ __noinline__ int exact_rank(const SM &sm, int m, int self, unsigned long long k, int p)
+{
+    int cnt = 0;
+    bool near = false;
+    for (int j = 0; j < m; ++j) {
+        const int pj = sm.pos[j];
+        const unsigned long long kj = sm.key[j];
+        cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
+        // two candidates within 2^-40 of each other: a decision that the log-domain reference takes on
+        // its own rounding noise
+        if (COUNT) near = near || (j != self && pj != kPosInvalid && k != 0ull && kj - k + 4096ull < 8192ull);
+    }
+    return (cnt > 255 ? 255 : cnt) | (near ? 0x10000 : 0);
+}
+
+// all candidates of the list against each other, exactly (a beam that is still filling up has more
+// extensions than lanes); ranks to sm.rnk, returns the near-tie flag
+template <int G, typename SM, bool COUNT>
+__device__ __noinline__ bool exact_rank_all(SM &sm, int m, int li)
+{
+    bool near = false;
+    for (int idx = li; idx < m; idx += G) {
+        const int p = sm.pos[idx];
+        if (p != kPosInvalid) {
+            const int r = exact_rank<SM, COUNT>(sm, m, idx, sm.key[idx], p);
+            sm.rnk[idx] = (uint8_t)(r & 0xff);
+            near = near || (r >> 16);
+        }
+    }
+    return near;
+}
+
 // The COUNT instantiations also report, in the fourth counter of a read, (frames whose entropy gate
 // H_s > s_threshold was open << 32) | frames that took the long way (see include/radian_b200.h)
 #define RADIAN_STAT(x) if (COUNT) { x }
@@ -837,14 +876,9 @@ decode_kernel(const DecodeArgs a)
                         sm.pos[li] = (uint16_t)pos_copy;
                         __syncwarp();
                         if (tied && av) {
-                            int cnt = 0;
-                            for (int j = 0; j < G; ++j) {
-                                const int pj = sm.pos[j];
-                                const unsigned long long kj = sm.key[j];
-                                cnt += (pj != kPosInvalid) && (kj > kcopy || (kj == kcopy && pj < pos_copy));
-                                if (COUNT) near = near || (j != li && pj != kPosInvalid && kcopy != 0ull && kj - kcopy + 4096ull < 8192ull);
-                            }
-                            base = cnt;
+                            const int r = exact_rank<GroupSmem<G, LM, PT>, COUNT>(sm, G, li, kcopy, pos_copy);
+                            base = r & 0xff;
+                            near = near || (r >> 16);
                         }
                         __syncwarp();
                     }
@@ -911,25 +945,22 @@ decode_kernel(const DecodeArgs a)
                         const int mv = na + n_ext;
                         const bool xtie = run && ssum != mv * (mv - 1) / 2;
                         if (__any_sync(kFull, xtie)) {
-                            // two candidates agree in their high words: every extension in turn against
-                            // all copies and all extensions, exactly (float64 bits desc, position asc)
-                            if (xtie) new_rank = av ? base : 255;
-                            for (int e = 0; e < nmax; ++e) {
-                                const unsigned long long ke = sm.key[G + e];
-                                const int pe = sm.pos[G + e];
-                                const bool valid = xtie && e < n_ext;
-                                const bool ibeat = av && (kcopy > ke || (kcopy == ke && pos_copy < pe));
-                                const bool xbeat = mine && (myk > ke || (myk == ke && myp < pe));
-                                const unsigned b1 = GBALLOT(ibeat), b2 = GBALLOT(xbeat);
-                                if (valid && av && !ibeat) ++new_rank;
-                                if (valid && li == e) my_rank = __popc(b1) + __popc(b2);
-                                // two candidates within 2^-40 of each other: a decision that the log-domain
-                                // reference takes on its own rounding noise
-                                if (COUNT)
-                                    near = near || (valid && ke != 0ull &&
-                                                    ((av && kcopy - ke + 4096ull < 8192ull) ||
-                                                     (mine && li != e && myk - ke + 4096ull < 8192ull)));
+                            // two candidates agree in their high words: copies and extensions against the
+                            // whole list, exactly (float64 bits desc, position asc)
+                            sm.key[li] = kcopy;
+                            sm.pos[li] = (uint16_t)pos_copy;
+                            __syncwarp();
+                            if (xtie && av) {
+                                const int r = exact_rank<GroupSmem<G, LM, PT>, COUNT>(sm, m, li, kcopy, pos_copy);
+                                new_rank = r & 0xff;
+                                near = near || (r >> 16);
                             }
+                            if (xtie && mine) {
+                                const int r = exact_rank<GroupSmem<G, LM, PT>, COUNT>(sm, m, G + li, myk, myp);
+                                my_rank = r & 0xff;
+                                near = near || (r >> 16);
+                            }
+                            __syncwarp();
                         }
                         const bool isnew = run && mine && my_rank < bw;
                         const unsigned nbal = GBALLOT(isnew);
@@ -943,22 +974,7 @@ decode_kernel(const DecodeArgs a)
                         sm.key[li] = kcopy;
                         sm.pos[li] = (uint16_t)pos_copy;
                         __syncwarp();
-                        if (run) {
-                            for (int idx = li; idx < m; idx += G) {
-                                const int p = sm.pos[idx];
-                                if (p != kPosInvalid) {
-                                    const unsigned long long k = sm.key[idx];
-                                    int cnt = 0;
-                                    for (int j = 0; j < m; ++j) {
-                                        const int pj = sm.pos[j];
-                                        const unsigned long long kj = sm.key[j];
-                                        cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
-                                        if (COUNT) near = near || (j != idx && pj != kPosInvalid && k != 0ull && kj - k + 4096ull < 8192ull);
-                                    }
-                                    sm.rnk[idx] = (uint8_t)(cnt > 255 ? 255 : cnt);
-                                }
-                            }
-                        }
+                        if (run) near = exact_rank_all<G, GroupSmem<G, LM, PT>, COUNT>(sm, m, li) || near;
                         __syncwarp();
                         if (run) new_rank = av ? (int)sm.rnk[li] : 255;
                         for (int b0 = G; b0 < G + nmax; b0 += G) {

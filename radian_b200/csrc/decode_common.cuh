@@ -37,7 +37,7 @@ __device__ __forceinline__ unsigned long long hash_step(unsigned long long h, in
 
 // natural log of p x 2^kacc (a read's final score).  The value is split into mantissa and exponent
 // first, so that the result does not depend on where the read happened to be rescaled.
-__device__ __noinline__ double final_log_score(double p, long long kacc)
+static __device__ __noinline__ double final_log_score(double p, long long kacc)
 {
     if (!(p > 0.0)) return -INFINITY;
     int e;
@@ -155,7 +155,7 @@ __device__ __forceinline__ void record_ext(double *rec, const double *v, const d
 // The entropy gate H_s > s_threshold in the reference's exact operation order (decode.py:73-76, 93), for
 // the frames whose float32 estimate lands within 1e-4 of the threshold.  Out of line: four double
 // logarithms are a few hundred instructions that the frame loop's instruction cache should never see.
-__device__ __noinline__ bool exact_gate(double q0, double q1, double q2, double q3, double s_thr)
+static __device__ __noinline__ bool exact_gate(double q0, double q1, double q2, double q3, double s_thr)
 {
     const double q[4] = {q0, q1, q2, q3};
     double H = 0.0;
@@ -165,7 +165,7 @@ __device__ __noinline__ bool exact_gate(double q0, double q1, double q2, double 
     return -H > s_thr;
 }
 // float32 input: numpy >= 2 keeps the sum and the products in float32 and compares in float32
-__device__ __noinline__ bool exact_gate(float q0, float q1, float q2, float q3, double s_thr)
+static __device__ __noinline__ bool exact_gate(float q0, float q1, float q2, float q3, double s_thr)
 {
     const float q[4] = {q0, q1, q2, q3};
     float H = 0.0f;
