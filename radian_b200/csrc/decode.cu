@@ -117,9 +117,90 @@ __device__ __forceinline__ int row_bound(const double *row, uint32_t km)
                max(rb.y & (int)byte_sign_mask<2>(km), rb.w & (int)byte_sign_mask<3>(km)));
 }
 
+// -DRADIAN_CHECKS: bounds checks of our own on every index the long way computes (arena, forwarding
+// table, candidate lists); a violation prints where and traps, which fails the launch.  compute-sanitizer
+// is closed on the build pool (profiles/r2_sanitizer_closed.txt); the test-suite is run once with this
+// build instead (profiles/r2_checks_build.txt).
+#ifdef RADIAN_CHECKS
+#define RADIAN_ASSERT(c)                                                                       \
+    do {                                                                                       \
+        if (!(c)) {                                                                            \
+            printf("radian check failed: %s (decode.cu:%d, block %d thread %d)\n", #c, __LINE__, \
+                   (int)blockIdx.x, (int)threadIdx.x);                                         \
+            __trap();                                                                          \
+        }                                                                                      \
+    } while (0)
+#else
+#define RADIAN_ASSERT(c)
+#endif
+
 // ---- rare, bulky pieces of the long way, out of line: the frame loop's instruction cache holds the
 // usual route only (ncu on the bench launch: with everything inline the kernel was 80 KB of code and
 // stalled 2.2 cycles per issued instruction on instruction fetch; profiles/r2_history.md)
+
+// Nursery collection of the back-pointer arena (whole warps call it, once in thousands of frames).
+// Returns the new top of the group's arena.
+template <int G>
+__device__ __noinline__ int collect_nursery(int *c_node, uint32_t *arena, uint32_t *fwd, int old_top, int top,
+                                            bool run, bool alive, int li, int gshift)
+{
+    constexpr unsigned GBITS = (G == 32) ? kFull : ((1u << G) - 1u);
+    const unsigned belowg = (1u << li) - 1u;
+    // 1. mark nursery nodes reachable from a live beam (stop at the old generation or
+    //    at a node somebody marked in an earlier step)
+    const int node = c_node[li];
+    int cur = node;
+    bool walking = run && alive && cur >= old_top;
+    while (__any_sync(kFull, walking)) {
+        if (walking) {
+            const uint32_t w = arena[cur];
+            if (w >> 31) {
+                walking = false;
+            } else {
+                arena[cur] = w | 0x80000000u;
+                cur = (int)(w >> 2);
+                walking = cur >= old_top;
+            }
+        }
+        __syncwarp();
+    }
+    // 2. slide marked nodes down in index order (parents always precede children);
+    //    fwd[] keeps the new index of every moved node for its children and the beams
+    int iters = run ? (top - old_top + G - 1) / G : 0;
+#pragma unroll
+    for (int o = 16; o >= G; o >>= 1) {
+        const int x = __shfl_xor_sync(kFull, iters, o);
+        iters = x > iters ? x : iters;
+    }
+    int cnt = old_top;
+    for (int k = 0; k < iters; ++k) {
+        const int base = old_top + k * G;
+        const int i = base + li;
+        const uint32_t w = (run && i < top) ? arena[i] : 0u;
+        const bool mk = (w >> 31) != 0;
+        const unsigned bal = (__ballot_sync(kFull, mk) >> gshift) & GBITS;
+        const int ni = cnt + __popc(bal & belowg);
+        const int par = (int)((w & 0x7fffffffu) >> 2);
+        int npar = par;
+        if (mk && par >= old_top) {
+            if (par >= base)
+                npar = cnt + __popc(bal & ((1u << (par - base)) - 1u));
+            else
+                npar = (int)fwd[par - old_top];
+        }
+        __syncwarp();
+        if (mk) {
+            RADIAN_ASSERT(ni >= 0 && ni <= i && i - old_top < kNursery && npar < ni);
+            arena[ni] = ((uint32_t)npar << 2) | (w & 3u);
+            fwd[i - old_top] = (uint32_t)ni;
+        }
+        cnt += __popc(bal);
+        __syncwarp();
+    }
+    if (run && alive && node >= old_top) c_node[li] = (int)fwd[node - old_top];
+    __syncwarp();
+    return cnt;
+}
 
 // exact rank of one candidate among the first `m` candidates of the group's list: (float64 bits desc,
 // dict insertion position asc); bit 16 of the result: another candidate within 2^-40 of it
@@ -159,23 +240,6 @@ __device__ __noinline__ bool exact_rank_all(SM &sm, int m, int li)
 // The COUNT instantiations also report, in the fourth counter of a read, (frames whose entropy gate
 // H_s > s_threshold was open << 32) | frames that took the long way (see include/radian_b200.h)
 #define RADIAN_STAT(x) if (COUNT) { x }
-
-// -DRADIAN_CHECKS: bounds checks of our own on every index the long way computes (arena, forwarding
-// table, candidate lists); a violation prints where and traps, which fails the launch.  compute-sanitizer
-// is closed on the build pool (profiles/r2_sanitizer_closed.txt); the test-suite is run once with this
-// build instead (profiles/r2_checks_build.txt).
-#ifdef RADIAN_CHECKS
-#define RADIAN_ASSERT(c)                                                                       \
-    do {                                                                                       \
-        if (!(c)) {                                                                            \
-            printf("radian check failed: %s (decode.cu:%d, block %d thread %d)\n", #c, __LINE__, \
-                   (int)blockIdx.x, (int)threadIdx.x);                                         \
-            __trap();                                                                          \
-        }                                                                                      \
-    } while (0)
-#else
-#define RADIAN_ASSERT(c)
-#endif
 
 // (A/B on B200, profiles/r2_history.md: with one frame in eight taking the long way, a pair loop spends
 // on discarded second frames what it saves on votes; it only pays for a warp that is alone on its
@@ -601,59 +665,7 @@ decode_kernel(const DecodeArgs a)
             // checked once per tile: a frame adds at most G nodes per read, a tile at most G*G
             if (__any_sync(kFull, run && (top + G * G > old_top + kNursery || top + G * G > cap))) {
                 // every running group of the warp collects (early collection is harmless)
-                // 1. mark nursery nodes reachable from a live beam (stop at the old generation or
-                //    at a node somebody marked in an earlier step)
-                const int node = sm.c_node[li];
-                int cur = node;
-                bool walking = run && alive && cur >= old_top;
-                while (__any_sync(kFull, walking)) {
-                    if (walking) {
-                        const uint32_t w = arena[cur];
-                        if (w >> 31) {
-                            walking = false;
-                        } else {
-                            arena[cur] = w | 0x80000000u;
-                            cur = (int)(w >> 2);
-                            walking = cur >= old_top;
-                        }
-                    }
-                    __syncwarp();
-                }
-                // 2. slide marked nodes down in index order (parents always precede children);
-                //    fwd[] keeps the new index of every moved node for its children and the beams
-                int iters = run ? (top - old_top + G - 1) / G : 0;
-#pragma unroll
-                for (int o = 16; o >= G; o >>= 1) {
-                    const int x = __shfl_xor_sync(kFull, iters, o);
-                    iters = x > iters ? x : iters;
-                }
-                int cnt = old_top;
-                for (int k = 0; k < iters; ++k) {
-                    const int base = old_top + k * G;
-                    const int i = base + li;
-                    const uint32_t w = (run && i < top) ? arena[i] : 0u;
-                    const bool mk = (w >> 31) != 0;
-                    const unsigned bal = GBALLOT(mk);
-                    const int ni = cnt + __popc(bal & belowg);
-                    const int par = (int)((w & 0x7fffffffu) >> 2);
-                    int npar = par;
-                    if (mk && par >= old_top) {
-                        if (par >= base)
-                            npar = cnt + __popc(bal & ((1u << (par - base)) - 1u));
-                        else
-                            npar = (int)fwd[par - old_top];
-                    }
-                    __syncwarp();
-                    if (mk) {
-                        RADIAN_ASSERT(ni >= 0 && ni < cap && ni <= i && i - old_top < kNursery && npar < ni);
-                        arena[ni] = ((uint32_t)npar << 2) | (w & 3u);
-                        fwd[i - old_top] = (uint32_t)ni;
-                    }
-                    cnt += __popc(bal);
-                    __syncwarp();
-                }
-                if (run && alive && node >= old_top) sm.c_node[li] = (int)fwd[node - old_top];
-                __syncwarp();
+                const int cnt = collect_nursery<G>(sm.c_node, arena, fwd, old_top, top, run, alive, li, gshift);
                 if (run) {
                     old_top = cnt;
                     top = cnt;
@@ -933,6 +945,7 @@ decode_kernel(const DecodeArgs a)
                             my_rank += (k4.x > myx) + (k4.y > myx) + (k4.z > myx) + (k4.w > myx);
                         }
                         const int jend = G / 4 + (nmax + 3) / 4;
+#pragma unroll 1
                         for (int j = G / 4; j < jend; ++j) {
                             const uint4 k4 = kv[j];
                             my_rank += (k4.x > myx) + (k4.y > myx) + (k4.z > myx) + (k4.w > myx);
