@@ -521,7 +521,8 @@ def run_decode(a, world, rank, local, device):
     if e2e:
         # all ranks started together: whole-job bases over the slowest rank's time
         e2e_line = {"value": float(pr[:, 11].sum() / pr[:, 12].max()), "unit": UNIT,
-                    "h2d_bytes_per_step": e2e["bytes_in"], "d2h_bytes_per_step": e2e["bytes_out"],
+                    "h2d_bytes_per_step": e2e["bytes_in"] * world, "d2h_bytes_per_step": e2e["bytes_out"] * world,
+                    "h2d_gbps_per_rank": e2e["bytes_in"] / float(pr[:, 12].max()) / 1e9,
                     "reads_per_call": e2e["reads"], "sec_per_call": e2e["sec"],
                     "what": "radian_decode_batch_host on page-locked buffers + FASTA records formed, per rank",
                     "fasta_bytes_per_call": e2e["fasta_bytes"]}

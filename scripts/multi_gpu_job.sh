@@ -1,5 +1,5 @@
 #!/bin/bash
-# One 8-GPU box: BASELINE configs[3] (chunk mode) and one configs[4] cell at 2/4/8 GPUs, the headline at 8
+# One 8-GPU box: the headline at 8 GPUs, BASELINE configs[3] (chunk mode) and one configs[4] cell at 8
 # (again with the per-rank batches rotated by one device if some rank is more than 3 % slower than the
 # fastest: slow device or slow batch?), and the sharded decode test.  Lines go to gpurun_out/r2_multi_*.
 cd "$(dirname "$0")/.." || exit 1
@@ -10,15 +10,10 @@ run() {  # run <n> <devices> <port> <tag> <bench args...>
       --master-port "$port" bench.py --gpus "$n" "$@" 2> "$out/r2_multi_${tag}_n$n.err" | tail -1 > "$out/r2_multi_${tag}_n$n.json"
 }
 QUICK="--steps 3 --warmup 3 --no-cpu --no-e2e --check-reads 8"
-run 2 0,1 29521 c4chunk --workload c4-chunk $QUICK &
-run 4 2,3,4,5 29522 c4chunk --workload c4-chunk $QUICK &
-wait
-run 2 0,1 29523 c5 --workload c5:16:12:1 $QUICK &
-run 4 2,3,4,5 29524 c5 --workload c5:16:12:1 $QUICK &
-wait
-run 8 0,1,2,3,4,5,6,7 29525 c4chunk --workload c4-chunk --steps 3 --warmup 3 --no-cpu --check-reads 8
+run 8 0,1,2,3,4,5,6,7 29527 c3 --steps 3 --warmup 3 --no-cpu --check-reads 64
+run 8 0,1,2,3,4,5,6,7 29525 c4chunk --workload c4-chunk $QUICK
 run 8 0,1,2,3,4,5,6,7 29526 c5 --workload c5:16:12:1 $QUICK
-run 8 0,1,2,3,4,5,6,7 29527 c3 --steps 3 --warmup 3 --cpu-reads 64 --check-reads 64
+python -m pytest tests/test_multi_gpu.py -q -m gpu 2>&1 | tail -3 > $out/r2_multi_gpu_test.txt
 python - <<'PY'
 import json, subprocess, sys
 d = json.load(open("gpurun_out/r2_multi_c3_n8.json"))
@@ -29,7 +24,6 @@ PY
 if [ "$(cat $out/r2_multi_need_rotate)" = "1" ]; then
   run 8 0,1,2,3,4,5,6,7 29528 c3rot --rotate 1 --steps 3 --warmup 3 --no-cpu --no-e2e --check-reads 8
 fi
-python -m pytest tests/test_multi_gpu.py -q -m gpu 2>&1 | tail -3 > $out/r2_multi_gpu_test.txt
 for f in $out/r2_multi_*_n*.json; do python - "$f" <<'PY'
 import json, sys
 try:
