@@ -107,16 +107,6 @@ __device__ __noinline__ int poll_arrivals(const int *ready, int *stop_flag, int 
     return landed;
 }
 
-// max over the symbols c whose extension is a candidate of its own (bit 7 of byte c of km) of the high
-// word of the table value r_c; row = the four float64 of a beam's extend-context
-__device__ __forceinline__ int row_bound(const double *row, uint32_t km)
-{
-    const int4 ra = *reinterpret_cast<const int4 *>(row);      // r0 lo,hi r1 lo,hi
-    const int4 rb = *reinterpret_cast<const int4 *>(row + 2);  // r2, r3
-    return max(max(ra.y & (int)byte_sign_mask<0>(km), ra.w & (int)byte_sign_mask<1>(km)),
-               max(rb.y & (int)byte_sign_mask<2>(km), rb.w & (int)byte_sign_mask<3>(km)));
-}
-
 // -DRADIAN_CHECKS: bounds checks of our own on every index the long way computes (arena, forwarding
 // table, candidate lists); a violation prints where and traps, which fails the launch.  compute-sanitizer
 // is closed on the build pool (profiles/r2_sanitizer_closed.txt); the test-suite is run once with this

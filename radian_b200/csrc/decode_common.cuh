@@ -71,6 +71,16 @@ __device__ __forceinline__ int4 lds_i4(unsigned addr)
     return v;
 }
 
+// max over the symbols c whose extension is a candidate of its own (bit 7 of byte c of km) of the high
+// word of the table value r_c; row = the four float64 of a beam's extend-context
+__device__ __forceinline__ int row_bound(const double *row, uint32_t km)
+{
+    const int4 ra = *reinterpret_cast<const int4 *>(row);      // r0 lo,hi r1 lo,hi
+    const int4 rb = *reinterpret_cast<const int4 *>(row + 2);  // r2, r3
+    return max(max(ra.y & (int)byte_sign_mask<0>(km), ra.w & (int)byte_sign_mask<1>(km)),
+               max(rb.y & (int)byte_sign_mask<2>(km), rb.w & (int)byte_sign_mask<3>(km)));
+}
+
 // Asynchronous global -> shared copies (LDGSTS): no register staging, completion awaited with
 // cp_async_wait_all() by the issuing thread right before the data is needed.
 template <int BYTES>

@@ -16,28 +16,50 @@
 
 namespace radian {
 
-constexpr int kWideWarps = 2;  // warps (reads) per CTA
+// -DRADIAN_WIDE_PROBE (diagnostic build, scripts/wide_probe.py): a lap timer per warp; RADIAN_LAP(ch)
+// charges the cycles since the previous mark to channel ch, totals over all reads in g_lap.
+#ifdef RADIAN_WIDE_PROBE
+__device__ unsigned long long g_lap[24];
+#define RADIAN_LAP(ch)                                                              \
+    do {                                                                            \
+        const long long now_ = clock64();                                           \
+        if (lane == 0) sm.lap[ch] += (unsigned long long)(now_ - lap_t);            \
+        lap_t = now_;                                                               \
+    } while (0)
+#else
+#define RADIAN_LAP(ch)
+#endif
+
+constexpr int kWideWarps = 1;  // warps (reads) per CTA: shared memory per read decides how many fit an SM,
+                               // and one-warp CTAs waste the least of it
 
 template <int BPL, bool LM, typename PT>
 struct __align__(16) WideSmem {
     static constexpr int NB = 32 * BPL;
-    static constexpr int REC = LM ? 18 : 10;  // doubles per frame, extended record of decode_common.cuh
+    static constexpr int REC = LM ? 14 : 6;   // doubles per frame, compact record of decode_common.cuh
     double rec[32 * REC];
     double row[LM ? NB * 4 : 4];      // RNA table row of every beam's extend-context (cp.async target)
     double ex[NB * 2];                // {pr_total, pr_blank} of every beam before the frame
+    double zero[2];                   // what a beam without a live parent merges with
+#ifdef RADIAN_WIDE_PROBE
+    unsigned long long lap[24];
+#endif
     unsigned long long key[5 * NB];   // candidate scores: [0,NB) copies by beam id, then extensions
-    unsigned long long sh[NB];        // staged: labeling hash of every beam
     uint32_t k32[5 * NB];             // high words of the candidate scores (incremental ranking)
     PT raw[32 * 5];                   // next tile of posterior rows, landed by cp.async
     uint32_t sctx[NB];                // staged: packed context
     int32_t slen[NB];                 // staged: labeling length
-    int32_t snode[NB];                // staged: arena node
     uint32_t kill[NB];                // byte c of word b: extension (b,c) merged into a live child's copy
     uint16_t pos[5 * NB];             // dict insertion position of the candidate
+    // Two staging arrays of the creation step share storage with arrays that are idle by then (shared
+    // memory per read decides how many reads an SM holds): the labeling hashes use the extensions' part
+    // of pos (read last by the exact ranking, rewritten by the next frame's candidate list), the
+    // arena nodes use kill (histogram of the ranking before, zeroed and rebuilt after the creation).
+    __device__ unsigned long long *sh() { return reinterpret_cast<unsigned long long *>(&pos[NB]); }
+    __device__ int32_t *snode() { return reinterpret_cast<int32_t *>(kill); }
     uint16_t src[5 * NB];             // beam*4+c of an extension candidate
     uint16_t rnk[5 * NB];             // rank of the candidate
     uint16_t newlist[NB];             // candidate indices of the new beams
-    uint16_t newbeam[NB];             // beam ids that received them
     uint16_t byrank[NB];              // beam id by rank
     uint16_t srank[NB];               // staged: rank of every beam
     uint8_t sgext[NB];                // staged: gate bit of every beam's extend-context
@@ -48,10 +70,11 @@ constexpr unsigned long long kHashEmpty = 0x243F6A8885A308D3ull;
 constexpr int kNoRmaxW = (int)0x80000000;
 
 template <int BPL, bool LM, typename PT, bool COUNT>
-__global__ void __launch_bounds__(kWideWarps * 32)
+__global__ void __launch_bounds__(kWideWarps * 32, BPL == 2 ? 15 : 8)
 decode_wide_kernel(const DecodeArgs a)
 {
     using SM = WideSmem<BPL, LM, PT>;
+    static_assert(offsetof(SM, pos) % 8 == 0 && (SM::NB * 2) % 8 == 0, "sh() must be 8-byte aligned");
     constexpr int NB = SM::NB;
     constexpr int REC = SM::REC;
     extern __shared__ __align__(16) unsigned char wide_smem_raw[];
@@ -77,6 +100,20 @@ decode_wide_kernel(const DecodeArgs a)
     bool tie_ok[BPL];  // a successor with exactly my score is still in the right place (later insertion position)
     int prep[BPL];  // 1 if the live parent (plane) ends in the same symbol as this beam
     int rmax[BPL];  // max high word of the unmerged entries of this beam's table row, or kNoRmaxW
+    bool rprov[BPL];  // this beam's table row is still in flight (its bound is the table-wide one, a.rcap)
+    // what a quiet frame needs besides the three scores, set by REFRESH after every frame that is not
+    // quiet (see decode.cu): where the copy emission of the beam is in a record (x, y), the score of
+    // the parent whose extension merges into it (or a zero), the high word of its successor, and
+    // whether that one has to be strictly smaller (q_inc = 1) or, for a pair whose order the long way
+    // has confirmed on all 64 bits although the high words agree, may be equal (0)
+    unsigned q_xa[BPL], q_ya[BPL], q_pa[BPL], q_ks[BPL];
+    uint32_t q_inc[BPL];
+    const unsigned a_rec = (unsigned)__cvta_generic_to_shared(&sm.rec[0]);
+    const unsigned a_ex = (unsigned)__cvta_generic_to_shared(&sm.ex[0]);
+    const unsigned a_k32 = (unsigned)__cvta_generic_to_shared(&sm.k32[0]);
+    const unsigned a_zero = (unsigned)__cvta_generic_to_shared(&sm.zero[0]);
+    if (lane < 2) sm.zero[lane] = 0.0;
+    unsigned c_lookup = 0, c_combine = 0;  // COUNT: table lookups / combined emissions of one quiet frame
 
     while (true) {
         // ------------------------------------------------------------ fetch a read
@@ -137,22 +174,90 @@ decode_wide_kernel(const DecodeArgs a)
             gext[s] = gcopy[s] = false;
             prep[s] = 0;
             rmax[s] = kNoRmaxW;
+            rprov[s] = false;
         }
         int first = 0, last_b = 0;  // beam ids of the best and the worst ranked beam
         int top = 1, old_top = 1, na = 1, status = 0;  // node 0 = the empty labeling
         long long kacc = 0;
         unsigned long long n_lookup = 0, n_combine = 0, n_tie = 0, n_diag = 0;  // n_diag: see include/radian_b200.h
+#ifdef RADIAN_WIDE_PROBE
+        if (lane < 24) sm.lap[lane] = 0;
+        long long lap_t = clock64();
+#endif
 
         __syncwarp();
         if (lane < T) prefetch_row(&sm.raw[lane * 5], rp, lane);
 
-        for (int t = 0; t < T && status == 0; ++t) {
+        // RESCALE by an exact power of two when the best beam has left [2^300, 2^900): back to 2^600.
+        // Checked once per tile and before every frame that is not quiet; in between, the quiet test
+        // refuses a frame in which the worst kept beam is not a normal number, and the long way
+        // reports RADIAN_READ_RANGE for a beam that underflows with non-zero factors: nothing is lost
+        // silently (see decode.cu).
+        auto rescale_check = [&]() {
+            int hi = 0;
+#pragma unroll
+            for (int s = 0; s < BPL; ++s) {
+                const int x = __shfl_sync(kFull, __double2hiint(ptot[s]), first & 31);
+                if ((first >> 5) == s) hi = x;
+            }
+            const int exb = (hi >> 20) & 0x7ff;
+            if ((unsigned)(exb - (1023 + 300)) >= 600u) {
+                const int k1 = exb == 0 ? 1000 : 1023 - exb;  // a subnormal best first comes up by 2^1000
+                const double s1 = __hiloint2double((1023 + k1) << 20, 0);
+                const double s2 = __hiloint2double((1023 + 600) << 20, 0);
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) {
+                    ptot[s] = __dmul_rn(__dmul_rn(ptot[s], s1), s2);
+                    pnb[s] = __dmul_rn(__dmul_rn(pnb[s], s1), s2);
+                    pb[s] = __dmul_rn(__dmul_rn(pb[s], s1), s2);
+                }
+                kacc -= k1 + 600;
+            }
+        };
+        // REFRESH: what the quiet frames use of a beam, after anything about the beams has changed
+        auto refresh = [&]() {
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < BPL; ++s)
+                sm.key[s * 32 + lane] = (unsigned long long)__double_as_longlong(ptot[s]);
+            __syncwarp();
+            unsigned cl = 0, cc = 0;
+#pragma unroll
+            for (int s = 0; s < BPL; ++s) {
+                const int b = s * 32 + lane;
+                const bool gc = LM && gcopy[s];
+                q_xa[s] = a_rec + (unsigned)((gc ? 6 + last[s] : last[s]) * 8);
+                q_ya[s] = a_rec + (unsigned)((gc ? 11 : 10) * 8);
+                q_pa[s] = (alive[s] && plane[s] >= 0) ? a_ex + (unsigned)((plane[s] * 2 + prep[s]) * 8) : a_zero;
+                q_ks[s] = a_k32 + (unsigned)(succ[s] * 4);
+                const bool has = alive[s] && succ[s] != b;
+                const unsigned long long mine = (unsigned long long)__double_as_longlong(ptot[s]);
+                const unsigned long long next = sm.key[succ[s]];
+                const bool hitie = has && (mine >> 32) == (next >> 32) && (mine > next || (mine == next && tie_ok[s]));
+                q_inc[s] = (has && !hitie) ? 1u : 0u;
+                if (LM && gext[s] && rmax[s] == kNoRmaxW)
+                    rmax[s] = rprov[s] ? a.rcap : row_bound(&sm.row[b * 4], km[s]);
+                if (COUNT && LM) {
+                    const bool lm_copy = alive[s] && len[s] >= L + 1;  // decode.py:157
+                    const bool lm_ext = alive[s] && len[s] >= L;       // decode.py:180
+                    cl += __popc(__ballot_sync(kFull, lm_copy)) + __popc(__ballot_sync(kFull, lm_ext));
+                    cc += __popc(__ballot_sync(kFull, lm_copy && gcopy[s])) + __popc(__ballot_sync(kFull, lm_ext && gext[s]));
+                }
+            }
+            c_lookup = cl;
+            c_combine = cc;
+            __syncwarp();
+        };
+        refresh();
+
+        int t = 0;
+        while (t < T && status == 0) {
             // -------------------------------------------------------- tile refill
             if ((t & 31) == 0) {
                 cp_async_wait_all();
                 __syncwarp();
                 int kf = 0;
-                if (t + lane < T) kf = make_record<LM, true, sizeof(PT) == 8>(&sm.raw[lane * 5], a.s_thr, &sm.rec[lane * REC]);
+                if (t + lane < T) kf = make_record<LM, true, sizeof(PT) == 8, true>(&sm.raw[lane * 5], a.s_thr, &sm.rec[lane * REC]);
                 __syncwarp();
                 if (t + 32 + lane < T) prefetch_row(&sm.raw[lane * 5], rp, t + 32 + lane);
                 if (sizeof(PT) == 8 && __any_sync(kFull, kf != 0)) {
@@ -161,8 +266,110 @@ decode_wide_kernel(const DecodeArgs a)
                     for (int o = 16; o > 0; o >>= 1) kf += __shfl_xor_sync(kFull, kf, o);
                     kacc -= kf;
                 }
+                rescale_check();
             }
 
+            // -------------------------------------------------------- QUIET frames
+            // The common case (decode.cu): the order of the copies holds, the beam is full and, by the
+            // integer bound on the high words (largest symbol of the frame, table bound of the beam),
+            // no extension can reach the worst copy.  Such a frame is three score updates per beam,
+            // two shared-memory exchanges (the parent's old score, the successor's new high word) and
+            // one vote; nothing else about the beams is touched.
+            RADIAN_LAP(13);
+            if (na >= bw) {
+                int it = t & 31;
+                const int tile0 = t - it;
+                const int nend = (T - tile0) < 32 ? (T - tile0) : 32;
+                const unsigned a_kw = a_k32 + (unsigned)(last_b * 4);
+#pragma unroll 1
+                for (; it < nend; ++it) {
+                    const unsigned ro = (unsigned)it * (unsigned)(REC * 8);
+                    const double P4 = lds_f64(a_rec + ro + 32);
+                    double g_ = 0.0;
+                    int4 gi = make_int4(0, 0, 0, 0);
+                    if (LM) {
+                        g_ = lds_f64(a_rec + ro + 40);
+                        gi = lds_i4(a_rec + ro + 96);   // {gate, hS, zP, zQ}, decode_common.cuh
+                    } else {
+                        gi.z = lds_i32(a_rec + ro + 40);
+                    }
+                    double nptot[BPL], npnb[BPL], npb[BPL], dl[BPL];
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) {
+                        // COPY (decode.py:150-175): (rcopy * gate + x) * y is P[last], or with the gate open
+                        // and a gated copy-context (r + p/S) * (S/2)
+                        dl[s] = lds_f64(q_xa[s] + ro);
+                        if (LM) dl[s] = __dmul_rn(__dadd_rn(__dmul_rn(rcopy[s], g_), dl[s]), lds_f64(q_ya[s] + ro));
+                        npnb[s] = __dmul_rn(pnb[s], dl[s]);
+                        npb[s] = __dmul_rn(ptot[s], P4);
+                        nptot[s] = __dadd_rn(npb[s], npnb[s]);
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a_ex + (unsigned)((s * 32 + lane) * 16)), "d"(ptot[s]),
+                                     "d"(pb[s])
+                                     : "memory");
+                    }
+                    __syncwarp();
+                    uint32_t kc[BPL];
+                    double pv[BPL];
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) pv[s] = lds_f64_volatile(q_pa[s]);
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) {
+                        // MERGE with the parent's extension by my last symbol
+                        const double v = __dmul_rn(pv[s], dl[s]);
+                        npnb[s] = __dadd_rn(npnb[s], v);
+                        nptot[s] = __dadd_rn(nptot[s], v);
+                        kc[s] = (uint32_t)__double2hiint(nptot[s]);
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_k32 + (unsigned)((s * 32 + lane) * 4)), "r"(kc[s]) : "memory");
+                    }
+                    __syncwarp();
+                    uint32_t kworst;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kworst) : "r"(a_kw) : "memory");
+                    bool quiet = kworst >= 0x00100000u;
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) {
+                        uint32_t ksucc;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ksucc) : "r"(q_ks[s]) : "memory");
+                        const int z = (LM && gext[s]) ? max(gi.w, rmax[s]) + gi.y : gi.z;
+                        quiet = quiet && kc[s] >= ksucc + q_inc[s] && __double2hiint(ptot[s]) + z < (int)kworst;
+                    }
+                    if (!__all_sync(kFull, quiet)) break;
+                    if (COUNT && LM) {
+                        n_lookup += c_lookup;
+                        if (gi.x != 0) {
+                            n_combine += c_combine;
+                            n_diag += 1ull << 32;
+                        }
+                    }
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) {
+                        ptot[s] = nptot[s];  // (a dead beam's new values are zero as well)
+                        pnb[s] = npnb[s];
+                        pb[s] = npb[s];
+                    }
+                }
+                t = tile0 + it;
+                RADIAN_LAP(0);
+                if (it == nend) continue;
+            }
+            bool need_ = false;
+            do {  // one frame the long way (a `break` leaves it with `status` set)
+            if (LM) {
+                // table bounds that were provisional (the row was in flight): the real ones now
+                bool pv = false;
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) pv = pv || (gext[s] && rprov[s]);
+                if (__any_sync(kFull, pv)) {
+                    cp_async_wait_all();
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s)
+                        if (gext[s] && rprov[s]) {
+                            rprov[s] = false;
+                            rmax[s] = kNoRmaxW;
+                        }
+                }
+            }
+
+            RADIAN_LAP(1);
             // -------------------------------------------------------- nursery collection
             if (top + NB > old_top + kNursery || top + NB > cap) {
                 // 1. mark the nursery nodes reachable from a live beam
@@ -216,32 +423,9 @@ decode_wide_kernel(const DecodeArgs a)
                 }
             }
 
-            // RESCALE by an exact power of two when the best beam has left [2^300, 2^900): back to
-            // 2^600 (checked every frame).  The quiet test refuses a frame in which the worst kept
-            // beam is not a normal number, and the long way reports RADIAN_READ_RANGE for a beam
-            // that underflows with non-zero factors: nothing is lost silently (see decode.cu).
-            {
-                int hi = 0;
-#pragma unroll
-                for (int s = 0; s < BPL; ++s) {
-                    const int x = __shfl_sync(kFull, __double2hiint(ptot[s]), first & 31);
-                    if ((first >> 5) == s) hi = x;
-                }
-                const int exb = (hi >> 20) & 0x7ff;
-                if ((unsigned)(exb - (1023 + 300)) >= 600u) {
-                    const int k1 = exb == 0 ? 1000 : 1023 - exb;  // a subnormal best first comes up by 2^1000
-                    const double s1 = __hiloint2double((1023 + k1) << 20, 0);
-                    const double s2 = __hiloint2double((1023 + 600) << 20, 0);
-#pragma unroll
-                    for (int s = 0; s < BPL; ++s) {
-                        ptot[s] = __dmul_rn(__dmul_rn(ptot[s], s1), s2);
-                        pnb[s] = __dmul_rn(__dmul_rn(pnb[s], s1), s2);
-                        pb[s] = __dmul_rn(__dmul_rn(pb[s], s1), s2);
-                    }
-                    kacc -= k1 + 600;
-                }
-            }
+            rescale_check();
 
+            RADIAN_LAP(2);
             // -------------------------------------------------------- one frame
             // (the structure of decode.cu's frame: copy, child-side merge, integer quiet test; the
             // extension scores are only computed when some extension may reach the beam)
@@ -251,7 +435,7 @@ decode_wide_kernel(const DecodeArgs a)
             bool fgate = false;
             int hS = 0;
             if (LM) {
-                const int2 gs = *reinterpret_cast<const int2 *>(reci + 32);
+                const int2 gs = *reinterpret_cast<const int2 *>(reci + 24);
                 fgate = gs.x != 0;
                 hS = gs.y;
             }
@@ -301,44 +485,11 @@ decode_wide_kernel(const DecodeArgs a)
                     ok = ok && (kcopy[s] > ks || (kcopy[s] == ks && tie_ok[s]));
                 }
             const unsigned long long kworst = sm.key[last_b];
-            {
-                // QUIET frame: order intact, beam full, and by the integer log bound of decode.cu no
-                // unmerged extension reaches the high word of the worst copy
-                const int hw = (int)(kworst >> 32);
-                bool quiet = ok && na >= bw && hw >= 0x00100000;
-#pragma unroll
-                for (int s = 0; s < BPL; ++s) {
-                    const int b = s * 32 + lane;
-                    const bool gated = LM && gext[s] && fgate;
-                    if (LM && gated && rmax[s] == kNoRmaxW) {
-                        cp_async_wait_all();  // the row gathered when this beam was created
-                        const int4 ra = *reinterpret_cast<const int4 *>(&sm.row[b * 4]);
-                        const int4 rb = *reinterpret_cast<const int4 *>(&sm.row[b * 4 + 2]);
-                        rmax[s] = max(max(ra.y & (int)byte_sign_mask<0>(km[s]), ra.w & (int)byte_sign_mask<1>(km[s])),
-                                      max(rb.y & (int)byte_sign_mask<2>(km[s]), rb.w & (int)byte_sign_mask<3>(km[s])));
-                    }
-                    const int4 hx = *reinterpret_cast<const int4 *>(reci + ((LM && gated) ? 28 : (LM ? 24 : 12)));
-                    int z = max(max(hx.x & (int)byte_sign_mask<0>(km[s]), hx.y & (int)byte_sign_mask<1>(km[s])),
-                                max(hx.z & (int)byte_sign_mask<2>(km[s]), hx.w & (int)byte_sign_mask<3>(km[s])));
-                    if (LM && gated) z = max(z, rmax[s]) + hS;
-                    // (the gated slack is folded into the record's hS word, decode_common.cuh)
-                    const int ub = __double2hiint(ptot[s]) + z + ((LM && gated) ? 0 : kSlackPlain);
-                    quiet = quiet && ub < hw;
-                }
-                if (COUNT && fgate) n_diag += 1ull << 32;
-                if (__all_sync(kFull, quiet)) {
-#pragma unroll
-                    for (int s = 0; s < BPL; ++s) {
-                        ptot[s] = nptot[s];  // (a dead beam's new values are zero as well)
-                        pnb[s] = npnb[s];
-                        pb[s] = npb[s];
-                    }
-                    continue;
-                }
-            }
+            if (COUNT && fgate) n_diag += 1ull << 32;
             if (COUNT) n_diag += 1;  // a frame that has to look at extensions
             const bool order_ok = __all_sync(kFull, ok);
 
+            RADIAN_LAP(3);
             // EXTEND (decode.py:177-201)
             unsigned long long ke[BPL][4];
             bool lost = false;  // see below
@@ -420,6 +571,8 @@ decode_wide_kernel(const DecodeArgs a)
                     anyc = anyc || comp[s][c];
                 }
             const bool need = !order_ok || __any_sync(kFull, anyc);
+            need_ = need;
+            RADIAN_LAP(4);
 
             if (!need) {
 #pragma unroll
@@ -461,6 +614,7 @@ decode_wide_kernel(const DecodeArgs a)
                     }
                 const int m = NB + n_ext;
                 __syncwarp();
+                RADIAN_LAP(5);
                 // ---- incremental ranks: a copy moves down from its rank among the copies by the
                 // number of extensions that outrank it, and an extension ranks behind the copies and
                 // extensions above it.  Counted on the high words; any equal pair of high words
@@ -499,44 +653,80 @@ decode_wide_kernel(const DecodeArgs a)
                 }
                 bool inc = copies_ok && n_ext <= 2 * NB;
                 if (inc) {
-                    int add[BPL];
+                    // The copies' high words in rank order are a descending array: an extension finds the
+                    // number of copies above it by bisection and counts the extensions above it four at
+                    // a time; a copy of rank r among the copies moves down by the number of extensions
+                    // that have at most r copies above them (a histogram and its prefix sums).
+                    uint32_t *const skey = sm.sctx;   // (staging array of the creation step: free here)
+                    uint32_t *const hist = sm.kill;   // (rebuilt after the creation step: free here)
 #pragma unroll
-                    for (int s = 0; s < BPL; ++s) add[s] = 0;
-                    bool tie = false;
-                    for (int j = 0; j < n_ext; ++j) {
-                        const uint32_t kj = sm.k32[NB + j];
-#pragma unroll
-                        for (int s = 0; s < BPL; ++s) {
-                            add[s] += kj > kc32[s];
-                            tie = tie || (alive[s] && kj == kc32[s]);
-                        }
+                    for (int s = 0; s < BPL; ++s) {
+                        if (alive[s]) skey[base[s]] = kc32[s];
+                        hist[s * 32 + lane] = 0u;
                     }
-                    const uint4 *kv = reinterpret_cast<const uint4 *>(sm.k32);
+                    if (lane < 4) sm.k32[m + lane] = 0u;  // the extensions' words padded to a multiple of four
+                    __syncwarp();
+                    const uint4 *ev = reinterpret_cast<const uint4 *>(&sm.k32[NB]);
+                    const int n4 = (n_ext + 3) >> 2;
+                    int rsum = 0;
+                    bool tie = false;
                     for (int ci = NB + lane; ci < m; ci += 32) {
                         const uint32_t k = sm.k32[ci];
-                        int cnt = 0;
-#pragma unroll 4
-                        for (int j4 = 0; j4 < NB / 4; ++j4) {
-                            const uint4 q = kv[j4];
-                            cnt += (q.x > k) + (q.y > k) + (q.z > k) + (q.w > k);
-                            tie = tie || q.x == k || q.y == k || q.z == k || q.w == k;
-                        }
-                        for (int j = 0; j < n_ext; ++j) {
-                            const uint32_t kj = sm.k32[NB + j];
-                            cnt += kj > k;
-                            tie = tie || (kj == k && NB + j != ci);
-                        }
-                        sm.rnk[ci] = (uint16_t)cnt;
-                    }
-                    if (__any_sync(kFull, tie)) {
-                        inc = false;
-                    } else {
+                        int c = 0;  // copies above: the largest c with skey[c - 1] > k
 #pragma unroll
-                        for (int s = 0; s < BPL; ++s)
-                            sm.rnk[s * 32 + lane] = alive[s] ? (uint16_t)(base[s] + add[s]) : (uint16_t)0xffff;
+                        for (int step = NB; step > 0; step >>= 1) {
+                            const int tt = c + step;
+                            const uint32_t v = skey[(tt < NB ? tt : NB) - 1];
+                            if (tt <= na && v > k) c = tt;
+                        }
+                        if (c < na) {
+                            tie = tie || skey[c] == k;  // a copy with my high word: the exact ranking decides
+                            atomicAdd(&hist[c], 1u);
+                        }
+                        int x = 0;
+                        for (int j = 0; j < n4; ++j) {
+                            const uint4 q = ev[j];
+                            x += (q.x > k) + (q.y > k) + (q.z > k) + (q.w > k);
+                        }
+                        sm.rnk[ci] = (uint16_t)(c + x);
+                        rsum += c + x;
                     }
                     __syncwarp();
+                    // inclusive prefix sums of the histogram, BPL consecutive entries per lane
+                    {
+                        uint32_t h[BPL];
+                        uint32_t run = 0;
+#pragma unroll
+                        for (int j = 0; j < BPL; ++j) {
+                            run += hist[lane * BPL + j];
+                            h[j] = run;
+                        }
+                        uint32_t incl = run;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t y = __shfl_up_sync(kFull, incl, o);
+                            if (lane >= o) incl += y;
+                        }
+                        const uint32_t excl = incl - run;
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < BPL; ++j) hist[lane * BPL + j] = excl + h[j];
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s) {
+                        const int r = alive[s] ? base[s] + (int)hist[base[s]] : 0xffff;
+                        sm.rnk[s * 32 + lane] = (uint16_t)r;
+                        rsum += alive[s] ? r : 0;
+                    }
+                    // two extensions with one high word leave the sum of all ranks short of mv(mv-1)/2
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(kFull, rsum, o);
+                    const int mv = na + n_ext;
+                    if (__any_sync(kFull, tie) || rsum != mv * (mv - 1) / 2) inc = false;
+                    __syncwarp();
                 }
+                RADIAN_LAP(6);
                 // ---- exact ranks: (float64 bits desc, dict insertion position asc)
                 if (!inc) {
                     bool near = false;  // two candidates within 2^-40 of each other (see decode.cu)
@@ -558,6 +748,7 @@ decode_wide_kernel(const DecodeArgs a)
                     if (COUNT) n_tie += __any_sync(kFull, near) ? 1 : 0;
                 }
                 __syncwarp();
+                RADIAN_LAP(7);
                 bool survive[BPL];
                 unsigned survb[BPL], evb[BPL];
                 int new_rank[BPL];
@@ -579,6 +770,7 @@ decode_wide_kernel(const DecodeArgs a)
                     n_new += __popc(bal);
                 }
 
+                RADIAN_LAP(8);
                 if (n_new > 0) {
                     // ---- stage what the new beams inherit from their parents
 #pragma unroll
@@ -586,8 +778,8 @@ decode_wide_kernel(const DecodeArgs a)
                         const int b = s * 32 + lane;
                         sm.sctx[b] = ctx[s];
                         sm.slen[b] = len[s];
-                        sm.snode[b] = node[s];
-                        sm.sh[b] = len[s] > 0 ? hash_step(hp[s], last[s]) : kHashEmpty;
+                        sm.snode()[b] = node[s];
+                        sm.sh()[b] = len[s] > 0 ? hash_step(hp[s], last[s]) : kHashEmpty;
                         sm.sgext[b] = (uint8_t)gext[s];
                         sm.slast[b] = (uint8_t)last[s];
                     }
@@ -640,7 +832,7 @@ decode_wide_kernel(const DecodeArgs a)
                             len[s] = sm.slen[pbm] + 1;
                             ctx[s] = (sm.sctx[pbm] << 2) | (uint32_t)c;
                             last[s] = c;
-                            hp[s] = sm.sh[pbm];
+                            hp[s] = sm.sh()[pbm];
                             unsigned sv = 0;
 #pragma unroll
                             for (int s2 = 0; s2 < BPL; ++s2)
@@ -648,13 +840,14 @@ decode_wide_kernel(const DecodeArgs a)
                             plane[s] = ((sv >> (pbm & 31)) & 1u) ? pbm : -1;
                             prep[s] = (c == (int)sm.slast[pbm]) ? 1 : 0;
                             alive[s] = true;
-                            arena[node[s]] = ((uint32_t)sm.snode[pbm] << 2) | (uint32_t)c;
-                            sm.newbeam[ford[s]] = (uint16_t)b;
+                            arena[node[s]] = ((uint32_t)sm.snode()[pbm] << 2) | (uint32_t)c;
                             if (LM) {
                                 gcopy[s] = sm.sgext[pbm] != 0;
                                 rcopy[s] = p_r[s];
                                 gext[s] = false;
+                                rprov[s] = false;
                                 if (len[s] >= L) {
+                                    rprov[s] = true;  // the row is in flight from here on
                                     const uint32_t ci = ctx[s] & ctx_mask;
                                     const uint32_t gwd = __ldg(a.gate + (ci >> 5));
                                     if (a.miss != nullptr && ((__ldg(a.miss + (ci >> 5)) >> (ci & 31u)) & 1u) &&
@@ -673,6 +866,7 @@ decode_wide_kernel(const DecodeArgs a)
                             ptot[s] = pnb[s] = pb[s] = 0.0;
                         }
                     }
+                    RADIAN_LAP(9);
                     top += n_new;
                     na = n_surv + n_new;
                     if (LM && a.miss != nullptr && t + 1 < T) {
@@ -696,22 +890,45 @@ decode_wide_kernel(const DecodeArgs a)
                     for (int s = 0; s < BPL; ++s)
                         if (take[s]) {
                             const int b = s * 32 + lane;
-                            sm.sh[b] = hash_step(hp[s], last[s]);
+                            sm.sh()[b] = hash_step(hp[s], last[s]);
                             sm.slen[b] = len[s];
                             sm.slast[b] = (uint8_t)last[s];
                         }
                     __syncwarp();
-                    for (int k = 0; k < n_new; ++k) {
-                        const int zb = (int)sm.newbeam[k];
-                        const unsigned long long zh = sm.sh[zb];
-                        const int zlen = sm.slen[zb];
+                    RADIAN_LAP(10);
+                    {
+                        // an open-addressing table of the new beams by labeling hash (4 NB slots in the
+                        // high-word array, whose ranking job is done); every orphan looks its parent up
+                        constexpr unsigned HM = 4 * NB - 1;
+                        uint32_t *const tab = sm.k32;
+#pragma unroll
+                        for (int j = 0; j < BPL; ++j)
+                            *reinterpret_cast<uint4 *>(&tab[(j * 32 + lane) * 4]) = make_uint4(~0u, ~0u, ~0u, ~0u);
+                        __syncwarp();
 #pragma unroll
                         for (int s = 0; s < BPL; ++s)
-                            if (survive[s] && plane[s] < 0 && len[s] == zlen + 1 && hp[s] == zh) {
-                                plane[s] = zb;
-                                prep[s] = ((int)sm.slast[zb] == last[s]) ? 1 : 0;
+                            if (take[s]) {
+                                unsigned i = (unsigned)(hash_step(hp[s], last[s]) >> 20) & HM;
+                                while (atomicCAS(&tab[i], ~0u, (uint32_t)(s * 32 + lane)) != ~0u) i = (i + 1) & HM;
+                            }
+                        __syncwarp();
+#pragma unroll
+                        for (int s = 0; s < BPL; ++s)
+                            if (survive[s] && plane[s] < 0 && len[s] > 0) {
+                                unsigned i = (unsigned)(hp[s] >> 20) & HM;
+                                while (true) {
+                                    const uint32_t zb = *(volatile uint32_t *)&tab[i];
+                                    if (zb == ~0u) break;
+                                    if (sm.sh()[zb] == hp[s] && sm.slen[zb] + 1 == len[s]) {
+                                        plane[s] = (int)zb;
+                                        prep[s] = ((int)sm.slast[zb] == last[s]) ? 1 : 0;
+                                        break;
+                                    }
+                                    i = (i + 1) & HM;
+                                }
                             }
                     }
+                    RADIAN_LAP(11);
                     // the beam set changed: refresh which extensions are merged into a live child
 #pragma unroll
                     for (int s = 0; s < BPL; ++s) sm.kill[s * 32 + lane] = 0u;
@@ -736,6 +953,7 @@ decode_wide_kernel(const DecodeArgs a)
                             rank[s] = new_rank[s];
                         }
                 }
+                RADIAN_LAP(12);
                 // successor of every beam, best and worst beam
                 __syncwarp();
 #pragma unroll
@@ -766,10 +984,22 @@ decode_wide_kernel(const DecodeArgs a)
                 for (int s = 0; s < BPL; ++s) tie_ok[s] = alive[s] && sm.pos[s * 32 + lane] < sm.pos[succ[s]];
                 __syncwarp();
             }
+            RADIAN_LAP(14);
+            } while (0);
+            ++t;
+            refresh();
+            RADIAN_LAP(15);
+#ifdef RADIAN_WIDE_PROBE
+            if (lane == 0) sm.lap[16 + (need_ ? 1 : 0)] += 1;
+#endif
         }
         cp_async_wait_all();
         __syncwarp();
 
+#ifdef RADIAN_WIDE_PROBE
+        __syncwarp();
+        if (lane < 24) atomicAdd(&g_lap[lane], sm.lap[lane]);
+#endif
         // ------------------------------------------------------------ end of read
         if (status == 0) {
             const long long seq_off = a.seq_offsets[read];
@@ -779,6 +1009,24 @@ decode_wide_kernel(const DecodeArgs a)
             for (int s = 0; s < BPL; ++s) {
                 const int x = __shfl_sync(kFull, succ[s], first & 31);
                 if ((first >> 5) == s) second = x;
+            }
+            {
+                // the best two beams, exactly: if they share their high word, their low words may have
+                // crossed since the order was last checked on all 64 bits (q_inc = 0, see REFRESH)
+                bool t1 = false;
+#pragma unroll
+                for (int s = 0; s < BPL; ++s) {
+                    sm.key[s * 32 + lane] = (unsigned long long)__double_as_longlong(ptot[s]);
+                    t1 = t1 || (s * 32 + lane == first && tie_ok[s]);
+                }
+                t1 = __any_sync(kFull, t1);
+                __syncwarp();
+                const unsigned long long p1 = sm.key[first], p2 = sm.key[second];
+                if (second != first && (p2 > p1 || (p2 == p1 && !t1))) {
+                    const int x = first;
+                    first = second;
+                    second = x;
+                }
             }
 #pragma unroll
             for (int s = 0; s < BPL; ++s) {
@@ -846,4 +1094,17 @@ int wide_pick(int beam_width, bool lm, bool f64, bool count, const void **kernel
     return 0;
 }
 
+#ifdef RADIAN_WIDE_PROBE
+}  // namespace radian
+extern "C" int radian_debug_wide_laps(unsigned long long *out, int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, radian::g_lap, sizeof(unsigned long long) * 24);
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[24] = {0};
+        e = cudaMemcpyToSymbol(radian::g_lap, z, sizeof(z));
+    }
+    return (int)e;
+}
+namespace radian {
+#endif
 }  // namespace radian
