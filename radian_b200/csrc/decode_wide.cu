@@ -684,6 +684,7 @@ decode_wide_kernel(const DecodeArgs a)
                             atomicAdd(&hist[c], 1u);
                         }
                         int x = 0;
+#pragma unroll 2  // (A/B on B200, profiles/r2_ab_wide2.log: +5.6 % at width 64, +2.6 % at 128)
                         for (int j = 0; j < n4; ++j) {
                             const uint4 q = ev[j];
                             x += (q.x > k) + (q.y > k) + (q.z > k) + (q.w > k);
