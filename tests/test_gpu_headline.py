@@ -206,7 +206,7 @@ def tie_read(T, seed, dtype):
     return p
 
 
-@pytest.mark.parametrize("bw", [2, 6, 16, 40])
+@pytest.mark.parametrize("bw", [2, 6, 16, 40, 100])
 def test_persistent_exact_ties(bw):
     """Kept beams with bit-equal scores over thousands of frames: ordered by the reference's dict
     insertion positions (stable sort, decode.py:35-39) in every frame, including the frames that only

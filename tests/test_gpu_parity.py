@@ -148,7 +148,8 @@ def test_table_entropies_match_reference_formula():
 @pytest.mark.parametrize("bw,L,f64", [(6, 0, False), (16, 6, True), (16, 11, True), (8, 4, False),
                                       (32, 5, True), (1, 3, True), (2, 0, True), (17, 2, False),
                                       (33, 0, False), (64, 6, True), (64, 11, False), (48, 3, True),
-                                      (100, 4, False), (128, 0, True), (65, 5, True)])
+                                      (100, 4, False), (128, 0, True), (65, 5, True),
+                                      (128, 7, False), (128, 5, True), (96, 9, False)])
 def test_batch_vs_oracle(bw, L, f64):
     """A mixed-length batch through one launch against the pinned C oracle, read by read."""
     from oracle import oracle
@@ -172,7 +173,7 @@ def test_batch_vs_oracle(bw, L, f64):
         assert int(cnt[i, 0]) == nl and int(cnt[i, 1]) == nc
 
 
-@pytest.mark.parametrize("bw,nb", [(16, (3000, 2500)), (64, (1500, 900))])
+@pytest.mark.parametrize("bw,nb", [(16, (3000, 2500)), (64, (1500, 900)), (128, (1200, 700))])
 def test_arena_compaction_long_read(bw, nb):
     """A read long enough to fill the back-pointer arena many times (compaction + flush)."""
     from oracle import oracle
