@@ -496,12 +496,12 @@ decode_wide_kernel(const DecodeArgs a)
             {
                 const double2 P01 = *reinterpret_cast<const double2 *>(rec);
                 const double2 P23 = *reinterpret_cast<const double2 *>(rec + 2);
+                if (LM && fgate) cp_async_wait_all();  // the rows of beams created in the frames before (uniform)
 #pragma unroll
                 for (int s = 0; s < BPL; ++s) {
                     const int b = s * 32 + lane;
                     double d0 = P01.x, d1 = P01.y, d2 = P23.x, d3 = P23.y;
                     if (LM && gext[s] && fgate) {
-                        cp_async_wait_all();
                         const double2 q01 = *reinterpret_cast<const double2 *>(rec + 6);
                         const double2 q23 = *reinterpret_cast<const double2 *>(rec + 8);
                         const double Sh = rec[11];
@@ -597,21 +597,35 @@ decode_wide_kernel(const DecodeArgs a)
                     }
                     sm.pos[s * 32 + lane] = alive[s] ? (uint16_t)pos_copy : kPosInvalid;
                 }
+                // (the order of the list is free: the insertion positions are explicit.  Every lane lists
+                // its own extensions one after the other, behind those of the lanes before it)
                 int n_ext = 0;
+                {
+                    int mine = 0;
 #pragma unroll
-                for (int s = 0; s < BPL; ++s)
+                    for (int s = 0; s < BPL; ++s)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const unsigned bal = __ballot_sync(kFull, comp[s][c]);
-                        if (comp[s][c]) {
-                            const int ci = NB + n_ext + __popc(bal & below);
-                            sm.key[ci] = ke[s][c];
-                            sm.k32[ci] = (uint32_t)(ke[s][c] >> 32);
-                            sm.pos[ci] = (uint16_t)(5 * rank[s] + 1 + c);
-                            sm.src[ci] = (uint16_t)((s * 32 + lane) * 4 + c);
-                        }
-                        n_ext += __popc(bal);
+                        for (int c = 0; c < 4; ++c) mine += comp[s][c] ? 1 : 0;
+                    int incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int y = __shfl_up_sync(kFull, incl, o);
+                        if (lane >= o) incl += y;
                     }
+                    n_ext = __shfl_sync(kFull, incl, 31);
+                    int ci = NB + incl - mine;
+#pragma unroll
+                    for (int s = 0; s < BPL; ++s)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (comp[s][c]) {
+                                sm.key[ci] = ke[s][c];
+                                sm.k32[ci] = (uint32_t)(ke[s][c] >> 32);
+                                sm.pos[ci] = (uint16_t)(5 * rank[s] + 1 + c);
+                                sm.src[ci] = (uint16_t)((s * 32 + lane) * 4 + c);
+                                ++ci;
+                            }
+                }
                 const int m = NB + n_ext;
                 __syncwarp();
                 RADIAN_LAP(5);
@@ -729,7 +743,42 @@ decode_wide_kernel(const DecodeArgs a)
                 }
                 RADIAN_LAP(6);
                 // ---- exact ranks: (float64 bits desc, dict insertion position asc)
-                if (!inc) {
+                if (!inc && !COUNT) {
+                    // counted on the high words, four per load; only a candidate that shares its high word
+                    // with another one (or is zero, like the dead copies) goes through all 64 bits
+                    const uint4 *kv = reinterpret_cast<const uint4 *>(sm.k32);
+                    const int m4 = m >> 2;
+                    for (int ci = lane; ci < m; ci += 32) {
+                        const uint16_t p = sm.pos[ci];
+                        int cnt = 0xffff;
+                        if (p != kPosInvalid) {
+                            const unsigned long long k = sm.key[ci];
+                            const uint32_t kh = (uint32_t)(k >> 32);
+                            int gt = 0, eq = 0;
+                            for (int j = 0; j < m4; ++j) {
+                                const uint4 q = kv[j];
+                                gt += (q.x > kh) + (q.y > kh) + (q.z > kh) + (q.w > kh);
+                                eq += (q.x == kh) + (q.y == kh) + (q.z == kh) + (q.w == kh);
+                            }
+                            for (int j = m4 * 4; j < m; ++j) {
+                                const uint32_t q = sm.k32[j];
+                                gt += q > kh;
+                                eq += q == kh;
+                            }
+                            cnt = gt;
+                            if (eq > 1) {
+                                cnt = 0;
+                                for (int j = 0; j < m; ++j) {
+                                    const uint16_t pj = sm.pos[j];
+                                    const unsigned long long kj = sm.key[j];
+                                    cnt += (pj != kPosInvalid) && (kj > k || (kj == k && pj < p));
+                                }
+                            }
+                        }
+                        sm.rnk[ci] = (uint16_t)cnt;
+                    }
+                } else if (!inc) {
+                    // (COUNT instantiation: every pair, which also finds the near ties it reports)
                     bool near = false;  // two candidates within 2^-40 of each other (see decode.cu)
                     for (int ci = lane; ci < m; ci += 32) {
                         const uint16_t p = sm.pos[ci];
