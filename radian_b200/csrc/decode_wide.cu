@@ -66,6 +66,13 @@ struct __align__(16) WideSmem {
     uint8_t slast[NB];                // staged: last symbol of every beam
 };
 
+// What the launch shape rests on (228 KB of shared memory per SM, 1 KB of it reserved per CTA): fifteen
+// one-warp CTAs per SM at BPL 2, eight at BPL 4 (float32 posteriors, model on).
+#ifndef RADIAN_WIDE_PROBE
+static_assert(15 * (sizeof(WideSmem<2, true, float>) + 1024) <= 233472, "BPL 2: fifteen reads per SM");
+static_assert(8 * (sizeof(WideSmem<4, true, float>) + 1024) <= 233472, "BPL 4: eight reads per SM");
+#endif
+
 constexpr unsigned long long kHashEmpty = 0x243F6A8885A308D3ull;
 constexpr int kNoRmaxW = (int)0x80000000;
 
