@@ -7,11 +7,17 @@
 // merge through a parent pointer, generational back-pointer arena -- laid out differently:
 //   * one warp owns a read; beam b lives in slot b/32 of lane b%32, so a lane carries BPL = 2 or 4
 //     beams in registers;
-//   * a frame first checks, with one compare per beam, that the rank order of the beams still
-//     holds (strictly) and that no extension reaches the worst beam; then only the scores are
-//     committed.  Otherwise all copies and the extensions that can reach the beam are ranked
-//     exactly: (float64 bit pattern desc, dict insertion position asc), the reference's stable
-//     sort over its insertion-ordered dict (decode.py:35-39, 145).
+//   * quiet frames (nine in ten: order intact, beam full, no extension can reach the worst copy by the
+//     integer bound on the high words) run in a loop of their own that only updates the scores:
+//     the parent's old score and the successor's new high word go through shared memory, one vote
+//     per frame; what the loop needs of a beam besides its scores is refreshed after every other frame;
+//   * every other frame computes the extensions; those that can reach the beam are ranked with the
+//     copies: (float64 bit pattern desc, dict insertion position asc), the reference's stable sort over
+//     its insertion-ordered dict (decode.py:35-39, 145) -- on high words by bisection in the copies'
+//     descending order plus a histogram, on all 64 bits wherever two high words agree;
+//   * shared memory per read decides how many reads an SM holds (15 at BPL 2, 8 at BPL 4): one-warp
+//     CTAs, compact records, staging arrays aliased onto arrays that are idle at that point.
+// Where the cycles of a read go: -DRADIAN_WIDE_PROBE, scripts/wide_probe.py, DESIGN.md 4.2.
 #include "decode_common.cuh"
 
 namespace radian {
